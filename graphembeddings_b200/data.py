@@ -1,0 +1,249 @@
+"""Host-side data preparation for the HolE path: file loaders, type->entity CSR, ranking
+filter CSR, and the seeded synthetic knowledge graphs BASELINE.json's configs name.
+
+Mirrors holE.py's ``init_data`` (holE.py:44-94) and ``init_inference_data``
+(holE.py:381-424).  File formats: SURVEY.md App. C.  Triple column order is
+(head, tail, relation) -- holE.py:80-81, 407.
+"""
+import json
+import os
+from collections import defaultdict
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# file loaders
+# --------------------------------------------------------------------------------------
+
+
+def load_triples(path):
+    """``head<TAB>tail<TAB>relation`` per line, decimal, no header (holE.py:76-81).
+
+    Returns int32 [T, 3].  An empty file gives shape (0, 3) (the 0712 subset's
+    triples-valid.txt is empty)."""
+    if os.path.getsize(path) == 0:
+        return np.zeros((0, 3), dtype=np.int32)
+    arr = np.loadtxt(path, dtype=np.int64, delimiter="\t", ndmin=2)
+    if arr.shape[1] != 3:
+        raise ValueError(f"{path}: expected 3 tab-separated columns, found {arr.shape[1]}")
+    if arr.min() < 0 or arr.max() > np.iinfo(np.int32).max:
+        raise ValueError(f"{path}: ids out of int32 range")
+    return arr.astype(np.int32)
+
+
+def count_lines(path):
+    """holE.py:52-53 count lines with ``sum(1 for line in open(f))``."""
+    with open(path, "rb") as f:
+        return sum(1 for _ in f)
+
+
+@dataclass
+class EntityMetadata:
+    """Parsed entity_metadata.tsv (holE.py:55-62, 390-399)."""
+    entity_count: int = 0                     # every row, relations included (holE.py:58)
+    id_to_type: dict = field(default_factory=dict)            # index -> type string
+    type_to_ids: dict = field(default_factory=lambda: defaultdict(list))
+    id_to_metadata: dict = field(default_factory=dict)        # index -> "id name"
+    mentions: dict = field(default_factory=dict)
+
+
+def load_entity_metadata(path):
+    """Header skipped; tab-separated.  The script unpacks 6 columns
+    (index, id, name, type, mentions, is_tail -- holE.py:59) but every committed file has 4
+    (Index, Id, Name, Type); both are accepted, ``mentions`` defaults to 0."""
+    md = EntityMetadata()
+    with open(path, "r") as f:
+        next(f)
+        for line in f:
+            cols = line.rstrip("\n").split("\t")
+            if len(cols) < 4:
+                raise ValueError(f"{path}: metadata row with {len(cols)} columns: {line!r}")
+            index = int(cols[0])
+            md.entity_count += 1
+            md.type_to_ids[cols[3]].append(index)
+            md.id_to_type[index] = cols[3]
+            md.id_to_metadata[index] = cols[1] + " " + cols[2]
+            md.mentions[index] = int(cols[4]) if len(cols) > 4 and cols[4] != "" else 0
+    return md
+
+
+# --------------------------------------------------------------------------------------
+# device-table builders (host side; the arrays are uploaded once)
+# --------------------------------------------------------------------------------------
+
+
+def type_arrays(md_or_types, n_rows=None):
+    """Dense ``type_of[N] int32`` plus the type-name list, from EntityMetadata (or pass a
+    ready type_of array through)."""
+    if isinstance(md_or_types, EntityMetadata):
+        md = md_or_types
+        names = list(md.type_to_ids.keys())
+        code = {n: i for i, n in enumerate(names)}
+        n = md.entity_count if n_rows is None else n_rows
+        type_of = np.zeros(n, dtype=np.int32)
+        for idx, t in md.id_to_type.items():
+            type_of[idx] = code[t]
+        return type_of, names
+    return np.asarray(md_or_types, dtype=np.int32), None
+
+
+def build_type_csr(type_of, n_types=None):
+    """type -> entity-id CSR (replaces holE.py's ``type_to_ids`` dict and its per-step
+    ``padded_size`` subsample, holE.py:343-347).  ids ascend within a type."""
+    type_of = np.asarray(type_of, dtype=np.int64)
+    T = int(type_of.max()) + 1 if n_types is None else int(n_types)
+    order = np.argsort(type_of, kind="stable")
+    counts = np.bincount(type_of, minlength=T)
+    off = np.zeros(T + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    return off, order.astype(np.int32)
+
+
+def build_filter_csr(queries, known_triples, side):
+    """Per-query list of known-true candidates to filter (holE.py:413-422, 454-461).
+
+    side "tail": for query (h, t, r) the known tails of (h, r); side "head": the known
+    heads of (t, r).  ``known_triples`` = train + valid triples [K, 3].  Returns
+    (off int64[Q+1], ids int32[.]) with ids ascending and de-duplicated per query."""
+    queries = np.asarray(queries, dtype=np.int64)
+    known = np.asarray(known_triples, dtype=np.int64).reshape(-1, 3)
+    if side == "tail":
+        kq, kv = known[:, 0], known[:, 1]
+        qq = queries[:, 0]
+    elif side == "head":
+        kq, kv = known[:, 1], known[:, 0]
+        qq = queries[:, 1]
+    else:
+        raise ValueError(side)
+    big = np.int64(1) << 32
+    kkey = kq * big + known[:, 2]
+    qkey = qq * big + queries[:, 2]
+    order = np.lexsort((kv, kkey))
+    kkey, kv = kkey[order], kv[order]
+    lo = np.searchsorted(kkey, qkey, side="left")
+    hi = np.searchsorted(kkey, qkey, side="right")
+    off = np.zeros(len(queries) + 1, dtype=np.int64)
+    chunks = []
+    for q in range(len(queries)):
+        ids = np.unique(kv[lo[q]:hi[q]])
+        chunks.append(ids)
+        off[q + 1] = off[q] + len(ids)
+    ids = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.int64)
+    return off, ids.astype(np.int32)
+
+
+# --------------------------------------------------------------------------------------
+# synthetic knowledge graphs
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class SyntheticKG:
+    n_relations: int
+    n_entities: int
+    dim: int
+    triples: np.ndarray        # int32 [T, 3] (h, t, r); entity ids offset by n_relations
+    type_of: np.ndarray        # int32 [N]; type 0 = relation rows
+    E: np.ndarray              # float32 [N, dim]
+
+    @property
+    def n_rows(self):
+        return self.n_relations + self.n_entities
+
+
+def xavier_stddev(n_rows, dim):
+    """holE.py:263-264 via xavier_initializer(uniform=False): sqrt(2.6 / (N + D))."""
+    return float(np.sqrt(2.6 / (n_rows + dim)))
+
+
+def init_embeddings(n_rows, dim, rng, trained_scale=False):
+    """Truncated-normal Xavier init (holE.py:263-264), or a "trained-scale" table whose row
+    norms are ~U(0.5, 1.5) so that the norm clip and its backward are exercised."""
+    sd = xavier_stddev(n_rows, dim)
+    x = rng.standard_normal((n_rows, dim), dtype=np.float32)
+    bad = np.abs(x) > 2.0
+    while bad.any():
+        x[bad] = rng.standard_normal(int(bad.sum()), dtype=np.float32)
+        bad = np.abs(x) > 2.0
+    if trained_scale:
+        norms = np.linalg.norm(x, axis=1, keepdims=True)
+        target = rng.uniform(0.5, 1.5, size=(n_rows, 1)).astype(np.float32)
+        return (x / norms * target).astype(np.float32)
+    return (x * np.float32(sd)).astype(np.float32)
+
+
+def _zipf_choice(rng, n, size, s=1.0):
+    w = 1.0 / np.arange(1, n + 1, dtype=np.float64) ** s
+    cdf = np.cumsum(w / w.sum())
+    return np.minimum(np.searchsorted(cdf, rng.random(size)), n - 1).astype(np.int64)
+
+
+def synthetic_kg(n_relations, n_entities, n_triples, n_types, dim, seed, zipf_entities=False,
+                 trained_scale=False, type_histogram=None, dominant_type_frac=None,
+                 with_embeddings=True):
+    """Seeded synthetic KG.  Rows 0..n_relations-1 are relations (type 0), entity rows
+    follow (surprise 3).  Relations ~ Zipf(1); entities uniform or
+    Zipf(1) (duplicate-index stress)."""
+    rng = np.random.default_rng(seed)
+    N = n_relations + n_entities
+    if type_histogram is not None:
+        hist = np.asarray(type_histogram, dtype=np.int64)
+        assert hist.sum() == n_entities
+        ent_type = np.repeat(np.arange(1, len(hist) + 1), hist)
+        rng.shuffle(ent_type)
+    elif dominant_type_frac is not None:
+        p = np.full(n_types, (1.0 - dominant_type_frac) / max(n_types - 1, 1))
+        p[0] = dominant_type_frac
+        ent_type = 1 + rng.choice(n_types, size=n_entities, p=p)
+    else:
+        ent_type = 1 + rng.integers(0, n_types, size=n_entities)
+    type_of = np.concatenate([np.zeros(n_relations, dtype=np.int64), ent_type]).astype(np.int32)
+    r = _zipf_choice(rng, n_relations, n_triples)
+    if zipf_entities:
+        perm = rng.permutation(n_entities)
+        h = perm[_zipf_choice(rng, n_entities, n_triples)]
+        t = perm[_zipf_choice(rng, n_entities, n_triples)]
+    else:
+        h = rng.integers(0, n_entities, size=n_triples)
+        t = rng.integers(0, n_entities, size=n_triples)
+    triples = np.stack([h + n_relations, t + n_relations, r], axis=1).astype(np.int32)
+    E = init_embeddings(N, dim, rng, trained_scale) if with_embeddings else None
+    return SyntheticKG(n_relations, n_entities, dim, triples, type_of, E)
+
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       "tests", "golden")
+
+
+def fb15k_type_histogram():
+    """The 815-class entity type histogram of the real FB15k metadata (372 singletons),
+    committed as tests/golden/fb15k_types.json by tests/golden/make_golden.py."""
+    with open(os.path.join(_GOLDEN, "fb15k_types.json")) as f:
+        return json.load(f)["entity_type_histogram"]
+
+
+#: BASELINE.json configs -> generator arguments (seeds 20170903+k)
+CONFIGS = {
+    "fb15k_d150": dict(n_relations=1345, n_entities=14951, n_triples=483142, n_types=815,
+                       dim=150, seed=20170903),
+    "diffbot_d256": dict(n_relations=14, n_entities=1200000, n_triples=30000000, n_types=12,
+                         dim=256, seed=20170904, dominant_type_frac=0.99),
+    "rank_fb15k_d150": dict(n_relations=1345, n_entities=14951, n_triples=59071, n_types=815,
+                            dim=150, seed=20170905),
+    "rank_diffbot_d256": dict(n_relations=14, n_entities=1200000, n_triples=100000,
+                              n_types=12, dim=256, seed=20170906, dominant_type_frac=0.99),
+    "sharded_d512": dict(n_relations=32, n_entities=20000000, n_triples=500000000,
+                         n_types=12, dim=512, seed=20170907, dominant_type_frac=0.99),
+}
+
+
+def make_config(name, n_triples=None, **overrides):
+    """Instantiate one of BASELINE.json's configs (optionally with fewer triples)."""
+    kw = dict(CONFIGS[name])
+    if n_triples is not None:
+        kw["n_triples"] = n_triples
+    kw.update(overrides)
+    if name in ("fb15k_d150", "rank_fb15k_d150") and "type_histogram" not in kw:
+        kw["type_histogram"] = fb15k_type_histogram()
+    return synthetic_kg(**kw)
