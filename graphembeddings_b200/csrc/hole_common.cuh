@@ -1,0 +1,122 @@
+// Shared declarations for libhole_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/hole_b200.h"
+
+// ---------------------------------------------------------------------------------------
+// error handling + launch accounting
+// ---------------------------------------------------------------------------------------
+extern thread_local std::string g_hole_err;
+extern thread_local int64_t g_hole_launches;
+
+int hole_set_error(int code, const char* fmt, ...);
+
+#define HOLE_CUDA_TRY(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return hole_set_error(HOLE_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,  \
+                            cudaGetErrorString(_e));                                     \
+  } while (0)
+
+#define HOLE_CHECK_ARG(cond)                                                             \
+  do {                                                                                   \
+    if (!(cond)) return hole_set_error(HOLE_ERR_ARG, "%s: bad argument: %s", __func__, #cond); \
+  } while (0)
+
+// Count a kernel launch and surface launch-configuration errors immediately.
+#define HOLE_LAUNCHED()                                                                  \
+  do {                                                                                   \
+    ++g_hole_launches;                                                                   \
+    HOLE_CUDA_TRY(cudaGetLastError());                                                   \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+struct hole_rank_ws;   // hole_rank.cu
+
+struct hole_ctx {
+  int device = 0;
+  int64_t n_rows = 0;
+  int dim = 0;         // embedding_dim (even)
+  int H = 0;           // dim / 2
+  int nvec = 0;        // float4s per (padded) half = round_up(H, 4) / 4
+  int row_stride = 0;  // floats per device row = 8 * nvec
+  int gs = 0, v = 0;   // lanes per row and float4s per lane per half (kernel variant)
+  int sm_count = 0;
+  int key_bits = 0;    // bits needed for a row id
+
+  // ---- training workspace (grown on demand; owned by the context)
+  int64_t cap_B = 0, cap_S = 0;
+  float* G = nullptr;            // [4B, row_stride] staged gradient rows of ONE step
+  uint32_t* keysA = nullptr;     // [S][4B] sort ping
+  uint32_t* keysB = nullptr;     // [S][4B] sort pong
+  uint32_t* valsA = nullptr;
+  uint32_t* valsB = nullptr;
+  uint32_t* sstart = nullptr;    // [S][4B] segment start (sorted index) of each sorted entry
+  uint32_t* slen = nullptr;      // [S][4B] segment length, valid at segment starts
+  int* counters = nullptr;       // [LEVELS][4B] tree-combine tickets (self-resetting)
+  int32_t* neg = nullptr;        // [S*B] corrupt entity per triple
+  float* loss = nullptr;         // [S*B] scratch when the caller passes no loss_out
+  float* loss_sum = nullptr;     // [S]
+  int32_t* triples_stage[2] = {nullptr, nullptr};  // device staging for the host-buffer path
+  int64_t cap_stage = 0;
+  float* loss_sum_pinned = nullptr;   // pinned host mirror of loss sums (e2e path)
+  int64_t cap_pinned = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+
+  hole_rank_ws* rank = nullptr;
+};
+
+constexpr int HOLE_TREE_C = 16;      // fan-in of the deterministic gradient combine tree
+constexpr int HOLE_TREE_LEVELS = 6;  // 16^6 > any 4B
+
+int hole_ws_reserve(hole_ctx* ctx, int64_t B, int64_t S);
+void hole_rank_ws_free(hole_ctx* ctx);
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (must match oracle/philox.py bit for bit)
+// ---------------------------------------------------------------------------------------
+#define HOLE_STREAM_SIDE   0x5EED0001u
+#define HOLE_STREAM_ENTITY 0x5EED0002u
+
+__host__ __device__ inline void hole_philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c[0];
+    uint64_t p1 = (uint64_t)M1 * c[2];
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += W0; k1 += W1;
+  }
+}
+
+__host__ __device__ inline int hole_side_coin(uint64_t seed, uint64_t step) {
+  uint32_t c[4] = {(uint32_t)step, (uint32_t)(step >> 32), 0u, HOLE_STREAM_SIDE};
+  hole_philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return (int)(c[0] & 1u);
+}
+
+// floor(r64 * cnt / 2^64), cnt < 2^32
+__host__ __device__ inline uint32_t hole_mulhi64_u32(uint32_t r_lo, uint32_t r_hi, uint32_t cnt) {
+  uint64_t lo = (uint64_t)r_lo * cnt;
+  uint64_t hi = (uint64_t)r_hi * cnt;
+  return (uint32_t)((hi + (lo >> 32)) >> 32);
+}
+
+__host__ __device__ inline uint32_t hole_entity_draw(uint64_t seed, uint64_t step, uint32_t index,
+                                                     uint32_t cnt) {
+  uint32_t c[4] = {index, (uint32_t)step, (uint32_t)(step >> 32), HOLE_STREAM_ENTITY};
+  hole_philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return hole_mulhi64_u32(c[0], c[1], cnt);
+}

@@ -1,0 +1,200 @@
+"""Device engine: owns the embedding table in HBM and calls libhole_b200 through ctypes.
+
+PyTorch is plumbing here (device memory, streams, torch.distributed); every numerical
+operation is a kernel of libhole_b200.so.  Method names follow the holE.py functions they
+replace (corrupt_batch holE.py:152, evaluate_triples holE.py:179, evaluate_batch
+holE.py:205 + minimize holE.py:296, eval_link_prediction holE.py:427).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import HOLE_RANK_BF16, HOLE_RANK_BF16X3, HOLE_SIDE_HEAD, HOLE_SIDE_TAIL, HoleError, check
+
+__all__ = ["HoleEngine", "HoleError", "inverse_time_decay", "HOLE_SIDE_TAIL", "HOLE_SIDE_HEAD",
+           "HOLE_RANK_BF16", "HOLE_RANK_BF16X3"]
+
+
+def inverse_time_decay(lr0, step, decay_steps, decay_rate):
+    """tf.train.inverse_time_decay evaluated in fp32 (holE.py:292-294; App. B)."""
+    f = np.float32
+    return f(lr0) / (f(1.0) + f(decay_rate) * (f(step) / f(decay_steps)))
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class HoleEngine:
+    """One GPU's share of the HolE model: the shared relation+entity table
+    (holE.py:263-264) in the padded device layout, plus the device-resident type tables
+    that replace holE.py's two MutableHashTables (holE.py:267-277)."""
+
+    def __init__(self, n_rows, dim, device=0):
+        if not torch.cuda.is_available():
+            raise HoleError("no CUDA device: libhole_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        self.n_rows, self.dim = int(n_rows), int(dim)
+        stride = self.lib.hole_row_stride(self.dim)
+        if stride < 0:
+            raise HoleError(f"embedding_dim must be a positive even number, got {dim}")
+        self.row_stride = stride
+        h = C.c_void_p()
+        check(self.lib.hole_ctx_create(C.byref(h), device, self.n_rows, self.dim))
+        self._ctx = h
+        self.table = None
+        self.type_of = self.csr_off = self.csr_ids = None
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.hole_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ table
+    def set_embeddings(self, E):
+        """E: [N, dim] float32 (numpy or torch, checkpoint layout [Re | Im])."""
+        E = torch.as_tensor(E, dtype=torch.float32)
+        assert E.shape == (self.n_rows, self.dim), E.shape
+        src = E.to(self.device).contiguous()
+        if self.table is None:
+            self.table = torch.empty((self.n_rows, self.row_stride), dtype=torch.float32,
+                                     device=self.device)
+        check(self.lib.hole_pack_rows(self._ctx, _ptr(src), _ptr(self.table), self.n_rows, _stream()))
+        torch.cuda.current_stream().synchronize()   # src may be freed by the caller
+        return self
+
+    def embeddings(self):
+        """Current table as a [N, dim] float32 CUDA tensor (checkpoint layout)."""
+        out = torch.empty((self.n_rows, self.dim), dtype=torch.float32, device=self.device)
+        check(self.lib.hole_unpack_rows(self._ctx, _ptr(self.table), _ptr(out), self.n_rows, _stream()))
+        return out
+
+    def set_types(self, type_of, csr_off, csr_ids):
+        """Device-resident type -> entity CSR (replaces holE.py:267-277, 343-347)."""
+        self.type_of = torch.as_tensor(np.asarray(type_of), dtype=torch.int32).to(self.device)
+        self.csr_off = torch.as_tensor(np.asarray(csr_off), dtype=torch.int64).to(self.device)
+        self.csr_ids = torch.as_tensor(np.asarray(csr_ids), dtype=torch.int32).to(self.device)
+        return self
+
+    def _triples(self, triples):
+        t = torch.as_tensor(triples)
+        if t.dtype != torch.int32:
+            t = t.to(torch.int32)
+        t = t.to(self.device).contiguous()
+        assert t.dim() == 2 and t.shape[1] == 3, t.shape
+        return t
+
+    # ------------------------------------------------------------------ hot path
+    def corrupt_batch(self, triples, seed, step):
+        """holE.py:152 corrupt_batch -> (side, neg_ent int32[B] on device)."""
+        t = self._triples(triples)
+        B = t.shape[0]
+        neg = torch.empty(B, dtype=torch.int32, device=self.device)
+        side = C.c_int(0)
+        check(self.lib.hole_corrupt(self._ctx, _ptr(t), B, _ptr(self.type_of), _ptr(self.csr_off),
+                                    _ptr(self.csr_ids), seed, step, None, _ptr(neg),
+                                    C.byref(side), _stream()))
+        return int(side.value), neg
+
+    def evaluate_triples(self, triples):
+        """holE.py:179 evaluate_triples -> sigma(score) float32[B] on device."""
+        t = self._triples(triples)
+        out = torch.empty(t.shape[0], dtype=torch.float32, device=self.device)
+        check(self.lib.hole_score(self._ctx, _ptr(self.table), _ptr(t), t.shape[0], _ptr(out), _stream()))
+        return out
+
+    def train_step(self, pos, neg_ent, side, margin, lr, return_sigma=False):
+        """One step: evaluate_batch hinge branch (holE.py:222-234) + minimize (holE.py:296),
+        with caller-supplied corruption.  Returns loss float32[B] (and sigma+/-)."""
+        p = self._triples(pos)
+        B = p.shape[0]
+        n = torch.as_tensor(neg_ent).to(torch.int32).to(self.device).contiguous()
+        loss = torch.empty(B, dtype=torch.float32, device=self.device)
+        sig = torch.empty(2 * B, dtype=torch.float32, device=self.device) if return_sigma else None
+        check(self.lib.hole_train_step(self._ctx, _ptr(self.table), _ptr(p), _ptr(n), int(side), B,
+                                       float(margin), float(lr), _ptr(loss), _ptr(sig), _stream()))
+        if return_sigma:
+            return loss, sig[:B], sig[B:]
+        return loss
+
+    def train_steps(self, triples, batch_size, seed, first_step, margin, lrs, want_loss=False):
+        """n_steps = len(triples) // batch_size consecutive steps on device-resident triples
+        (the loop body holE.py:340-362).  Returns per-step loss sums (device float32)."""
+        t = self._triples(triples)
+        n_steps = t.shape[0] // batch_size
+        lrs = np.ascontiguousarray(np.asarray(lrs, dtype=np.float32))
+        assert len(lrs) >= n_steps
+        sums = torch.empty(n_steps, dtype=torch.float32, device=self.device)
+        loss = (torch.empty(n_steps * batch_size, dtype=torch.float32, device=self.device)
+                if want_loss else None)
+        check(self.lib.hole_train_steps(self._ctx, _ptr(self.table), _ptr(t), batch_size, n_steps,
+                                        _ptr(self.type_of), _ptr(self.csr_off), _ptr(self.csr_ids),
+                                        seed, first_step, float(margin),
+                                        lrs.ctypes.data_as(C.c_void_p), _ptr(loss), _ptr(sums),
+                                        _stream()))
+        return (sums, loss) if want_loss else sums
+
+    def train_steps_host(self, triples_host, batch_size, seed, first_step, margin, lrs):
+        """Same from a HOST int32 [n,3] array (numpy or pinned torch tensor); host<->device
+        copies happen inside the call.  Returns per-step loss sums as a numpy array."""
+        if isinstance(triples_host, torch.Tensor):
+            assert triples_host.device.type == "cpu" and triples_host.dtype == torch.int32
+            assert triples_host.is_contiguous()
+            n, ptr = triples_host.shape[0], C.c_void_p(triples_host.data_ptr())
+        else:
+            triples_host = np.ascontiguousarray(triples_host, dtype=np.int32)
+            n, ptr = triples_host.shape[0], triples_host.ctypes.data_as(C.c_void_p)
+        n_steps = n // batch_size
+        lrs = np.ascontiguousarray(np.asarray(lrs, dtype=np.float32))
+        out = np.empty(n_steps, dtype=np.float32)
+        check(self.lib.hole_train_steps_host(self._ctx, _ptr(self.table), ptr, batch_size, n_steps,
+                                             _ptr(self.type_of), _ptr(self.csr_off),
+                                             _ptr(self.csr_ids), seed, first_step, float(margin),
+                                             lrs.ctypes.data_as(C.c_void_p),
+                                             out.ctypes.data_as(C.c_void_p), _stream()))
+        return out
+
+    # ------------------------------------------------------------------ ranking
+    def rank(self, queries, side, ent_begin, ent_end, filter_off=None, filter_ids=None,
+             precision=HOLE_RANK_BF16, true_score=None, compute_true=True,
+             raw_before=None, filt_before=None):
+        """All-candidate ranking of queries [Q,3] over candidate rows [ent_begin, ent_end)
+        (eval_link_prediction holE.py:427-469 as a tensor-core contraction).  Returns
+        (raw_before int32[Q], filt_before int32[Q], true_score float32[Q]); rank = 1 + count.
+        Counts are accumulated into raw_before / filt_before when given (candidate shards)."""
+        q = self._triples(queries)
+        Q = q.shape[0]
+        if raw_before is None:
+            raw_before = torch.zeros(Q, dtype=torch.int32, device=self.device)
+        if filt_before is None:
+            filt_before = torch.zeros(Q, dtype=torch.int32, device=self.device)
+        if true_score is None:
+            true_score = torch.zeros(Q, dtype=torch.float32, device=self.device)
+        fo = fi = None
+        if filter_off is not None:
+            fo = torch.as_tensor(filter_off).to(torch.int64).to(self.device).contiguous()
+            fi = torch.as_tensor(filter_ids).to(torch.int32).to(self.device).contiguous()
+        check(self.lib.hole_rank(self._ctx, _ptr(self.table), int(ent_begin), int(ent_end), _ptr(q),
+                                 Q, int(side), int(precision), _ptr(fo), _ptr(fi), _ptr(true_score),
+                                 1 if compute_true else 0, _ptr(raw_before), _ptr(filt_before),
+                                 _stream()))
+        return raw_before, filt_before, true_score
+
+    def launch_count(self):
+        return int(self.lib.hole_launch_count())
+
+    def reset_launch_count(self):
+        self.lib.hole_launch_count_reset()

@@ -1,0 +1,155 @@
+/* hole_b200.h -- C ABI of the B200-native HolE hot path (libhole_b200.so).
+ *
+ * Drop-in boundary for holE.py's training step and link-prediction ranking
+ * (greysun/GraphEmbeddings).  The reference has no FFI around this path (it is inline
+ * TensorFlow graph code); each entry point below names the holE.py seam it replaces, and
+ * the calling convention follows the repository's only C-ABI precedent, init.cpp + ctypes
+ * (init.cpp:47,129-142,223-246; transE.py:95-112): extern "C", plain ints and raw
+ * caller-owned buffers.  Two departures from that precedent, both deliberate:
+ *   - every call returns int (0 = ok, negative = error) and hole_last_error() gives a
+ *     thread-local message (init.cpp reports nothing, e.g. unchecked fopen at init.cpp:53);
+ *   - no process-global state (init.cpp:145-150 keeps a global, racy RNG): everything
+ *     lives in an opaque hole_ctx, and the sampler is counter-based.
+ *
+ * Unless a parameter is marked [host], every pointer is a DEVICE pointer owned by the
+ * caller (e.g. a torch tensor's data_ptr()).  Every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream) unless it says otherwise.
+ * There is no CPU fallback: every entry point fails with HOLE_ERR_CUDA when no sm_100
+ * device is present.
+ *
+ * Layouts
+ *   triples  int32 [B,3], columns (head, tail, relation)            -- holE.py:80-81
+ *   table    float32 [N, row_stride]; a row is [Re(0..H-1) pad | Im(0..H-1) pad] with
+ *            H = dim/2 and each half zero-padded to a multiple of 4 floats, so that
+ *            row_stride = hole_row_stride(dim) and every half starts 16-byte aligned.
+ *            hole_pack_rows / hole_unpack_rows convert from/to the checkpoint layout
+ *            float32 [N, dim] = [Re | Im] (holE.py:164-165).
+ */
+#ifndef HOLE_B200_H
+#define HOLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hole_ctx hole_ctx;
+
+#if defined(__GNUC__)
+#define HOLE_API __attribute__((visibility("default")))
+#else
+#define HOLE_API
+#endif
+
+#define HOLE_OK            0
+#define HOLE_ERR_ARG      (-1)   /* bad argument (odd dim, negative size, null pointer) */
+#define HOLE_ERR_CUDA     (-2)   /* CUDA runtime/driver error, or no sm_100 device      */
+#define HOLE_ERR_ALLOC    (-3)   /* workspace allocation failed                          */
+#define HOLE_ERR_UNSUPPORTED (-4)/* shape outside what the kernels are built for         */
+
+#define HOLE_SIDE_TAIL 0         /* corrupt / rank tails */
+#define HOLE_SIDE_HEAD 1         /* corrupt / rank heads */
+
+/* Operand precision of the tensor-core ranking contraction. */
+#define HOLE_RANK_BF16   0       /* bf16 operands, fp32 accumulate                      */
+#define HOLE_RANK_BF16X3 1       /* split-bf16 (hi*hi + hi*lo + lo*hi), ~fp32 accuracy  */
+
+/* ABI version of this header; hole_abi_version() returns the library's. */
+#define HOLE_ABI_VERSION 1
+HOLE_API int hole_abi_version(void);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+HOLE_API const char* hole_last_error(void);
+
+/* floats per device row for an (even) embedding_dim: 2 * round_up(dim/2, 4). */
+HOLE_API int hole_row_stride(int dim);
+
+/* Create / destroy a context bound to CUDA device `device` for a table of n_rows x dim
+ * (holE.py:263-264: one shared table for relations and entities).  Synchronous. */
+HOLE_API int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int dim);
+HOLE_API int hole_ctx_destroy(hole_ctx* ctx);
+
+/* Checkpoint layout [n, dim] <-> device layout [n, row_stride]. */
+HOLE_API int hole_pack_rows(hole_ctx* ctx, const float* src_nd, float* dst_padded, int64_t n, void* stream);
+HOLE_API int hole_unpack_rows(hole_ctx* ctx, const float* src_padded, float* dst_nd, int64_t n, void* stream);
+
+/* ---- corruption: replaces corrupt_batch (holE.py:97-158) and the per-step host
+ * subsample + table insert (holE.py:343-347).
+ * One Philox coin per (seed, step) picks the side for the whole batch (holE.py:137-140);
+ * triple i's replacement is csr_ids[csr_off[ty] + mulhi64(philox(seed, step, i), cnt[ty])]
+ * with ty = type_of[replaced entity].  The stream is specified in oracle/philox.py.
+ *   side_out  int32[1] (may be NULL)   neg_out  int32[B]
+ * Returns the side also through *side_host [host] when non-NULL (it depends on
+ * (seed, step) only and is computed on the host). */
+HOLE_API int hole_corrupt(hole_ctx* ctx, const int32_t* triples, int64_t B,
+                 const int32_t* type_of, const int64_t* csr_off, const int32_t* csr_ids,
+                 uint64_t seed, uint64_t step,
+                 int32_t* side_out, int32_t* neg_out, int* side_host, void* stream);
+
+/* ---- forward: replaces evaluate_triples (holE.py:179-202): out_sigma[i] =
+ * sigmoid(sum_k Re(h_k * r_k * conj(t_k))) on norm-clipped rows (holE.py:161-168). */
+HOLE_API int hole_score(hole_ctx* ctx, const float* table, const int32_t* triples, int64_t B,
+               float* out_sigma, void* stream);
+
+/* ---- one training step: replaces evaluate_batch's hinge branch (holE.py:222-234) plus
+ * GradientDescentOptimizer.minimize (holE.py:296) -- forward, backward and the sparse
+ * update table[idx] -= lr * g with duplicates accumulated in a fixed order.
+ *   neg_ent int32[B]: replacement entity per triple; side: HOLE_SIDE_*.
+ *   loss_out float32[B] (hinge per triple); sigma_out float32[2B] or NULL
+ *   (sigma+ then sigma-, the tensors holE.py:200 summarises). */
+HOLE_API int hole_train_step(hole_ctx* ctx, float* table, const int32_t* pos, const int32_t* neg_ent,
+                    int side, int64_t B, float margin, float lr,
+                    float* loss_out, float* sigma_out, void* stream);
+
+/* ---- the training loop body for n_steps consecutive batches: replaces
+ * `for batch in range(1, batch_count): sess.run([optimizer])` (holE.py:340-362) without
+ * returning to the host between steps.  Step k uses triples[k*B .. (k+1)*B), draws its
+ * corruption with (seed, first_step + k) and learning rate lr[k] [host, float32[n_steps]]
+ * (the caller evaluates inverse_time_decay, holE.py:292-294).
+ *   loss_out float32[n_steps*B] or NULL; loss_sum_out float32[n_steps] or NULL. */
+HOLE_API int hole_train_steps(hole_ctx* ctx, float* table, const int32_t* triples, int64_t B,
+                     int64_t n_steps, const int32_t* type_of, const int64_t* csr_off,
+                     const int32_t* csr_ids, uint64_t seed, uint64_t first_step,
+                     float margin, const float* lr, float* loss_out, float* loss_sum_out,
+                     void* stream);
+
+/* Same, end to end from HOST buffers: triples_host [host] int32[n_steps*B,3] (pinned or
+ * pageable) is copied to the device in chunks overlapped with compute, and the per-step
+ * loss sums are copied back to loss_sum_host [host] float32[n_steps].  Blocks until the
+ * losses are on the host.  This is the call bench.py times for its "e2e" figure. */
+HOLE_API int hole_train_steps_host(hole_ctx* ctx, float* table, const int32_t* triples_host, int64_t B,
+                          int64_t n_steps, const int32_t* type_of, const int64_t* csr_off,
+                          const int32_t* csr_ids, uint64_t seed, uint64_t first_step,
+                          float margin, const float* lr, float* loss_sum_host, void* stream);
+
+/* ---- ranking: replaces the scoring loop of infer_triples (holE.py:564-573) and the heap
+ * of eval_link_prediction (holE.py:427-469) with a dense contraction on tcgen05 tensor
+ * cores.  For query q = (h, t, r) and side:
+ *   TAIL: candidates j in [ent_begin, ent_end) scored s_j = clip(E_j) . (h * r)
+ *   HEAD: candidates j scored s_j = clip(E_j) . (r * conj(t))~        
+ * raw_before[q]  = #{j : (s_j, j) < (s_true, true_id)}  (ascending: lower is better,
+ *                  holE.py:231, 446-453; ties by smaller candidate id, holE.py:434)
+ * filt_before[q] = raw_before[q] - #{f in filter[q], f in range : (s_f, f) < (s_true, true_id)}
+ *                  (train/valid-true candidates do not advance the filtered rank,
+ *                  holE.py:454-463).  rank = 1 + count.
+ * filter_off int64[Q+1] / filter_ids int32[.] may be NULL (no filtering).
+ * true_score_io float32[Q]: if compute_true != 0 it is written for queries whose true
+ * candidate lies in [ent_begin, ent_end) and left untouched otherwise (so candidate shards
+ * on several GPUs can be combined by the caller); if compute_true == 0 it is read.
+ * Counts are ADDED to raw_before / filt_before (caller zeroes them), so shards accumulate. */
+HOLE_API int hole_rank(hole_ctx* ctx, const float* table, int64_t ent_begin, int64_t ent_end,
+              const int32_t* queries, int64_t Q, int side, int precision,
+              const int64_t* filter_off, const int32_t* filter_ids,
+              float* true_score_io, int compute_true,
+              int32_t* raw_before, int32_t* filt_before, void* stream);
+
+/* Number of kernels this library has launched on this thread's contexts since the last
+ * reset (bench.py's "gpu_launches"). */
+HOLE_API int64_t hole_launch_count(void);
+HOLE_API void hole_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOLE_B200_H */

@@ -1,0 +1,212 @@
+"""Parity of the CUDA training path (through the C ABI) against the oracle.
+
+Standards (north_star / SURVEY 8c):
+  * corruption ids, side coin: bit-exact;
+  * sigma, loss: |d| <= 1e-6 vs the fp32 and fp64 oracle;
+  * updated rows after one step: |d| <= 2e-6 + 1e-5*|x| vs the fp64 oracle (fp32 compute,
+    fixed but different summation order than TF's sequential ScatterSub).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from graphembeddings_b200 import data as D
+from oracle import hole_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SIGMA_ATOL = 1e-6
+ROW_ATOL, ROW_RTOL = 2e-6, 1e-5
+
+
+@pytest.fixture(scope="module")
+def eng_mod():
+    from graphembeddings_b200 import build
+    build.build()
+    from graphembeddings_b200 import engine
+    return engine
+
+
+def _engine(eng_mod, kg):
+    e = eng_mod.HoleEngine(kg.n_rows, kg.dim)
+    e.set_embeddings(kg.E)
+    off, ids = D.build_type_csr(kg.type_of)
+    e.set_types(kg.type_of, off, ids)
+    return e, off, ids
+
+
+DIMS = [20, 64, 128, 150, 256, 512, 600]
+
+
+@pytest.mark.parametrize("dim", DIMS)
+def test_pack_unpack_roundtrip(eng_mod, dim):
+    kg = D.synthetic_kg(5, 300, 10, 3, dim, seed=1)
+    e, _, _ = _engine(eng_mod, kg)
+    assert torch.equal(e.embeddings().cpu(), torch.from_numpy(kg.E))
+    # padding lanes are zero
+    H, Hp = dim // 2, e.row_stride // 2
+    tab = e.table.cpu().numpy()
+    assert np.all(tab[:, H:Hp] == 0) and np.all(tab[:, Hp + H:] == 0)
+
+
+@pytest.mark.parametrize("dim", DIMS)
+@pytest.mark.parametrize("trained", [False, True])
+def test_score_matches_oracle(eng_mod, dim, trained):
+    kg = D.synthetic_kg(9, 2000, 3000, 6, dim, seed=dim, trained_scale=trained, zipf_entities=True)
+    e, _, _ = _engine(eng_mod, kg)
+    got = e.evaluate_triples(kg.triples).cpu().numpy()
+    want64 = O.evaluate_triples(kg.E.astype(np.float64), kg.triples, np.float64)
+    want32 = O.evaluate_triples(kg.E, kg.triples, np.float32)
+    assert np.abs(got - want64).max() <= SIGMA_ATOL
+    assert np.abs(got - want32).max() <= SIGMA_ATOL
+    if trained:
+        assert got.std() > 1e-3      # not a degenerate all-0.5 comparison
+
+
+def test_corruption_bit_exact(eng_mod):
+    kg = D.make_config("fb15k_d150", n_triples=20000, with_embeddings=False)
+    kg.E = D.init_embeddings(kg.n_rows, 8, np.random.default_rng(0))
+    kg.dim = 8
+    e, off, ids = _engine(eng_mod, kg)
+    seen = set()
+    for step in (0, 1, 2, 3, 2**33 + 5):
+        side, neg = e.corrupt_batch(kg.triples, seed=0xC0FFEE123456789, step=step)
+        oside, oneg = O.corrupt(kg.triples, kg.type_of, off, ids, 0xC0FFEE123456789, step)
+        assert side == oside
+        assert np.array_equal(neg.cpu().numpy(), oneg)
+        seen.add(side)
+    assert seen == {0, 1}
+
+
+def _check_step(eng_mod, kg, B, side_force=None, seed=3, step=0, lr=0.1, margin=0.2):
+    e, off, ids = _engine(eng_mod, kg)
+    pos = kg.triples[:B]
+    side, neg = O.corrupt(pos, kg.type_of, off, ids, seed, step)
+    if side_force is not None:
+        side = side_force
+    loss, vp, vn = e.train_step(pos, neg, side, margin, lr, return_sigma=True)
+    E64 = kg.E.astype(np.float64)
+    l64, vp64, vn64 = O.sgd_step(E64, pos, neg, side, margin, lr, np.float64, "tf")
+    E32 = kg.E.copy()
+    l32, _, _ = O.sgd_step(E32, pos, neg, side, margin, lr, np.float32, "tf")
+    assert np.abs(vp.cpu().numpy() - vp64).max() <= SIGMA_ATOL
+    assert np.abs(vn.cpu().numpy() - vn64).max() <= SIGMA_ATOL
+    assert np.abs(loss.cpu().numpy() - l64).max() <= 2 * SIGMA_ATOL
+    got = e.embeddings().cpu().numpy()
+    err = np.abs(got - E64)
+    tol = ROW_ATOL + ROW_RTOL * np.abs(E64)
+    assert (err <= tol).all(), float((err - tol).max())
+    # also against the fp32 oracle in TF order
+    assert np.abs(got - E32).max() <= 4e-6
+    # the step did move the touched rows and nothing else
+    touched = np.unique(np.concatenate([pos.ravel(), neg]))
+    untouched = np.setdiff1d(np.arange(kg.n_rows), touched)
+    assert np.array_equal(got[untouched], kg.E[untouched])
+    assert np.abs(got - kg.E).max() > 1e-5
+    return e
+
+
+@pytest.mark.parametrize("dim", DIMS)
+@pytest.mark.parametrize("side", [0, 1])
+def test_train_step_matches_oracle(eng_mod, dim, side):
+    kg = D.synthetic_kg(7, 500, 1024, 5, dim, seed=100 + dim, trained_scale=True, zipf_entities=True)
+    _check_step(eng_mod, kg, 1024, side_force=side)
+
+
+def test_train_step_xavier_init_all_hinges_active(eng_mod):
+    kg = D.synthetic_kg(11, 4000, 2048, 5, 150, seed=5)
+    e = _check_step(eng_mod, kg, 2048)
+
+
+def test_train_step_heavy_duplicates(eng_mod):
+    """3 relations, 40 entities, 6000 triples: every row has hundreds of occurrences, so the
+    combine tree runs several levels deep."""
+    kg = D.synthetic_kg(3, 40, 6000, 2, 64, seed=8, trained_scale=True, zipf_entities=True)
+    _check_step(eng_mod, kg, 6000)
+
+
+@pytest.mark.parametrize("B", [1, 2, 31, 33, 513])
+def test_train_step_ragged_batches(eng_mod, B):
+    kg = D.synthetic_kg(4, 200, 600, 3, 150, seed=B, trained_scale=True)
+    _check_step(eng_mod, kg, B)
+
+
+def test_empty_batch_is_a_noop(eng_mod):
+    kg = D.synthetic_kg(4, 50, 10, 3, 16, seed=2)
+    e, _, _ = _engine(eng_mod, kg)
+    loss = e.train_step(np.zeros((0, 3), np.int32), np.zeros(0, np.int32), 0, 0.2, 0.1)
+    assert loss.numel() == 0
+    assert torch.equal(e.embeddings().cpu(), torch.from_numpy(kg.E))
+    assert e.evaluate_triples(np.zeros((0, 3), np.int32)).numel() == 0
+
+
+def test_train_step_is_deterministic(eng_mod):
+    kg = D.synthetic_kg(3, 100, 4096, 2, 128, seed=21, trained_scale=True, zipf_entities=True)
+    outs = []
+    for _ in range(3):
+        e, off, ids = _engine(eng_mod, kg)
+        side, neg = O.corrupt(kg.triples, kg.type_of, off, ids, 1, 0)
+        e.train_step(kg.triples, neg, side, 0.2, 0.1)
+        outs.append(e.embeddings().cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_golden_fixture_step(eng_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "train_step_oracle.npz"))
+    E0, pos = z["E0"], z["pos"]
+    for step in (0, 1):
+        e = eng_mod.HoleEngine(E0.shape[0], E0.shape[1])
+        e.set_embeddings(E0)
+        loss = e.train_step(pos, z[f"neg{step}"], int(z[f"side{step}"]), 0.2, 0.1)
+        assert np.abs(loss.cpu().numpy() - z[f"loss64_{step}"]).max() <= 2 * SIGMA_ATOL
+        got = e.embeddings().cpu().numpy()
+        assert np.abs(got - z[f"E64_{step}"]).max() <= ROW_ATOL + ROW_RTOL
+
+
+@pytest.mark.parametrize("dim,B", [(150, 512), (256, 1000)])
+def test_multi_step_matches_oracle_loop(eng_mod, dim, B):
+    """hole_train_steps (device-side loop incl. Philox corruption) vs the oracle loop."""
+    n_steps = 5
+    kg = D.synthetic_kg(6, 3000, B * n_steps, 4, dim, seed=77, trained_scale=True)
+    e, off, ids = _engine(eng_mod, kg)
+    lrs = [eng_mod.inverse_time_decay(0.1, s, 32 * 100, 0.5) for s in range(n_steps)]
+    sums, loss = e.train_steps(kg.triples, B, seed=9, first_step=0, margin=0.2, lrs=lrs, want_loss=True)
+    E64 = kg.E.astype(np.float64)
+    want = []
+    for s in range(n_steps):
+        pos = kg.triples[s * B:(s + 1) * B]
+        side, neg = O.corrupt(pos, kg.type_of, off, ids, 9, s)
+        l, _, _ = O.sgd_step(E64, pos, neg, side, 0.2, float(lrs[s]), np.float64, "tf")
+        want.append(l)
+    want = np.concatenate(want)
+    assert np.abs(loss.cpu().numpy() - want).max() <= 5e-6
+    assert np.abs(sums.cpu().numpy() - want.reshape(n_steps, B).sum(1)).max() <= 1e-3
+    got = e.embeddings().cpu().numpy()
+    assert np.abs(got - E64).max() <= 1e-5
+    # host-buffer path gives the same table bit for bit
+    e2, _, _ = _engine(eng_mod, kg)
+    hs = e2.train_steps_host(kg.triples, B, seed=9, first_step=0, margin=0.2, lrs=lrs)
+    assert np.array_equal(hs, sums.cpu().numpy())
+    assert torch.equal(e2.embeddings().cpu(), e.embeddings().cpu())
+
+
+def test_full_size_properties_config0(eng_mod):
+    """BASELINE config 0 at full size (16,296 x 150, 483,142 triples, B = 8192): properties
+    that need no oracle -- determinism across runs, untouched rows unchanged, loss in range,
+    row norms finite."""
+    kg = D.make_config("fb15k_d150")
+    B = 8192
+    n_steps = kg.triples.shape[0] // B
+    lrs = [0.1] * n_steps
+    res = []
+    for _ in range(2):
+        e, _, _ = _engine(eng_mod, kg)
+        sums = e.train_steps(kg.triples, B, seed=1, first_step=0, margin=0.2, lrs=lrs)
+        res.append((sums.cpu(), e.embeddings().cpu()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    mean_loss = res[0][0].numpy() / B
+    assert np.all(mean_loss > 0.0) and np.all(mean_loss < 0.7)
+    assert mean_loss[-1] < mean_loss[0]          # it learns
+    assert torch.isfinite(res[0][1]).all()
