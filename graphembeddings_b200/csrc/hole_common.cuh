@@ -60,6 +60,10 @@ struct hole_ctx {
   uint32_t* valsB = nullptr;
   uint32_t* sstart = nullptr;    // [S][4B] segment start (sorted index) of each sorted entry
   uint32_t* slen = nullptr;      // [S][4B] segment length, valid at segment starts
+  uint32_t* ghist = nullptr;     // [S][256][tiles] radix histograms
+  uint32_t* skey = nullptr;      // sorted keys (points into keysA or keysB)
+  uint32_t* spos = nullptr;      // sorted positions (points into valsA or valsB)
+  uint8_t* uniq = nullptr;       // [S][4B] per ORIGINAL position: row occurs once in the step
   int* counters = nullptr;       // [LEVELS][4B] tree-combine tickets (self-resetting)
   int32_t* neg = nullptr;        // [S*B] corrupt entity per triple
   float* loss = nullptr;         // [S*B] scratch when the caller passes no loss_out

@@ -198,137 +198,175 @@ __global__ void hole_keys_kernel(const int32_t* __restrict__ pos, const int32_t*
 }
 
 // ---------------------------------------------------------------------------------------
-// update plan: one CTA sorts one step's 4B (row, position) pairs by row, stably (LSD
-// radix, 8-bit digits), then marks segments.  Integer-only; runs for many steps at once
-// ahead of the steps that consume it.
+// update plan: for every step of a chunk, sort the step's 4B (row, position) pairs by row,
+// stably (LSD radix, 8-bit digits), then mark segments.  Integer-only, off the critical
+// path (it depends on the triples and the Philox draw, never on the table), so a chunk of
+// steps is planned in one batch of launches: grid.y = step, grid.x = tile of the step.
 // ---------------------------------------------------------------------------------------
-constexpr int SORT_THREADS = 1024;
-constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int ST_THREADS = 256;
+constexpr int ST_WARPS = ST_THREADS / 32;
+constexpr int ST_SLICE = 512;                    // entries per warp
+constexpr int ST_TILE = ST_SLICE * ST_WARPS;     // entries per block
 
-__global__ void __launch_bounds__(SORT_THREADS, 1)
-hole_plan_sort_kernel(uint32_t* keysA, uint32_t* valsA, uint32_t* keysB, uint32_t* valsB,
-                      uint32_t* sstart, uint32_t* slen, int M, int passes) {
-  __shared__ uint32_t hist[256 * SORT_WARPS];   // [digit][warp]
-  __shared__ uint32_t wsum[SORT_WARPS];
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const size_t base = (size_t)blockIdx.x * M;
-  uint32_t* kin = keysA + base;
-  uint32_t* vin = valsA + base;
-  uint32_t* kout = keysB + base;
-  uint32_t* vout = valsB + base;
-  // each warp owns a contiguous slice (multiple of 32 entries)
-  const int per_warp = ((M + SORT_WARPS - 1) / SORT_WARPS + 31) & ~31;
-  const int w_lo = min(M, w * per_warp), w_hi = min(M, w_lo + per_warp);
-
-  for (int pass = 0; pass < passes; ++pass) {
-    const int shift = 8 * pass;
-    for (int i = tid; i < 256 * SORT_WARPS; i += SORT_THREADS) hist[i] = 0;
-    __syncthreads();
-    // 1. per-warp digit histogram
-    for (int j0 = w_lo; j0 < w_hi; j0 += 32) {
-      int j = j0 + lane;
-      bool ok = j < w_hi;
-      uint32_t d = ok ? ((kin[j] >> shift) & 255u) : 256u + lane;   // inactive lanes: unique
+// per-warp digit histogram of the warp's slice of the tile (wh = this warp's 256 counters)
+__device__ __forceinline__ void st_warp_hist(const uint32_t* __restrict__ k, int lo, int hi,
+                                             int shift, uint32_t* wh, int lane) {
+  for (int j0 = lo; j0 < hi; j0 += 128) {
+    uint32_t key[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int j = j0 + 32 * u + lane;
+      key[u] = (j < hi) ? k[j] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int j = j0 + 32 * u + lane;
+      bool ok = j < hi;
+      uint32_t d = ok ? ((key[u] >> shift) & 255u) : 256u + lane;   // inactive lanes: unique
       uint32_t peers = __match_any_sync(0xffffffffu, d);
-      if (ok && lane == __ffs(peers) - 1) hist[d * SORT_WARPS + w] += __popc(peers);
+      if (ok && lane == __ffs(peers) - 1) wh[d] += __popc(peers);
       __syncwarp();
     }
-    __syncthreads();
-    // 2. exclusive scan in (digit-major, warp-minor) order: 8 entries per thread
-    uint32_t loc[8];
-    uint32_t tsum = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { loc[q] = hist[tid * 8 + q]; tsum += loc[q]; }
-    uint32_t inc = tsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += y;
-    }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t x = wsum[lane];
-      uint32_t xi = x;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, xi, o);
-        if (lane >= o) xi += y;
-      }
-      wsum[lane] = xi - x;
-    }
-    __syncthreads();
-    uint32_t run = wsum[w] + inc - tsum;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { hist[tid * 8 + q] = run; run += loc[q]; }
-    __syncthreads();
-    // 3. stable scatter
-    for (int j0 = w_lo; j0 < w_hi; j0 += 32) {
-      int j = j0 + lane;
-      bool ok = j < w_hi;
-      uint32_t key = ok ? kin[j] : 0u;
-      uint32_t val = ok ? (pass == 0 ? (uint32_t)j : vin[j]) : 0u;
-      uint32_t d = ok ? ((key >> shift) & 255u) : 256u + lane;
-      uint32_t peers = __match_any_sync(0xffffffffu, d);
-      uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-      uint32_t dst = 0;
-      if (ok) {
-        dst = hist[d * SORT_WARPS + w] + rank;
-        kout[dst] = key;
-        vout[dst] = val;
-      }
-      __syncwarp();
-      if (ok && lane == __ffs(peers) - 1) hist[d * SORT_WARPS + w] += __popc(peers);
-      __syncwarp();
-    }
-    __syncthreads();
-    uint32_t* t;
-    t = kin; kin = kout; kout = t;
-    t = vin; vin = vout; vout = t;
-    __threadfence_block();
   }
-  // sorted pairs are now in (kin, vin).  Host guarantees that is (keysA, valsA) by choosing
-  // an even pass count.
-  // 4. segment starts: sstart[j] = first sorted index holding the same row as j.
-  const int per_thr = (M + SORT_THREADS - 1) / SORT_THREADS;
-  const int t_lo = min(M, tid * per_thr), t_hi = min(M, t_lo + per_thr);
-  int last_head = -1;   // last segment head inside my chunk
-  for (int j = t_lo; j < t_hi; ++j)
-    if (j == 0 || kin[j - 1] != kin[j]) last_head = j;
-  // block-wide inclusive max-scan of last_head
-  int incm = last_head;
+}
+
+// ghist[(s*256 + digit)*P + p] = number of entries of tile p of step s with that digit
+__global__ void __launch_bounds__(ST_THREADS)
+hole_sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t* __restrict__ ghist, int M, int P,
+                      int shift) {
+  __shared__ uint32_t wh[ST_WARPS][256];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int p = blockIdx.x, s = blockIdx.y;
+  for (int i = tid; i < ST_WARPS * 256; i += ST_THREADS) (&wh[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t* k = keys + (size_t)s * M;
+  const int lo = min(M, p * ST_TILE + w * ST_SLICE), hi = min(M, lo + ST_SLICE);
+  st_warp_hist(k, lo, hi, shift, wh[w], lane);
+  __syncthreads();
+  uint32_t tot = 0;
+#pragma unroll
+  for (int q = 0; q < ST_WARPS; ++q) tot += wh[q][tid];
+  ghist[((size_t)s * 256 + tid) * P + p] = tot;
+}
+
+// exclusive scan of one step's [256][P] tile histogram in (digit-major, tile-minor) order
+__global__ void __launch_bounds__(256)
+hole_sort_scan_kernel(uint32_t* __restrict__ ghist, int P) {
+  __shared__ uint32_t wsum[8];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  uint32_t* h = ghist + ((size_t)blockIdx.x * 256 + tid) * P;
+  uint32_t tot = 0;
+  for (int p = 0; p < P; ++p) tot += h[p];
+  uint32_t inc = tot;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    int y = __shfl_up_sync(0xffffffffu, incm, o);
-    if (lane >= o) incm = max(incm, y);
+    uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
   }
-  __shared__ int wmax[SORT_WARPS];
-  if (lane == 31) wmax[w] = incm;
+  if (lane == 31) wsum[w] = inc;
   __syncthreads();
-  if (w == 0) {
-    int x = wmax[lane];
+  uint32_t base = inc - tot;
+  for (int q = 0; q < w; ++q) base += wsum[q];
+  for (int p = 0; p < P; ++p) {
+    uint32_t c = h[p];
+    h[p] = base;
+    base += c;
+  }
+}
+
+// stable scatter of one tile; vals_in == nullptr means "value = index" (first pass)
+__global__ void __launch_bounds__(ST_THREADS)
+hole_sort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                         uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                         const uint32_t* __restrict__ ghist, int M, int P, int shift) {
+  __shared__ uint32_t wh[ST_WARPS][256];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int p = blockIdx.x, s = blockIdx.y;
+  for (int i = tid; i < ST_WARPS * 256; i += ST_THREADS) (&wh[0][0])[i] = 0;
+  __syncthreads();
+  const size_t base = (size_t)s * M;
+  const uint32_t* k = keys_in + base;
+  const uint32_t* v = vals_in ? vals_in + base : nullptr;
+  uint32_t* ko = keys_out + base;
+  uint32_t* vo = vals_out + base;
+  const int lo = min(M, p * ST_TILE + w * ST_SLICE), hi = min(M, lo + ST_SLICE);
+  st_warp_hist(k, lo, hi, shift, wh[w], lane);
+  __syncthreads();
+  {   // per digit: exclusive scan over the warps of this tile, on top of the global offset
+    uint32_t run = ghist[((size_t)s * 256 + tid) * P + p];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x = max(x, y);
+    for (int q = 0; q < ST_WARPS; ++q) {
+      uint32_t c = wh[q][tid];
+      wh[q][tid] = run;
+      run += c;
     }
-    wmax[lane] = x;
   }
   __syncthreads();
-  int carry = (w > 0) ? wmax[w - 1] : -1;
-  int prev = __shfl_up_sync(0xffffffffu, incm, 1);
-  if (lane > 0) carry = max(carry, prev);
-  uint32_t* ss = sstart + base;
-  uint32_t* sl = slen + base;
-  int cur = carry;
-  for (int j = t_lo; j < t_hi; ++j) {
-    if (j == 0 || kin[j - 1] != kin[j]) cur = j;
-    ss[j] = (uint32_t)cur;
+  uint32_t* myh = wh[w];
+  for (int j0 = lo; j0 < hi; j0 += 128) {
+    uint32_t key[4], val[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int j = j0 + 32 * u + lane;
+      key[u] = (j < hi) ? k[j] : 0u;
+      val[u] = (j < hi) ? (v ? v[j] : (uint32_t)j) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int j = j0 + 32 * u + lane;
+      bool ok = j < hi;
+      uint32_t d = ok ? ((key[u] >> shift) & 255u) : 256u + lane;
+      uint32_t peers = __match_any_sync(0xffffffffu, d);
+      uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      if (ok) {
+        uint32_t dst = myh[d] + rank;
+        ko[dst] = key[u];
+        vo[dst] = val[u];
+      }
+      __syncwarp();
+      if (ok && lane == __ffs(peers) - 1) myh[d] += __popc(peers);
+      __syncwarp();
+    }
   }
-  __syncthreads();
-  // 5. segment lengths at the heads (written by the last entry of each segment)
-  for (int j = t_lo; j < t_hi; ++j)
-    if (j == M - 1 || kin[j + 1] != kin[j]) sl[ss[j]] = (uint32_t)(j + 1) - ss[j];
+}
+
+// segments of the sorted keys: sstart[j] = first sorted index with the same row; slen at
+// segment starts; uniq[original position] = row occurs exactly once in the step (such rows
+// are updated in place by K1, nobody else reads them during the step).
+__global__ void __launch_bounds__(256)
+hole_plan_segments_kernel(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ spos,
+                          uint32_t* __restrict__ sstart, uint32_t* __restrict__ slen,
+                          uint8_t* __restrict__ uniq, int M) {
+  const size_t base = (size_t)blockIdx.y * M;
+  const uint32_t* k = skey + base;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+    const uint32_t key = k[j];
+    const bool head = (j == 0) || (k[j - 1] != key);
+    const bool last = (j == M - 1) || (k[j + 1] != key);
+    uniq[base + spos[base + j]] = (head && last) ? 1 : 0;
+    int s = j;
+    if (!head) {          // lower_bound(key) in [0, j)
+      int lo = 0, hi = j;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (k[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      s = lo;
+    }
+    sstart[base + j] = (uint32_t)s;
+    if (head) {
+      int e = j + 1;
+      if (!last) {        // upper_bound(key) in (j, M)
+        int lo = j + 1, hi = M;
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (k[mid] <= key) lo = mid + 1; else hi = mid;
+        }
+        e = lo;
+      }
+      slen[base + j] = (uint32_t)(e - j);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -363,30 +401,107 @@ hole_score_kernel(const float* __restrict__ E, const int32_t* __restrict__ tripl
 
 // ---------------------------------------------------------------------------------------
 // K1: fused forward + backward of one batch.  One group of GS lanes per positive triple.
-// Writes the four merged gradient rows of triple i to G[slot*B + i], slots
-// [relation, tail-slot, head-slot, corrupt entity] (the rows shared by the positive and
-// the negative triple get the sum of both contributions; the clip backward is linear in
-// the incoming gradient, so merging before it is exact in real arithmetic).
+// For each of the triple's four rows [relation, tail-slot, head-slot, corrupt entity]
+// (rows shared by the positive and the negative triple get the sum of both contributions;
+// the clip backward is linear in the incoming gradient, so merging before it is exact in
+// real arithmetic):
+//   * if the row occurs exactly once in this step (uniq flag from the plan) nobody else
+//     reads it during the step, so it is updated in place: E[row] = x - lr * dx;
+//   * otherwise the gradient row is staged at G[slot*B + i] for K3.
+// The four rows are emitted one after the other to keep the register footprint at
+// (4 input rows + 1 gradient row).
 // ---------------------------------------------------------------------------------------
+enum { ROLE_R = 0, ROLE_T = 1, ROLE_H = 2, ROLE_N = 3 };
+
+template <int GS, int V, int ROLE>
+__device__ __forceinline__ void emit_row(const Row<V>& xh, const Row<V>& xt, const Row<V>& xr,
+                                         const Row<V>& xn, float sh, float st, float sr, float sn,
+                                         float inv_self, int side, float gp, float gn, bool uniq,
+                                         bool act, float lr, float* erow, float* grow, int lane,
+                                         int nvec, bool valid) {
+  Row<V> d;
+  float proj = 0.f;
+  const Row<V>& xs = (ROLE == ROLE_R) ? xr : (ROLE == ROLE_T) ? xt : (ROLE == ROLE_H) ? xh : xn;
+  const float ss = (ROLE == ROLE_R) ? sr : (ROLE == ROLE_T) ? st : (ROLE == ROLE_H) ? sh : sn;
+#pragma unroll
+  for (int k = 0; k < 4 * V; ++k) {
+    const float a = xh.re[k] * sh, b = xh.im[k] * sh, c = xr.re[k] * sr, dd = xr.im[k] * sr,
+                e = xt.re[k] * st, f = xt.im[k] * st;
+    const float nr = xn.re[k] * sn, ni = xn.im[k] * sn;
+    float gre, gim;
+    if (ROLE == ROLE_R) {          // d/dr = g+ [a e + b f ; a f - b e] + g- [same with the negative's h,t]
+      const float a2 = side ? nr : a, b2 = side ? ni : b, e2 = side ? e : nr, f2 = side ? f : ni;
+      gre = gp * (a * e + b * f) + gn * (a2 * e2 + b2 * f2);
+      gim = gp * (a * f - b * e) + gn * (a2 * f2 - b2 * e2);
+    } else if (ROLE == ROLE_T) {   // d/dt = g [a c - b d ; a d + b c]
+      gre = gp * (a * c - b * dd);
+      gim = gp * (a * dd + b * c);
+      if (side) {                  // negative (n, t, r) shares t
+        gre += gn * (nr * c - ni * dd);
+        gim += gn * (nr * dd + ni * c);
+      }
+    } else if (ROLE == ROLE_H) {   // d/dh = g [c e + d f ; c f - d e]
+      gre = gp * (c * e + dd * f);
+      gim = gp * (c * f - dd * e);
+      if (!side) {                 // negative (h, n, r) shares h
+        gre += gn * (c * nr + dd * ni);
+        gim += gn * (c * ni - dd * nr);
+      }
+    } else {                       // corrupt entity: head role if side else tail role
+      gre = side ? gn * (c * e + dd * f) : gn * (a * c - b * dd);
+      gim = side ? gn * (c * f - dd * e) : gn * (a * dd + b * c);
+    }
+    d.re[k] = gre;
+    d.im[k] = gim;
+    proj = fmaf(xs.re[k] * ss, gre, fmaf(xs.im[k] * ss, gim, proj));
+  }
+  // through the norm clip: dx = clipped ? (dy - y (y.dy)) * inv : dy, y = x * s   (App. A.3)
+  if (inv_self <= 1.0f) {          // group-uniform
+    proj = group_sum<GS>(proj);
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) {
+      d.re[k] = (d.re[k] - (xs.re[k] * ss) * proj) * inv_self;
+      d.im[k] = (d.im[k] - (xs.im[k] * ss) * proj) * inv_self;
+    }
+  }
+  if (!valid) return;
+  if (uniq) {
+    if (act) {                     // inactive hinge: zero gradient, row unchanged
+#pragma unroll
+      for (int k = 0; k < 4 * V; ++k) {
+        d.re[k] = xs.re[k] - lr * d.re[k];
+        d.im[k] = xs.im[k] - lr * d.im[k];
+      }
+      row_store<GS, V>(d, erow, lane, nvec);
+    }
+  } else {
+    row_store<GS, V>(d, grow, lane, nvec);
+  }
+}
+
 template <int GS, int V>
 __global__ void __launch_bounds__(256)
-hole_train_fwd_bwd_kernel(const float* __restrict__ E, const int32_t* __restrict__ pos,
-                          const int32_t* __restrict__ neg, int side, int64_t B, int nvec,
-                          int stride, float margin, float* __restrict__ G,
-                          float* __restrict__ loss, float* __restrict__ sigma) {
+hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ pos,
+                          const int32_t* __restrict__ neg, const uint8_t* __restrict__ uniq,
+                          int side, int64_t B, int nvec, int stride, float margin, float lr,
+                          float* __restrict__ G, float* __restrict__ loss,
+                          float* __restrict__ sigma) {
   const int lane = threadIdx.x % GS;
   int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
   const bool valid = g < B;
   const int64_t i = valid ? g : B - 1;
   const int h = pos[3 * i], t = pos[3 * i + 1], r = pos[3 * i + 2], n = neg[i];
+  const bool uq_r = uniq[i] != 0, uq_t = uniq[B + i] != 0, uq_h = uniq[2 * B + i] != 0,
+             uq_n = uniq[3 * B + i] != 0;
 
-  Row<V> yh, yt, yr, yn;
-  row_load<GS, V, true>(yh, E + (size_t)h * stride, lane, nvec);
-  row_load<GS, V, true>(yt, E + (size_t)t * stride, lane, nvec);
-  row_load<GS, V, true>(yr, E + (size_t)r * stride, lane, nvec);
-  row_load<GS, V, true>(yn, E + (size_t)n * stride, lane, nvec);
+  // unscaled rows stay in registers (needed again for the in-place update); y = x * s
+  Row<V> xh, xt, xr, xn;
+  row_load<GS, V, false>(xh, E + (size_t)h * stride, lane, nvec);
+  row_load<GS, V, false>(xt, E + (size_t)t * stride, lane, nvec);
+  row_load<GS, V, false>(xr, E + (size_t)r * stride, lane, nvec);
+  row_load<GS, V, false>(xn, E + (size_t)n * stride, lane, nvec);
 
-  float ssh = row_sumsq(yh), sst = row_sumsq(yt), ssr = row_sumsq(yr), ssn = row_sumsq(yn);
+  float ssh = row_sumsq(xh), sst = row_sumsq(xt), ssr = row_sumsq(xr), ssn = row_sumsq(xn);
 #pragma unroll
   for (int o = GS / 2; o > 0; o >>= 1) {
     ssh += __shfl_xor_sync(0xffffffffu, ssh, o);
@@ -394,23 +509,23 @@ hole_train_fwd_bwd_kernel(const float* __restrict__ E, const int32_t* __restrict
     ssr += __shfl_xor_sync(0xffffffffu, ssr, o);
     ssn += __shfl_xor_sync(0xffffffffu, ssn, o);
   }
+  // clip_by_norm(row, 1): y = x * min(rsqrt(sum x^2), 1)  (App. B)
   const float ih = __frsqrt_rn(ssh), it = __frsqrt_rn(sst), ir = __frsqrt_rn(ssr),
               in_ = __frsqrt_rn(ssn);
-  row_clip(yh, ih); row_clip(yt, it); row_clip(yr, ir); row_clip(yn, in_);
+  const float sh = fminf(ih, 1.0f), st_ = fminf(it, 1.0f), sr = fminf(ir, 1.0f),
+              sn_ = fminf(in_, 1.0f);
 
   // scores: s = sum (a c - b d) e + (a d + b c) f   with h=(a,b) r=(c,d) t=(e,f)
   float sp = 0.f, sn = 0.f;
 #pragma unroll
   for (int k = 0; k < 4 * V; ++k) {
-    const float a = yh.re[k], b = yh.im[k], c = yr.re[k], d = yr.im[k], e = yt.re[k], f = yt.im[k];
+    const float a = xh.re[k] * sh, b = xh.im[k] * sh, c = xr.re[k] * sr, d = xr.im[k] * sr,
+                e = xt.re[k] * st_, f = xt.im[k] * st_;
+    const float nr = xn.re[k] * sn_, ni = xn.im[k] * sn_;
     const float pr = a * c - b * d, pi = a * d + b * c;
     sp += pr * e + pi * f;
-    if (side) {   // negative = (n, t, r)
-      const float a2 = yn.re[k], b2 = yn.im[k];
-      sn += (a2 * c - b2 * d) * e + (a2 * d + b2 * c) * f;
-    } else {      // negative = (h, n, r)
-      sn += pr * yn.re[k] + pi * yn.im[k];
-    }
+    if (side) sn += (nr * c - ni * d) * e + (nr * d + ni * c) * f;   // negative = (n, t, r)
+    else      sn += pr * nr + pi * ni;                               // negative = (h, n, r)
   }
 #pragma unroll
   for (int o = GS / 2; o > 0; o >>= 1) {
@@ -426,60 +541,23 @@ hole_train_fwd_bwd_kernel(const float* __restrict__ E, const int32_t* __restrict
     loss[i] = fmaxf(pre, 0.0f);
     if (sigma != nullptr) { sigma[i] = vp; sigma[B + i] = vn; }
   }
-
-  // gradients w.r.t. the clipped rows
-  Row<V> dh, dt, dr, dn;
-#pragma unroll
-  for (int k = 0; k < 4 * V; ++k) {
-    const float a = yh.re[k], b = yh.im[k], c = yr.re[k], d = yr.im[k], e = yt.re[k], f = yt.im[k];
-    const float nr = yn.re[k], ni = yn.im[k];
-    const float p_re = a * c - b * d, p_im = a * d + b * c;     // h * r        -> d/dt
-    const float q_re = c * e + d * f, q_im = c * f - d * e;     // r * conj(t)~ -> d/dh
-    const float u_re = a * e + b * f, u_im = a * f - b * e;     //              -> d/dr
-    if (side) {   // negative (n, t, r): t and r shared, n plays the head
-      const float p2_re = nr * c - ni * d, p2_im = nr * d + ni * c;
-      const float u2_re = nr * e + ni * f, u2_im = nr * f - ni * e;
-      dh.re[k] = gp * q_re;               dh.im[k] = gp * q_im;
-      dn.re[k] = gn * q_re;               dn.im[k] = gn * q_im;
-      dt.re[k] = gp * p_re + gn * p2_re;  dt.im[k] = gp * p_im + gn * p2_im;
-      dr.re[k] = gp * u_re + gn * u2_re;  dr.im[k] = gp * u_im + gn * u2_im;
-    } else {      // negative (h, n, r): h and r shared, n plays the tail
-      const float q2_re = c * nr + d * ni, q2_im = c * ni - d * nr;
-      const float u2_re = a * nr + b * ni, u2_im = a * ni - b * nr;
-      dt.re[k] = gp * p_re;               dt.im[k] = gp * p_im;
-      dn.re[k] = gn * p_re;               dn.im[k] = gn * p_im;
-      dh.re[k] = gp * q_re + gn * q2_re;  dh.im[k] = gp * q_im + gn * q2_im;
-      dr.re[k] = gp * u_re + gn * u2_re;  dr.im[k] = gp * u_im + gn * u2_im;
-    }
-  }
-  // through the norm clip
-  float ph = row_dot(yh, dh), pt = row_dot(yt, dt), pr_ = row_dot(yr, dr), pn = row_dot(yn, dn);
-#pragma unroll
-  for (int o = GS / 2; o > 0; o >>= 1) {
-    ph += __shfl_xor_sync(0xffffffffu, ph, o);
-    pt += __shfl_xor_sync(0xffffffffu, pt, o);
-    pr_ += __shfl_xor_sync(0xffffffffu, pr_, o);
-    pn += __shfl_xor_sync(0xffffffffu, pn, o);
-  }
-  clip_backward(dh, yh, ph, ih);
-  clip_backward(dt, yt, pt, it);
-  clip_backward(dr, yr, pr_, ir);
-  clip_backward(dn, yn, pn, in_);
-  if (valid) {
-    row_store<GS, V>(dr, G + (size_t)(0 * B + i) * stride, lane, nvec);
-    row_store<GS, V>(dt, G + (size_t)(1 * B + i) * stride, lane, nvec);
-    row_store<GS, V>(dh, G + (size_t)(2 * B + i) * stride, lane, nvec);
-    row_store<GS, V>(dn, G + (size_t)(3 * B + i) * stride, lane, nvec);
-  }
+  emit_row<GS, V, ROLE_R>(xh, xt, xr, xn, sh, st_, sr, sn_, ir, side, gp, gn, uq_r, act, lr,
+                          E + (size_t)r * stride, G + (size_t)(0 * B + i) * stride, lane, nvec, valid);
+  emit_row<GS, V, ROLE_T>(xh, xt, xr, xn, sh, st_, sr, sn_, it, side, gp, gn, uq_t, act, lr,
+                          E + (size_t)t * stride, G + (size_t)(1 * B + i) * stride, lane, nvec, valid);
+  emit_row<GS, V, ROLE_H>(xh, xt, xr, xn, sh, st_, sr, sn_, ih, side, gp, gn, uq_h, act, lr,
+                          E + (size_t)h * stride, G + (size_t)(2 * B + i) * stride, lane, nvec, valid);
+  emit_row<GS, V, ROLE_N>(xh, xt, xr, xn, sh, st_, sr, sn_, in_, side, gp, gn, uq_n, act, lr,
+                          E + (size_t)n * stride, G + (size_t)(3 * B + i) * stride, lane, nvec, valid);
 }
 
 // ---------------------------------------------------------------------------------------
-// K3: deterministic sparse SGD update.  One group per sorted entry; only entries that head
-// a chunk of C consecutive occurrences of a row do work.  A row with n occurrences is
-// reduced by a fixed C-ary tree over its sorted occurrences (order: slot, then batch
-// index); the last group to finish a node's children combines them in child order, so the
-// result does not depend on scheduling.  Partials reuse the (already consumed) staged
-// gradient row of a node's first occurrence.
+// K3: deterministic sparse SGD update for rows that occur more than once in the step.
+// One group per sorted entry; only entries that head a chunk of C consecutive occurrences
+// of a row do work.  A row with n occurrences is reduced by a fixed C-ary tree over its
+// sorted occurrences (order: slot, then batch index); the last group to finish a node's
+// children combines them in child order, so the result does not depend on scheduling.
+// Partials reuse the (already consumed) staged gradient row of a node's first occurrence.
 // ---------------------------------------------------------------------------------------
 template <int V>
 __device__ __forceinline__ void row_zero(Row<V>& x) {
@@ -492,6 +570,32 @@ __device__ __forceinline__ void row_add(Row<V>& acc, const Row<V>& x) {
   for (int k = 0; k < 4 * V; ++k) { acc.re[k] += x.re[k]; acc.im[k] += x.im[k]; }
 }
 
+// acc = sum over q < cnt (<= C) of the staged rows G[idx(q)], in q order, with the loads of
+// NB rows in flight at a time.  idx0/idx1 hold this lane's share of the row indices:
+// lane l has idx(l) in idx0 and idx(l + GS) in idx1.
+template <int GS, int V>
+__device__ __forceinline__ void sum_rows(Row<V>& acc, const float* __restrict__ G, uint32_t idx0,
+                                         uint32_t idx1, int cnt, int stride, int lane, int nvec,
+                                         unsigned gmask, int gbase) {
+  constexpr int C = HOLE_TREE_C;
+  constexpr int NB = (V == 1) ? 8 : 4;
+  row_zero(acc);
+#pragma unroll
+  for (int q0 = 0; q0 < C; q0 += NB) {
+    if (q0 >= cnt) break;          // group-uniform
+    Row<V> x[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int q = q0 + u;
+      const uint32_t p = __shfl_sync(gmask, (q < GS) ? idx0 : idx1, gbase + (q % GS));
+      if (q < cnt) row_load<GS, V, false>(x[u], G + (size_t)p * stride, lane, nvec);
+      else row_zero(x[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) row_add(acc, x[u]);
+  }
+}
+
 template <int GS, int V>
 __global__ void __launch_bounds__(256)
 hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint32_t* __restrict__ skey,
@@ -499,31 +603,33 @@ hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint32_t* 
                   const uint32_t* __restrict__ slen, int* __restrict__ counters, int M, int nvec,
                   int stride, float lr) {
   constexpr int C = HOLE_TREE_C;
+  static_assert(C <= 2 * GS, "index broadcast assumes C <= 2*GS");
   const int lane = threadIdx.x % GS;
-  const unsigned gmask = (GS == 32) ? 0xffffffffu
-                                    : (((1u << GS) - 1u) << ((threadIdx.x % 32) / GS * GS));
+  const int gbase = (threadIdx.x % 32) / GS * GS;
+  const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << gbase);
   const int64_t j64 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
   if (j64 >= M) return;
   const int j = (int)j64;
   const int s = (int)sstart[j];
   const int rel = j - s;
   if (rel % C != 0) return;
-  const int row = (int)skey[j];
   const int n = (int)slen[s];
+  if (n == 1) return;              // updated in place by K1
+  const int row = (int)skey[j];
   const int cnt = min(C, n - rel);
 
-  Row<V> acc, x;
-  row_zero(acc);
-  for (int q = 0; q < cnt; ++q) {
-    const uint32_t p = spos[j + q];
-    row_load<GS, V, false>(x, G + (size_t)p * stride, lane, nvec);
-    row_add(acc, x);
+  Row<V> acc;
+  {
+    const uint32_t i0 = (lane < cnt) ? spos[j + lane] : 0u;
+    const uint32_t i1 = (lane + GS < cnt) ? spos[j + lane + GS] : 0u;
+    sum_rows<GS, V>(acc, G, i0, i1, cnt, stride, lane, nvec, gmask, gbase);
   }
   int level = 0, idx = rel / C, nl = (n + C - 1) / C;
   int64_t span = C;   // sorted entries covered by one node of this level
   while (true) {
     if (nl == 1) {    // root: apply   E[row] -= lr * acc   (holE.py:296)
       float* erow = E + (size_t)row * stride;
+      Row<V> x;
       row_load<GS, V, false>(x, erow, lane, nvec);
 #pragma unroll
       for (int k = 0; k < 4 * V; ++k) {
@@ -541,15 +647,15 @@ hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint32_t* 
     int* ctr = counters + (size_t)level * M + (s + parent * span * C);
     int ticket = 0;
     if (lane == 0) ticket = atomicAdd(ctr, 1);
-    ticket = __shfl_sync(gmask, ticket, (threadIdx.x % 32) / GS * GS);
+    ticket = __shfl_sync(gmask, ticket, gbase);
     if (ticket != nchild - 1) return;
     if (lane == 0) *ctr = 0;          // self-reset for the next step
     __threadfence();
-    row_zero(acc);
-    for (int c = 0; c < nchild; ++c) {
-      const uint32_t p = spos[s + (parent * (int64_t)C + c) * span];
-      row_load<GS, V, false>(x, G + (size_t)p * stride, lane, nvec);
-      row_add(acc, x);
+    {
+      const int64_t cb = s + (parent * (int64_t)C) * span;
+      const uint32_t i0 = (lane < nchild) ? spos[cb + lane * span] : 0u;
+      const uint32_t i1 = (lane + GS < nchild) ? spos[cb + (lane + GS) * span] : 0u;
+      sum_rows<GS, V>(acc, G, i0, i1, nchild, stride, lane, nvec, gmask, gbase);
     }
     ++level;
     idx = parent;
@@ -557,6 +663,7 @@ hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint32_t* 
     span *= C;
   }
 }
+
 
 // deterministic per-step loss sum: one CTA per step, fixed-shape tree
 __global__ void __launch_bounds__(256)
@@ -652,7 +759,8 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
 static void ws_free(hole_ctx* c) {
   cudaFree(c->G); cudaFree(c->keysA); cudaFree(c->keysB); cudaFree(c->valsA); cudaFree(c->valsB);
   cudaFree(c->sstart); cudaFree(c->slen); cudaFree(c->counters); cudaFree(c->neg);
-  cudaFree(c->loss); cudaFree(c->loss_sum);
+  cudaFree(c->loss); cudaFree(c->loss_sum); cudaFree(c->uniq); cudaFree(c->ghist);
+  c->uniq = nullptr; c->ghist = nullptr; c->skey = c->spos = nullptr;
   c->G = nullptr; c->keysA = c->keysB = c->valsA = c->valsB = c->sstart = c->slen = nullptr;
   c->counters = nullptr; c->neg = nullptr; c->loss = nullptr; c->loss_sum = nullptr;
   c->cap_B = c->cap_S = 0;
@@ -700,6 +808,8 @@ int hole_ws_reserve(hole_ctx* c, int64_t B, int64_t S) {
   WS_ALLOC(c->neg, (size_t)S * B * 4);
   WS_ALLOC(c->loss, (size_t)S * B * 4);
   WS_ALLOC(c->loss_sum, (size_t)S * 4);
+  WS_ALLOC(c->uniq, S * M);
+  WS_ALLOC(c->ghist, (size_t)S * 256 * ((M + ST_TILE - 1) / ST_TILE) * 4);
 #undef WS_ALLOC
   HOLE_CUDA_TRY(cudaMemset(c->counters, 0, (size_t)HOLE_TREE_LEVELS * M * 4));
   c->cap_B = B;
@@ -756,9 +866,30 @@ extern "C" int hole_score(hole_ctx* c, const float* table, const int32_t* triple
   return HOLE_OK;
 }
 
-static int sort_passes(const hole_ctx* c) {
-  int p = (c->key_bits + 7) / 8;
-  return (p + 1) & ~1;   // even, so the sorted pairs end in (keysA, valsA)
+// Plan S steps whose unsorted keys are in keysA[S][M]: stable radix sort by row, then
+// segments.  On return ctx->skey / ctx->spos point at the sorted pairs.
+static int build_plan(hole_ctx* c, int64_t S, int M, cudaStream_t st) {
+  const int passes = (c->key_bits + 7) / 8;
+  const int P = (M + ST_TILE - 1) / ST_TILE;
+  uint32_t *kin = c->keysA, *vin = nullptr, *kout = c->keysB, *vout = c->valsB;
+  dim3 grid((unsigned)P, (unsigned)S);
+  for (int pass = 0; pass < passes; ++pass) {
+    hole_sort_hist_kernel<<<grid, ST_THREADS, 0, st>>>(kin, c->ghist, M, P, 8 * pass);
+    HOLE_LAUNCHED();
+    hole_sort_scan_kernel<<<(unsigned)S, 256, 0, st>>>(c->ghist, P);
+    HOLE_LAUNCHED();
+    hole_sort_scatter_kernel<<<grid, ST_THREADS, 0, st>>>(kin, vin, kout, vout, c->ghist, M, P, 8 * pass);
+    HOLE_LAUNCHED();
+    uint32_t* nk = (kout == c->keysB) ? c->keysA : c->keysB;
+    uint32_t* nv = (vout == c->valsB) ? c->valsA : c->valsB;
+    kin = kout; vin = vout; kout = nk; vout = nv;
+  }
+  c->skey = kin;
+  c->spos = vin;
+  dim3 sgrid((unsigned)std::min<int64_t>((M + 255) / 256, 1024), (unsigned)S);
+  hole_plan_segments_kernel<<<sgrid, 256, 0, st>>>(c->skey, c->spos, c->sstart, c->slen, c->uniq, M);
+  HOLE_LAUNCHED();
+  return HOLE_OK;
 }
 
 // K1 + K3 of one step whose plan (sorted keys, segments) is at plan slot `slot`.
@@ -766,11 +897,12 @@ static int run_step(hole_ctx* c, float* table, const int32_t* pos, const int32_t
                     int64_t B, float margin, float lr, float* loss_out, float* sigma_out,
                     int64_t slot, cudaStream_t st) {
   const int M = (int)(4 * B);
-  HOLE_DISPATCH(c, hole_train_fwd_bwd_kernel, grid_for_groups(B, c->gs), 256, st, table, pos, neg,
-                side, B, c->nvec, c->row_stride, margin, c->G, loss_out, sigma_out);
   const size_t off = (size_t)slot * M;
+  HOLE_DISPATCH(c, hole_train_fwd_bwd_kernel, grid_for_groups(B, c->gs), 256, st, table, pos, neg,
+                c->uniq + off, side, B, c->nvec, c->row_stride, margin, lr, c->G, loss_out,
+                sigma_out);
   HOLE_DISPATCH(c, hole_apply_kernel, grid_for_groups(M, c->gs), 256, st, table, c->G,
-                c->keysA + off, c->valsA + off, c->sstart + off, c->slen + off, c->counters, M,
+                c->skey + off, c->spos + off, c->sstart + off, c->slen + off, c->counters, M,
                 c->nvec, c->row_stride, lr);
   return HOLE_OK;
 }
@@ -788,9 +920,10 @@ extern "C" int hole_train_step(hole_ctx* c, float* table, const int32_t* pos, co
   cudaStream_t st = (cudaStream_t)stream;
   hole_keys_kernel<<<(unsigned)std::min<int64_t>((B + 255) / 256, 65535), 256, 0, st>>>(pos, neg_ent, B, c->keysA);
   HOLE_LAUNCHED();
-  hole_plan_sort_kernel<<<1, SORT_THREADS, 0, st>>>(c->keysA, c->valsA, c->keysB, c->valsB, c->sstart,
-                                                   c->slen, (int)(4 * B), sort_passes(c));
-  HOLE_LAUNCHED();
+  {
+    int rc2 = build_plan(c, 1, (int)(4 * B), st);
+    if (rc2) return rc2;
+  }
   return run_step(c, table, pos, neg_ent, side, B, margin, lr, loss_out, sigma_out, 0, st);
 }
 
@@ -811,9 +944,10 @@ static int train_chunk(hole_ctx* c, float* table, const int32_t* triples_dev, in
   hole_corrupt_kernel<<<grid, 256, 0, st>>>(triples_dev, B, (int)S, type_of, csr_off, csr_ids, seed,
                                             first_step, c->neg, nullptr, c->keysA);
   HOLE_LAUNCHED();
-  hole_plan_sort_kernel<<<(unsigned)S, SORT_THREADS, 0, st>>>(c->keysA, c->valsA, c->keysB, c->valsB,
-                                                              c->sstart, c->slen, M, sort_passes(c));
-  HOLE_LAUNCHED();
+  {
+    int rc2 = build_plan(c, S, M, st);
+    if (rc2) return rc2;
+  }
   for (int64_t k = 0; k < S; ++k) {
     int side = hole_side_coin(seed, first_step + (uint64_t)k);
     int rc = run_step(c, table, triples_dev + (size_t)k * B * 3, c->neg + (size_t)k * B, side, B,

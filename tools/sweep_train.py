@@ -48,8 +48,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", default="both")
     ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--batches", type=str, default="")
     a = ap.parse_args()
+    bl = [int(x) for x in a.batches.split(",")] if a.batches else None
     if a.cfg in ("both", "fb15k"):
-        run("fb15k_d150", 483142, [512, 2048, 8192, 32768], a.steps)
+        run("fb15k_d150", 483142, bl or [512, 2048, 8192, 32768], a.steps)
     if a.cfg in ("both", "diffbot"):
-        run("diffbot_d256", 4_000_000, [512, 2048, 4096, 8192, 16384, 32768, 131072], a.steps)
+        run("diffbot_d256", 4_000_000, bl or [512, 2048, 4096, 8192, 16384, 32768, 131072], a.steps)
