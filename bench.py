@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- HolE training throughput on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch B]
+
+A "step" is one pass of the hot path over one batch of B synthetic triples: Philox
+type-safe corruption, fused gather/clip/score/sigmoid/hinge forward+backward, deterministic
+sparse SGD update.  Workload at N=1: BASELINE.json configs[1] (HolE d=256, 1,200,014-row
+shared table, 12 types with one holding 99 %, Zipf relations) -- the table (1.2 GB) is far
+larger than L2, so no flush is needed between steps.
+
+  value    whole-job triples/s with the triples already resident in HBM
+  e2e      same metric through the C-ABI host-buffer call (hole_train_steps_host): the
+           step's triples are copied from pinned host memory and the step's loss is read
+           back inside the timed region
+  roofline algorithmic bytes (32*D + 20 per triple) / summed duration of the
+           step's two hot kernels, measured with CUDA events in a second pass
+  cpu_baseline  oracle/hole_ref.c (C/OpenMP port of the reference arithmetic) on a bounded
+           sample of the same workload, on this box's host cores
+
+`--impl reference` times that CPU port alone (TensorFlow 1.2, which holE.py needs, cannot be
+installed offline).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = "diffbot_d256"
+MARGIN, LR0 = 0.2, 0.1
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", p
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            c = [x.strip() for x in l.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx = float(c[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(n_triples, with_embeddings=True):
+    from graphembeddings_b200 import data as D
+    kg = D.make_config(WORKLOAD, n_triples=n_triples, with_embeddings=with_embeddings)
+    off, ids = D.build_type_csr(kg.type_of)
+    return kg, off, ids
+
+
+def lr_schedule(n_steps, first_step, batch_count):
+    f = np.float32
+    return np.array([f(LR0) / (f(1.0) + f(0.5) * (f(s) / f(32 * batch_count)))
+                     for s in range(first_step, first_step + n_steps)], dtype=np.float32)
+
+
+def cpu_port_throughput(kg, off, ids, B, min_seconds, max_steps, warmup=1):
+    """Time oracle/hole_ref.c train steps (corruption drawn by the NumPy Philox oracle
+    outside the timed region).  Returns (triples/s, cores, steps, seconds)."""
+    from oracle import hole_oracle as O
+    from oracle import hole_ref as R
+    E = np.ascontiguousarray(kg.E, np.float32).copy()
+    sc = R.TrainScratch(B, kg.dim)
+    n_avail = kg.triples.shape[0] // B
+    negs = []
+    for s in range(min(n_avail, max_steps + warmup)):
+        pos = kg.triples[s * B:(s + 1) * B]
+        negs.append(O.corrupt(pos, kg.type_of, off, ids, 1, s))
+    for s in range(min(warmup, len(negs))):
+        R.train_step(E, kg.triples[s * B:(s + 1) * B], negs[s][1], negs[s][0], MARGIN, LR0, sc)
+    done, t0 = 0, time.perf_counter()
+    for s in range(warmup, len(negs)):
+        R.train_step(E, kg.triples[s * B:(s + 1) * B], negs[s][1], negs[s][0], MARGIN, LR0, sc)
+        done += 1
+        if time.perf_counter() - t0 >= min_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return done * B / dt, R.threads(), done, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, K, W = args.batch, args.steps, args.warmup
+    kg, off, ids = make_workload((K + W) * B)
+    from oracle import hole_oracle as O
+    from oracle import hole_ref as R
+    E = np.ascontiguousarray(kg.E, np.float32)
+    sc = R.TrainScratch(B, kg.dim)
+    negs = [O.corrupt(kg.triples[s * B:(s + 1) * B], kg.type_of, off, ids, 1, s) for s in range(K + W)]
+    for s in range(W):
+        R.train_step(E, kg.triples[s * B:(s + 1) * B], negs[s][1], negs[s][0], MARGIN, LR0, sc)
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        R.train_step(E, kg.triples[s * B:(s + 1) * B], negs[s][1], negs[s][0], MARGIN, LR0, sc)
+    dt = time.perf_counter() - t0
+    v = K * B / dt
+    sample = f"{K} steps of B={B} triples of the {WORKLOAD} workload (corruption ids precomputed)"
+    print(json.dumps({
+        "impl": "reference", "metric": "HolE train triples/s", "value": v, "unit": "triples/s",
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: HolE d=256, 1,200,014-row table, type-safe corruption",
+                   "batch": B, "note": "CPU port of holE.py arithmetic (TensorFlow 1.2 not installable)"},
+        "cpu_baseline": {"value": v, "unit": "triples/s", "cores": R.threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from graphembeddings_b200.engine import HoleEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from graphembeddings_b200 import sharded
+        return sharded.bench(args, dist, rank, world, local_rank)
+
+    B, K, W = args.batch, args.steps, args.warmup
+    t_gen = time.time()
+    kg, off, ids = make_workload((K + W) * B)
+    eng = HoleEngine(kg.n_rows, kg.dim, local_rank).set_embeddings(kg.E).set_types(kg.type_of, off, ids)
+    batch_count = 30_000_000 // B      # the named config has 30 M triples per epoch
+    dev_tri = torch.from_numpy(kg.triples).cuda()
+    host_tri = torch.from_numpy(kg.triples).pin_memory()
+    t_gen = time.time() - t_gen
+
+    def barrier():
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    eng.train_steps(dev_tri[: W * B], B, 1, 0, MARGIN, lr_schedule(W, 0, batch_count))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.reset_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    sums = eng.train_steps(dev_tri[W * B:(W + K) * B], B, 1, W, MARGIN, lr_schedule(K, W, batch_count))
+    ev1.record()
+    barrier()
+    launches = eng.launch_count()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    value = K * B / (ms * 1e-3)
+    mean_loss = float(sums.mean().item()) / B
+
+    # ---- end to end from pinned host triples ("e2e")
+    eng.train_steps_host(host_tri[: W * B], B, 1, W + K, MARGIN, lr_schedule(W, W + K, batch_count))
+    barrier()
+    t0 = time.perf_counter()
+    hs = eng.train_steps_host(host_tri[W * B:(W + K) * B], B, 1, 2 * W + K, MARGIN,
+                              lr_schedule(K, 2 * W + K, batch_count))
+    e2e_s = time.perf_counter() - t0
+    e2e = K * B / e2e_s
+    assert np.isfinite(hs).all()
+
+    # ---- roofline: CUDA events around the two hot kernels of every step (separate pass)
+    eng.profile(True)
+    eng.train_steps(dev_tri[W * B:(W + K) * B], B, 1, 3 * W + 2 * K, MARGIN, lr_schedule(K, W, batch_count))
+    k1_ms, k3_ms, n_prof = eng.profile_read()
+    eng.profile(False)
+    peak, peak_src, _ = peaks()
+    alg_bytes = (32 * kg.dim + 20) * B
+    kern_s = (k1_ms + k3_ms) * 1e-3 / max(n_prof, 1)
+    achieved = alg_bytes / kern_s / 1e9
+
+    # ---- CPU baseline on a bounded sample
+    cpu_v, cores, cpu_steps, cpu_dt = cpu_port_throughput(kg, off, ids, B, args.cpu_seconds, 64)
+
+    out = {
+        "metric": "HolE train triples/s", "value": value, "unit": "triples/s", "n_gpus": 1,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{WORKLOAD}: BASELINE.json configs[1], HolE d=256, 1,200,014-row shared table "
+                        "(14 relations + 1.2M typed entities), type-safe Philox corruption",
+            "batch": B, "margin": MARGIN, "lr0": LR0, "triples_generated": int(kg.triples.shape[0]),
+            "epoch_triples": 30_000_000, "l2": "table (1.2 GB) larger than L2; no flush",
+            "mean_loss_last_pass": mean_loss, "gen_seconds": round(t_gen, 1)},
+        "e2e": {"value": e2e, "unit": "triples/s", "h2d_bytes_per_step": 12 * B,
+                "d2h_bytes_per_step": 4, "call": "hole_train_steps_host (pinned host triples in, loss sums out)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "hole_train_fwd_bwd_kernel + hole_apply_kernel (one step)",
+                     "k1_us": k1_ms * 1e3 / max(n_prof, 1), "k3_us": k3_ms * 1e3 / max(n_prof, 1),
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "whole_step_frac": value * (32 * kg.dim + 20) / 1e9 / peak},
+        "cpu_baseline": {"value": cpu_v, "unit": "triples/s", "cores": cores, "kind": "port",
+                         "sample": f"{cpu_steps} steps of B={B} ({cpu_dt:.1f} s) of the same workload, "
+                                   "oracle/hole_ref.c (C/OpenMP)"},
+    }
+    ranking = None
+    if not args.no_ranking:
+        try:
+            from graphembeddings_b200 import rank_bench
+            ranking = rank_bench.run(eng, kg, quick=True)
+        except Exception as exc:  # ranking is reported beside the headline, never instead of it
+            ranking = {"error": repr(exc)}
+    if ranking is not None:
+        out["ranking"] = ranking
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-ranking", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/hole_b200.h"
 
@@ -77,6 +78,11 @@ struct hole_ctx {
   cudaEvent_t ev_done[2] = {nullptr, nullptr};
 
   hole_rank_ws* rank = nullptr;
+
+  // ---- measurement hooks
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;   // 3 per measured step
+  size_t prof_used = 0;
 };
 
 constexpr int HOLE_TREE_C = 16;      // fan-in of the deterministic gradient combine tree

@@ -1,7 +1,627 @@
-// placeholder, replaced below
+// All-candidate link-prediction ranking for sm_100a: a dense bf16 contraction
+// S = Q . C^T on tcgen05 tensor cores (TMEM accumulators, TMA-fed shared-memory operands)
+// whose epilogue counts, per query row, the candidates that rank before the true one.
+// The Q x N score matrix is never written.
+//
+// Reference seams: the scoring loop of infer_triples (holE.py:564-573) and the heap of
+// eval_link_prediction (holE.py:427-469); GEMM form: SURVEY.md App. A.4, rank rule App. A.5.
+//
+// Kernel anatomy (one CTA per SM, persistent over work items = (query tile, candidate chunk)):
+//   warp 0      TMA producer: query tile once per item, candidate k-blocks through a ring
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma cta_group::1, M=128 N=256 K=16,
+//               accumulators double-buffered in TMEM (2 x 256 columns)
+//   warps 2..9  epilogue: tcgen05.ld 32 columns at a time, compare against the row's
+//               threshold, count; two warps per TMEM lane quarter split the columns
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
 #include "hole_common.cuh"
-void hole_rank_ws_free(hole_ctx*) {}
-extern "C" int hole_rank(hole_ctx*, const float*, int64_t, int64_t, const int32_t*, int64_t, int, int,
-                         const int64_t*, const int32_t*, float*, int, int32_t*, int32_t*, void*) {
-  return hole_set_error(HOLE_ERR_UNSUPPORTED, "hole_rank not built yet");
+
+namespace {
+
+constexpr int BM = 128;            // query rows per tile (UMMA M)
+constexpr int BN = 256;            // candidates per tile (UMMA N)
+constexpr int BK = 64;             // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_KB_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_KB_BYTES = BN * BK * 2;   // 32 KB
+constexpr int RANK_THREADS = 320;
+constexpr int EPI_WARPS = 8;
+constexpr int MAX_STAGES = 4;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+enum { MODE_COUNT = 0, MODE_DIAG = 1 };
+
+struct RankParams {
+  int mode;
+  int num_kb;        // K / 64
+  int stages;        // ring depth for candidate k-blocks
+  int m_tiles;       // query tiles
+  int n_tiles;       // candidate tiles (COUNT mode)
+  int chunk_tiles;   // candidate tiles per work item
+  int n_chunks;
+  int Q;             // valid queries
+  int Nc;            // valid candidates in this shard
+  const float* true_score;     // [Q]   COUNT: thresholds
+  const int32_t* true_idx;     // [Qpad] shard-local index of the true candidate (may be out of range)
+  int32_t* raw_cnt;            // [Q]   COUNT: += count
+  int32_t* filt_cnt;           // [Q]   COUNT: += count (filter hits are subtracted afterwards)
+  float* true_out;             // [Q]   DIAG: score of the true candidate if it lives in this shard
+};
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 in, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile whose rows are 128 bytes (64 bf16): 8-row groups
+// are 1024 bytes apart (SBO); LBO is unused for swizzled K-major layouts (canonical value 1).
+// Bits: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major,
+// N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct SmemLayout {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t a_full;
+  uint64_t a_empty;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+// ------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(RANK_THREADS, 1)
+hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const RankParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte swizzle atoms repeat every 1024 bytes: align the operand area explicitly
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                       // num_kb x 16 KB
+  uint8_t* sB = smem + (size_t)p.num_kb * A_KB_BYTES;       // stages x 32 KB
+  SmemLayout* sl = reinterpret_cast<SmemLayout*>(sB + (size_t)p.stages * B_KB_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.m_tiles * p.n_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&sl->full[s], 1); mbar_init(&sl->empty[s], 1); }
+    mbar_init(&sl->a_full, 1);
+    mbar_init(&sl->a_empty, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&sl->tmem_full[s], 1); mbar_init(&sl->tmem_empty[s], EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&sl->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int m_tile = item / p.n_chunks, chunk = item % p.n_chunks;
+        mbar_wait(&sl->a_empty, a_phase ^ 1);
+        mbar_expect_tx(&sl->a_full, (uint32_t)p.num_kb * A_KB_BYTES);
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_2d(sA + (size_t)kb * A_KB_BYTES, &tmA, &sl->a_full, kb * BK, m_tile * BM);
+        a_phase ^= 1;
+        const int t0 = chunk * p.chunk_tiles;
+        const int t1 = (p.mode == MODE_DIAG) ? t0 + 1 : min(p.n_tiles, t0 + p.chunk_tiles);
+        for (int t = t0; t < t1; ++t) {
+          const int row0 = (p.mode == MODE_DIAG) ? m_tile * BM : t * BN;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&sl->empty[stage], phase ^ 1);
+            mbar_expect_tx(&sl->full[stage], B_KB_BYTES);
+            tma_load_2d(sB + (size_t)stage * B_KB_BYTES, &tmB, &sl->full[stage], kb * BK, row0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int chunk = item % p.n_chunks;
+        mbar_wait(&sl->a_full, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+        const int t0 = chunk * p.chunk_tiles;
+        const int t1 = (p.mode == MODE_DIAG) ? t0 + 1 : min(p.n_tiles, t0 + p.chunk_tiles);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&sl->tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_addr = tmem_base + (uint32_t)acc * BN;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&sl->full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + (size_t)kb * A_KB_BYTES);
+            const uint32_t b_addr = smem_u32(sB + (size_t)stage * B_KB_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2);
+              const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2);
+              umma_bf16(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&sl->empty[stage]);          // frees the smem slot when the MMAs retire
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&sl->tmem_full[acc]);          // accumulator ready for the epilogue
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        umma_commit(&sl->a_empty);                   // query tile may be overwritten
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - 2;                 // 0..7
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                // which 128 columns of the tile
+    const int row_in_tile = quarter * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int m_tile = item / p.n_chunks, chunk = item % p.n_chunks;
+      const int q = m_tile * BM + row_in_tile;
+      const bool qok = q < p.Q;
+      float thr = -INFINITY, thr_hi = -INFINITY;
+      int tie = 0;
+      if (p.mode == MODE_COUNT && qok) {
+        thr = p.true_score[q];
+        thr_hi = nextafterf(thr, INFINITY);          // s <= thr  <=>  s < thr_hi
+        const int ti = p.true_idx[q];
+        tie = ti < 0 ? 0 : (ti > p.Nc ? p.Nc : ti);  // candidates with local index < tie win ties
+      }
+      int cnt = 0;
+      const int t0 = chunk * p.chunk_tiles;
+      const int t1 = (p.mode == MODE_DIAG) ? t0 + 1 : min(p.n_tiles, t0 + p.chunk_tiles);
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&sl->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+        if (p.mode == MODE_COUNT) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(taddr0 + c * 32, v);
+            const int j0 = t * BN + half * 128 + c * 32;       // shard-local index of v[0]
+            const bool slow = (j0 < tie && tie < j0 + 32) || (j0 + 32 > p.Nc);
+            if (!__any_sync(0xffffffffu, slow)) {
+              const float tt = (j0 + 32 <= tie) ? thr_hi : thr;
+#pragma unroll
+              for (int k = 0; k < 32; ++k) cnt += (__uint_as_float(v[k]) < tt) ? 1 : 0;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const int j = j0 + k;
+                const float tt = (j < tie) ? thr_hi : thr;
+                cnt += (j < p.Nc && __uint_as_float(v[k]) < tt) ? 1 : 0;
+              }
+            }
+          }
+        } else if (half == 0) {
+          // DIAG: row i of the tile wants column i, which lives in chunk `quarter`, register `lane`
+          uint32_t v[32];
+          tmem_ld32(taddr0 + quarter * 32, v);
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) s = (k == lane) ? __uint_as_float(v[k]) : s;
+          if (qok) {
+            const int ti = p.true_idx[q];
+            if (ti >= 0 && ti < p.Nc) p.true_out[q] = s;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sl->tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (p.mode == MODE_COUNT && qok && cnt != 0) {
+        atomicAdd(&p.raw_cnt[q], cnt);
+        atomicAdd(&p.filt_cnt[q], cnt);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------ operand packing
+// One warp per row.  Candidate operand: clip(E_j) rounded to bf16, [Re | Im | 0-pad] of K columns.
+__global__ void __launch_bounds__(256)
+hole_rank_pack_cand_kernel(const float* __restrict__ table, int stride, int H, int64_t ent_begin,
+                           int Nc, int Npad, int K, __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= Npad) return;
+  __nv_bfloat16* o = out + (size_t)r * K;
+  if (r >= Nc) {
+    for (int k = lane; k < K; k += 32) o[k] = __float2bfloat16(0.f);
+    return;
+  }
+  const float* x = table + (size_t)(ent_begin + r) * stride;
+  const int Hp = stride / 2;
+  float ss = 0.f;
+  for (int k = lane; k < H; k += 32) { float a = x[k], b = x[Hp + k]; ss = fmaf(a, a, fmaf(b, b, ss)); }
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o2);
+  const float sc = fminf(__frsqrt_rn(ss), 1.0f);
+  for (int k = lane; k < K; k += 32) {
+    float v = 0.f;
+    if (k < H) v = x[k] * sc;
+    else if (k < 2 * H) v = x[Hp + (k - H)] * sc;
+    o[k] = __float2bfloat16(v);
+  }
+}
+
+// Query operand (App. A.4): tail side q = h * r; head side q = r * conj(t) with the imaginary
+// half negated.  Also records the shard-local index of the true candidate.
+__global__ void __launch_bounds__(256)
+hole_rank_pack_query_kernel(const float* __restrict__ table, int stride, int H,
+                            const int32_t* __restrict__ queries, int Q, int Qpad, int side,
+                            int64_t ent_begin, int K, __nv_bfloat16* __restrict__ out,
+                            int32_t* __restrict__ true_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t qi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (qi >= Qpad) return;
+  __nv_bfloat16* o = out + (size_t)qi * K;
+  if (qi >= Q) {
+    for (int k = lane; k < K; k += 32) o[k] = __float2bfloat16(0.f);
+    if (lane == 0) true_idx[qi] = -1;
+    return;
+  }
+  const int h = queries[3 * qi], t = queries[3 * qi + 1], r = queries[3 * qi + 2];
+  const int Hp = stride / 2;
+  const float* x1 = table + (size_t)(side == HOLE_SIDE_TAIL ? h : r) * stride;   // first factor
+  const float* x2 = table + (size_t)(side == HOLE_SIDE_TAIL ? r : t) * stride;   // second factor
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = lane; k < H; k += 32) {
+    float a = x1[k], b = x1[Hp + k], c = x2[k], d = x2[Hp + k];
+    s1 = fmaf(a, a, fmaf(b, b, s1));
+    s2 = fmaf(c, c, fmaf(d, d, s2));
+  }
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o2);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o2);
+  }
+  const float c1 = fminf(__frsqrt_rn(s1), 1.0f), c2 = fminf(__frsqrt_rn(s2), 1.0f);
+  for (int k = lane; k < K; k += 32) o[k] = __float2bfloat16(0.f);
+  __syncwarp();
+  for (int k = lane; k < H; k += 32) {
+    const float a = x1[k] * c1, b = x1[Hp + k] * c1, c = x2[k] * c2, d = x2[Hp + k] * c2;
+    float re, im;
+    if (side == HOLE_SIDE_TAIL) { re = a * c - b * d; im = a * d + b * c; }   // (a,b)=h (c,d)=r
+    else                        { re = a * c + b * d; im = a * d - b * c; }   // (a,b)=r (c,d)=t
+    o[k] = __float2bfloat16(re);
+    o[H + k] = __float2bfloat16(im);
+  }
+  if (lane == 0) true_idx[qi] = (int32_t)((int64_t)(side == HOLE_SIDE_TAIL ? t : h) - ent_begin);
+}
+
+// T[q] = packed candidate row of q's true candidate (zeros when it is not in this shard)
+__global__ void __launch_bounds__(256)
+hole_rank_gather_true_kernel(const __nv_bfloat16* __restrict__ cand, const int32_t* __restrict__ true_idx,
+                             int Nc, int rows, int K, __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t qi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (qi >= rows) return;
+  const int ti = true_idx[qi];
+  const bool ok = ti >= 0 && ti < Nc;
+  const uint4* src = reinterpret_cast<const uint4*>(cand + (size_t)(ok ? ti : 0) * K);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)qi * K);
+  for (int k = lane; k < K / 8; k += 32) dst[k] = ok ? src[k] : make_uint4(0, 0, 0, 0);
+}
+
+// Filtered counts: one warp per query walks its filter list (known-true candidates,
+// holE.py:454-461) and removes those that rank before the true one.  Scores are fp32 dot
+// products of the same bf16 operands (CUDA cores): identical to the tensor-core value except
+// for accumulation order, i.e. only exact near-ties can differ.
+__global__ void __launch_bounds__(256)
+hole_rank_filter_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ cand,
+                        int K, const int64_t* __restrict__ foff, const int32_t* __restrict__ fids,
+                        int64_t ent_begin, int Nc, const float* __restrict__ true_score,
+                        const int32_t* __restrict__ true_idx, int Q, int32_t* __restrict__ filt_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t qi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (qi >= Q) return;
+  const float thr = true_score[qi];
+  const int ti = true_idx[qi];
+  const __nv_bfloat16* qrow = qp + (size_t)qi * K;
+  int hits = 0;
+  for (int64_t p = foff[qi]; p < foff[qi + 1]; ++p) {
+    const int64_t j = (int64_t)fids[p] - ent_begin;
+    if (j < 0 || j >= Nc) continue;            // warp-uniform
+    const __nv_bfloat16* crow = cand + (size_t)j * K;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(__bfloat162float(qrow[k]), __bfloat162float(crow[k]), s);
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+    hits += (s < thr || (s == thr && j < ti)) ? 1 : 0;
+  }
+  if (lane == 0 && hits != 0) atomicSub(&filt_cnt[qi], hits);
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 [rows, K] row-major, box = 64 columns x box_rows rows, 128-byte swizzle
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return hole_set_error(HOLE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return hole_set_error(HOLE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return HOLE_OK;
+}
+
+}  // namespace
+
+struct hole_rank_ws {
+  __nv_bfloat16* cand = nullptr;   // [Npad, K]
+  __nv_bfloat16* qp = nullptr;     // [Qpad, K]
+  __nv_bfloat16* tq = nullptr;     // [Qpad + BN, K] gathered true rows
+  int32_t* true_idx = nullptr;     // [Qpad]
+  size_t cand_cap = 0, q_cap = 0;  // elements
+  bool attr_set = false;
+  int64_t last_npad = 0, last_qpad = 0;
+  int last_K = 0;
+};
+
+void hole_rank_ws_free(hole_ctx* c) {
+  if (c->rank == nullptr) return;
+  cudaFree(c->rank->cand); cudaFree(c->rank->qp); cudaFree(c->rank->tq); cudaFree(c->rank->true_idx);
+  delete c->rank;
+  c->rank = nullptr;
+}
+
+extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int64_t ent_end,
+                         const int32_t* queries, int64_t Q, int side, int precision,
+                         const int64_t* filter_off, const int32_t* filter_ids, float* true_score_io,
+                         int compute_true, int32_t* raw_before, int32_t* filt_before, void* stream) {
+  HOLE_CHECK_ARG(c && Q >= 0 && ent_begin >= 0 && ent_end >= ent_begin && ent_end <= c->n_rows);
+  HOLE_CHECK_ARG(side == HOLE_SIDE_TAIL || side == HOLE_SIDE_HEAD);
+  if (Q == 0 || ent_end == ent_begin) return HOLE_OK;
+  HOLE_CHECK_ARG(table && queries && true_score_io && raw_before && filt_before);
+  HOLE_CHECK_ARG((filter_off == nullptr) == (filter_ids == nullptr));
+  if (precision != HOLE_RANK_BF16)
+    return hole_set_error(HOLE_ERR_UNSUPPORTED, "ranking precision %d not built (only HOLE_RANK_BF16)", precision);
+  HOLE_CHECK_ARG(Q < (int64_t(1) << 30) && ent_end - ent_begin < (int64_t(1) << 30));
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+
+  const int Nc = (int)(ent_end - ent_begin);
+  const int K = (c->dim + BK - 1) / BK * BK;
+  const int num_kb = K / BK;
+  const int Npad = (Nc + BN - 1) / BN * BN;
+  const int Qpad = (int)((Q + BM - 1) / BM * BM);
+  const int a_bytes = num_kb * A_KB_BYTES;
+  int stages = (SMEM_LIMIT - a_bytes - 2048) / B_KB_BYTES;
+  stages = std::min(stages, MAX_STAGES);
+  if (stages < 2)
+    return hole_set_error(HOLE_ERR_UNSUPPORTED, "embedding_dim %d too large for the ranking kernel's smem budget", c->dim);
+  const int smem_bytes = a_bytes + stages * B_KB_BYTES + 2048;   // + alignment slack + barriers
+
+  if (c->rank == nullptr) c->rank = new hole_rank_ws();
+  hole_rank_ws* w = c->rank;
+  if ((size_t)Npad * K > w->cand_cap) {
+    HOLE_CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(w->cand); w->cand = nullptr; w->cand_cap = 0;
+    if (cudaMalloc((void**)&w->cand, (size_t)Npad * K * 2) != cudaSuccess) {
+      cudaGetLastError();
+      return hole_set_error(HOLE_ERR_ALLOC, "ranking candidate operand allocation failed");
+    }
+    w->cand_cap = (size_t)Npad * K;
+  }
+  if ((size_t)Qpad * K > w->q_cap) {
+    HOLE_CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(w->qp); cudaFree(w->tq); cudaFree(w->true_idx);
+    w->qp = w->tq = nullptr; w->true_idx = nullptr; w->q_cap = 0;
+    if (cudaMalloc((void**)&w->qp, (size_t)Qpad * K * 2) != cudaSuccess ||
+        cudaMalloc((void**)&w->tq, (size_t)(Qpad + BN) * K * 2) != cudaSuccess ||
+        cudaMalloc((void**)&w->true_idx, (size_t)Qpad * 4) != cudaSuccess) {
+      cudaGetLastError();
+      return hole_set_error(HOLE_ERR_ALLOC, "ranking query operand allocation failed");
+    }
+    w->q_cap = (size_t)Qpad * K;
+  }
+  if (!w->attr_set) {
+    HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    w->attr_set = true;
+  }
+
+  w->last_npad = Npad; w->last_qpad = Qpad; w->last_K = K;
+  // operands
+  hole_rank_pack_cand_kernel<<<(unsigned)((Npad + 7) / 8), 256, 0, st>>>(table, c->row_stride, c->H, ent_begin, Nc, Npad, K, w->cand);
+  HOLE_LAUNCHED();
+  hole_rank_pack_query_kernel<<<(unsigned)((Qpad + 7) / 8), 256, 0, st>>>(table, c->row_stride, c->H, queries, (int)Q, Qpad, side, ent_begin, K, w->qp, w->true_idx);
+  HOLE_LAUNCHED();
+
+  CUtensorMap mapA, mapB;
+  int rc = make_map(&mapA, w->qp, Qpad, K, BM);
+  if (rc) return rc;
+
+  RankParams p{};
+  p.num_kb = num_kb;
+  p.stages = stages;
+  p.m_tiles = Qpad / BM;
+  p.Q = (int)Q;
+  p.Nc = Nc;
+  p.true_idx = w->true_idx;
+
+  if (compute_true) {
+    const int rows = Qpad + BN;
+    hole_rank_gather_true_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w->cand, w->true_idx, Nc, Qpad, K, w->tq);
+    HOLE_LAUNCHED();
+    HOLE_CUDA_TRY(cudaMemsetAsync(w->tq + (size_t)Qpad * K, 0, (size_t)BN * K * 2, st));
+    rc = make_map(&mapB, w->tq, rows, K, BN);
+    if (rc) return rc;
+    p.mode = MODE_DIAG;
+    p.n_tiles = 1; p.chunk_tiles = 1; p.n_chunks = 1;
+    p.true_out = true_score_io;
+    const int grid = std::min(p.m_tiles, c->sm_count);
+    hole_rank_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    HOLE_LAUNCHED();
+  }
+
+  rc = make_map(&mapB, w->cand, Npad, K, BN);
+  if (rc) return rc;
+  p.mode = MODE_COUNT;
+  p.n_tiles = Npad / BN;
+  // work items: enough to balance the persistent CTAs, chunks of at least 8 candidate tiles
+  {
+    int want_items = 8 * c->sm_count;
+    int chunks = std::max(1, std::min(p.n_tiles / 8, (want_items + p.m_tiles - 1) / p.m_tiles));
+    p.chunk_tiles = (p.n_tiles + chunks - 1) / chunks;
+    p.n_chunks = (p.n_tiles + p.chunk_tiles - 1) / p.chunk_tiles;
+  }
+  p.true_score = true_score_io;
+  p.raw_cnt = raw_before;
+  p.filt_cnt = filt_before;
+  {
+    const int n_items = p.m_tiles * p.n_chunks;
+    const int grid = std::min(n_items, c->sm_count);
+    hole_rank_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    HOLE_LAUNCHED();
+  }
+  if (filter_off != nullptr) {
+    hole_rank_filter_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, st>>>(w->qp, w->cand, K, filter_off, filter_ids, ent_begin, Nc, true_score_io, w->true_idx, (int)Q, filt_before);
+    HOLE_LAUNCHED();
+  }
+  return HOLE_OK;
+}
+
+extern "C" int hole_rank_debug_operands(hole_ctx* c, void* cand_out, void* query_out, int64_t* n_pad,
+                                        int64_t* q_pad, int* K, void* stream) {
+  HOLE_CHECK_ARG(c && n_pad && q_pad && K);
+  if (c->rank == nullptr || c->rank->last_K == 0)
+    return hole_set_error(HOLE_ERR_ARG, "hole_rank has not been called on this context");
+  hole_rank_ws* w = c->rank;
+  *n_pad = w->last_npad; *q_pad = w->last_qpad; *K = w->last_K;
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  if (cand_out)
+    HOLE_CUDA_TRY(cudaMemcpyAsync(cand_out, w->cand, (size_t)w->last_npad * w->last_K * 2,
+                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (query_out)
+    HOLE_CUDA_TRY(cudaMemcpyAsync(query_out, w->qp, (size_t)w->last_qpad * w->last_K * 2,
+                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return HOLE_OK;
 }

@@ -779,6 +779,7 @@ extern "C" int hole_ctx_destroy(hole_ctx* c) {
     if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
   }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   delete c;
   return HOLE_OK;
 }
@@ -898,12 +899,52 @@ static int run_step(hole_ctx* c, float* table, const int32_t* pos, const int32_t
                     int64_t slot, cudaStream_t st) {
   const int M = (int)(4 * B);
   const size_t off = (size_t)slot * M;
+  cudaEvent_t* pe = nullptr;
+  if (c->profile) {
+    if (c->prof_used + 3 > c->prof_ev.size()) {
+      for (int q = 0; q < 3; ++q) {
+        cudaEvent_t e;
+        HOLE_CUDA_TRY(cudaEventCreate(&e));
+        c->prof_ev.push_back(e);
+      }
+    }
+    pe = &c->prof_ev[c->prof_used];
+    c->prof_used += 3;
+    HOLE_CUDA_TRY(cudaEventRecord(pe[0], st));
+  }
   HOLE_DISPATCH(c, hole_train_fwd_bwd_kernel, grid_for_groups(B, c->gs), 256, st, table, pos, neg,
                 c->uniq + off, side, B, c->nvec, c->row_stride, margin, lr, c->G, loss_out,
                 sigma_out);
+  if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[1], st));
   HOLE_DISPATCH(c, hole_apply_kernel, grid_for_groups(M, c->gs), 256, st, table, c->G,
                 c->skey + off, c->spos + off, c->sstart + off, c->slen + off, c->counters, M,
                 c->nvec, c->row_stride, lr);
+  if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[2], st));
+  return HOLE_OK;
+}
+
+extern "C" int hole_profile_enable(hole_ctx* c, int on) {
+  HOLE_CHECK_ARG(c != nullptr);
+  c->profile = on != 0;
+  c->prof_used = 0;
+  return HOLE_OK;
+}
+
+extern "C" int hole_profile_read(hole_ctx* c, double* k1_ms, double* k3_ms, int64_t* n_steps) {
+  HOLE_CHECK_ARG(c && k1_ms && k3_ms && n_steps);
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  HOLE_CUDA_TRY(cudaDeviceSynchronize());
+  double a = 0.0, b = 0.0;
+  for (size_t q = 0; q + 2 < c->prof_used + 0 && q + 2 < c->prof_ev.size() + 0; q += 3) {
+    float t1 = 0.f, t3 = 0.f;
+    HOLE_CUDA_TRY(cudaEventElapsedTime(&t1, c->prof_ev[q], c->prof_ev[q + 1]));
+    HOLE_CUDA_TRY(cudaEventElapsedTime(&t3, c->prof_ev[q + 1], c->prof_ev[q + 2]));
+    a += t1;
+    b += t3;
+  }
+  *k1_ms = a;
+  *k3_ms = b;
+  *n_steps = (int64_t)(c->prof_used / 3);
   return HOLE_OK;
 }
 

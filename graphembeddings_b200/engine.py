@@ -193,6 +193,28 @@ class HoleEngine:
                                  _stream()))
         return raw_before, filt_before, true_score
 
+    def rank_debug_operands(self):
+        """(candidate operand [n_pad, K], query operand [q_pad, K]) of the last rank() call as
+        bf16 CUDA tensors -- test hook."""
+        n, q, k = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        check(self.lib.hole_rank_debug_operands(self._ctx, None, None, C.byref(n), C.byref(q),
+                                                C.byref(k), _stream()))
+        cand = torch.empty((n.value, k.value), dtype=torch.bfloat16, device=self.device)
+        qp = torch.empty((q.value, k.value), dtype=torch.bfloat16, device=self.device)
+        check(self.lib.hole_rank_debug_operands(self._ctx, _ptr(cand), _ptr(qp), C.byref(n),
+                                                C.byref(q), C.byref(k), _stream()))
+        return cand, qp
+
+    def profile(self, on):
+        """Record CUDA events around K1/K3 of every following step (bench.py roofline)."""
+        check(self.lib.hole_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile_read(self):
+        """-> (k1_ms_total, k3_ms_total, n_steps) since profile(True)."""
+        a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+        check(self.lib.hole_profile_read(self._ctx, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     def launch_count(self):
         return int(self.lib.hole_launch_count())
 

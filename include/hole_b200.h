@@ -144,6 +144,19 @@ HOLE_API int hole_rank(hole_ctx* ctx, const float* table, int64_t ent_begin, int
               float* true_score_io, int compute_true,
               int32_t* raw_before, int32_t* filt_before, void* stream);
 
+/* Test hook: copy the bf16 operands the last hole_rank call packed (device to device).
+ * cand_out [n_pad, K] / query_out [q_pad, K] may be NULL to query the shapes only. */
+HOLE_API int hole_rank_debug_operands(hole_ctx* ctx, void* cand_out, void* query_out,
+                             int64_t* n_pad, int64_t* q_pad, int* K, void* stream);
+
+/* ---- measurement hooks (bench.py's roofline figure).  With profiling enabled every
+ * training step records CUDA events on `stream` around its two hot kernels (K1 =
+ * hole_train_fwd_bwd_kernel, K3 = hole_apply_kernel).  hole_profile_read synchronises and
+ * returns the summed kernel times in milliseconds and the number of steps measured since
+ * the last hole_profile_enable call. */
+HOLE_API int hole_profile_enable(hole_ctx* ctx, int on);
+HOLE_API int hole_profile_read(hole_ctx* ctx, double* k1_ms, double* k3_ms, int64_t* n_steps);
+
 /* Number of kernels this library has launched on this thread's contexts since the last
  * reset (bench.py's "gpu_launches"). */
 HOLE_API int64_t hole_launch_count(void);
