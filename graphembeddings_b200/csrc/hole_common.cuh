@@ -41,6 +41,25 @@ int hole_set_error(int code, const char* fmt, ...);
 // ---------------------------------------------------------------------------------------
 struct hole_rank_ws;   // hole_rank.cu
 
+// Update plan of a chunk of S steps (integer-only; built ahead of the steps that use it).
+struct hole_plan {
+  uint32_t* keysA = nullptr;     // [S][4B] sort ping (unsorted row keys are written here)
+  uint32_t* keysB = nullptr;     // [S][4B] sort pong
+  uint32_t* valsA = nullptr;
+  uint32_t* valsB = nullptr;
+  uint32_t* ghist = nullptr;     // [S][256][tiles] radix histograms
+  uint32_t* skey = nullptr;      // sorted keys (points into keysA or keysB)
+  uint32_t* spos = nullptr;      // sorted original positions (points into valsA or valsB)
+  uint8_t* uniq = nullptr;       // [S][4B] per ORIGINAL position: row occurs once in the step
+  uint4* heads = nullptr;        // [S][heads_cap] leaves of the combine trees {j, seg start, n, row}
+  int* nheads = nullptr;         // [S]
+  int32_t* neg = nullptr;        // [S*B] corrupt entity per triple
+  int heads_cap = 0;
+  cudaEvent_t ready = nullptr;     // recorded by the builder when the plan is complete
+  cudaEvent_t released = nullptr;  // recorded by the consumer when it no longer needs the plan
+  bool used = false;
+};
+
 struct hole_ctx {
   int device = 0;
   int64_t n_rows = 0;
@@ -55,27 +74,18 @@ struct hole_ctx {
   // ---- training workspace (grown on demand; owned by the context)
   int64_t cap_B = 0, cap_S = 0;
   float* G = nullptr;            // [4B, row_stride] staged gradient rows of ONE step
-  uint32_t* keysA = nullptr;     // [S][4B] sort ping
-  uint32_t* keysB = nullptr;     // [S][4B] sort pong
-  uint32_t* valsA = nullptr;
-  uint32_t* valsB = nullptr;
-  uint32_t* sstart = nullptr;    // [S][4B] segment start (sorted index) of each sorted entry
-  uint32_t* slen = nullptr;      // [S][4B] segment length, valid at segment starts
-  uint32_t* ghist = nullptr;     // [S][256][tiles] radix histograms
-  uint32_t* skey = nullptr;      // sorted keys (points into keysA or keysB)
-  uint32_t* spos = nullptr;      // sorted positions (points into valsA or valsB)
-  uint8_t* uniq = nullptr;       // [S][4B] per ORIGINAL position: row occurs once in the step
   int* counters = nullptr;       // [LEVELS][4B] tree-combine tickets (self-resetting)
-  int32_t* neg = nullptr;        // [S*B] corrupt entity per triple
   float* loss = nullptr;         // [S*B] scratch when the caller passes no loss_out
   float* loss_sum = nullptr;     // [S]
+  hole_plan plan[2];             // double-buffered: chunk c+1 is planned while chunk c trains
+  cudaStream_t plan_stream = nullptr;
+  cudaEvent_t ev_entry = nullptr;
   int32_t* triples_stage[2] = {nullptr, nullptr};  // device staging for the host-buffer path
   int64_t cap_stage = 0;
   float* loss_sum_pinned = nullptr;   // pinned host mirror of loss sums (e2e path)
   int64_t cap_pinned = 0;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
-  cudaEvent_t ev_done[2] = {nullptr, nullptr};
 
   hole_rank_ws* rank = nullptr;
 

@@ -330,13 +330,16 @@ hole_sort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* _
   }
 }
 
-// segments of the sorted keys: sstart[j] = first sorted index with the same row; slen at
-// segment starts; uniq[original position] = row occurs exactly once in the step (such rows
-// are updated in place by K1, nobody else reads them during the step).
+// Segments of the sorted keys.  uniq[original position] = row occurs exactly once in the
+// step (such rows are updated in place by K1; nobody else reads them during the step).
+// For rows that occur n >= 2 times, every sorted entry that heads a chunk of C occurrences
+// is appended to the step's compact work list heads[] = {sorted index, segment start, n, row}
+// (list order is irrelevant: each entry is an independent leaf of the combine tree).
 __global__ void __launch_bounds__(256)
 hole_plan_segments_kernel(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ spos,
-                          uint32_t* __restrict__ sstart, uint32_t* __restrict__ slen,
-                          uint8_t* __restrict__ uniq, int M) {
+                          uint8_t* __restrict__ uniq, uint4* __restrict__ heads,
+                          int* __restrict__ nheads, int M, int heads_cap) {
+  constexpr int C = HOLE_TREE_C;
   const size_t base = (size_t)blockIdx.y * M;
   const uint32_t* k = skey + base;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
@@ -344,6 +347,7 @@ hole_plan_segments_kernel(const uint32_t* __restrict__ skey, const uint32_t* __r
     const bool head = (j == 0) || (k[j - 1] != key);
     const bool last = (j == M - 1) || (k[j + 1] != key);
     uniq[base + spos[base + j]] = (head && last) ? 1 : 0;
+    if (head && last) continue;
     int s = j;
     if (!head) {          // lower_bound(key) in [0, j)
       int lo = 0, hi = j;
@@ -353,19 +357,18 @@ hole_plan_segments_kernel(const uint32_t* __restrict__ skey, const uint32_t* __r
       }
       s = lo;
     }
-    sstart[base + j] = (uint32_t)s;
-    if (head) {
-      int e = j + 1;
-      if (!last) {        // upper_bound(key) in (j, M)
-        int lo = j + 1, hi = M;
-        while (lo < hi) {
-          int mid = (lo + hi) >> 1;
-          if (k[mid] <= key) lo = mid + 1; else hi = mid;
-        }
-        e = lo;
+    if ((j - s) % C != 0) continue;
+    int e = j + 1;
+    if (!last) {          // upper_bound(key) in (j, M)
+      int lo = j + 1, hi = M;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (k[mid] <= key) lo = mid + 1; else hi = mid;
       }
-      slen[base + j] = (uint32_t)(e - j);
+      e = lo;
     }
+    const int slot = atomicAdd(&nheads[blockIdx.y], 1);
+    heads[(size_t)blockIdx.y * heads_cap + slot] = make_uint4((uint32_t)j, (uint32_t)s, (uint32_t)(e - s), key);
   }
 }
 
@@ -598,24 +601,19 @@ __device__ __forceinline__ void sum_rows(Row<V>& acc, const float* __restrict__ 
 
 template <int GS, int V>
 __global__ void __launch_bounds__(256)
-hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint32_t* __restrict__ skey,
-                  const uint32_t* __restrict__ spos, const uint32_t* __restrict__ sstart,
-                  const uint32_t* __restrict__ slen, int* __restrict__ counters, int M, int nvec,
-                  int stride, float lr) {
+hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint32_t* __restrict__ spos,
+                  const uint4* __restrict__ heads, const int* __restrict__ nheads,
+                  int* __restrict__ counters, int M, int nvec, int stride, float lr) {
   constexpr int C = HOLE_TREE_C;
   static_assert(C <= 2 * GS, "index broadcast assumes C <= 2*GS");
   const int lane = threadIdx.x % GS;
   const int gbase = (threadIdx.x % 32) / GS * GS;
   const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << gbase);
-  const int64_t j64 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
-  if (j64 >= M) return;
-  const int j = (int)j64;
-  const int s = (int)sstart[j];
+  const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
+  if (g >= *nheads) return;
+  const uint4 hd = heads[g];
+  const int j = (int)hd.x, s = (int)hd.y, n = (int)hd.z, row = (int)hd.w;
   const int rel = j - s;
-  if (rel % C != 0) return;
-  const int n = (int)slen[s];
-  if (n == 1) return;              // updated in place by K1
-  const int row = (int)skey[j];
   const int cnt = min(C, n - rel);
 
   Row<V> acc;
@@ -748,21 +746,30 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
   while ((int64_t(1) << bits) < n_rows) ++bits;
   c->key_bits = bits;
   HOLE_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  HOLE_CUDA_TRY(cudaStreamCreateWithFlags(&c->plan_stream, cudaStreamNonBlocking));
+  HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
   for (int k = 0; k < 2; ++k) {
     HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming));
-    HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+    HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->plan[k].ready, cudaEventDisableTiming));
+    HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->plan[k].released, cudaEventDisableTiming));
   }
   *out = c;
   return HOLE_OK;
 }
 
+static void plan_free(hole_plan& p) {
+  cudaFree(p.keysA); cudaFree(p.keysB); cudaFree(p.valsA); cudaFree(p.valsB);
+  cudaFree(p.uniq); cudaFree(p.heads); cudaFree(p.nheads); cudaFree(p.neg); cudaFree(p.ghist);
+  p.keysA = p.keysB = p.valsA = p.valsB = nullptr;
+  p.uniq = nullptr; p.heads = nullptr; p.nheads = nullptr; p.neg = nullptr; p.ghist = nullptr;
+  p.skey = p.spos = nullptr;
+}
+
 static void ws_free(hole_ctx* c) {
-  cudaFree(c->G); cudaFree(c->keysA); cudaFree(c->keysB); cudaFree(c->valsA); cudaFree(c->valsB);
-  cudaFree(c->sstart); cudaFree(c->slen); cudaFree(c->counters); cudaFree(c->neg);
-  cudaFree(c->loss); cudaFree(c->loss_sum); cudaFree(c->uniq); cudaFree(c->ghist);
-  c->uniq = nullptr; c->ghist = nullptr; c->skey = c->spos = nullptr;
-  c->G = nullptr; c->keysA = c->keysB = c->valsA = c->valsB = c->sstart = c->slen = nullptr;
-  c->counters = nullptr; c->neg = nullptr; c->loss = nullptr; c->loss_sum = nullptr;
+  cudaFree(c->G); cudaFree(c->counters); cudaFree(c->loss); cudaFree(c->loss_sum);
+  c->G = nullptr; c->counters = nullptr; c->loss = nullptr; c->loss_sum = nullptr;
+  plan_free(c->plan[0]);
+  plan_free(c->plan[1]);
   c->cap_B = c->cap_S = 0;
 }
 
@@ -776,15 +783,18 @@ extern "C" int hole_ctx_destroy(hole_ctx* c) {
   if (c->loss_sum_pinned) cudaFreeHost(c->loss_sum_pinned);
   for (int k = 0; k < 2; ++k) {
     if (c->ev_copy[k]) cudaEventDestroy(c->ev_copy[k]);
-    if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+    if (c->plan[k].ready) cudaEventDestroy(c->plan[k].ready);
+    if (c->plan[k].released) cudaEventDestroy(c->plan[k].released);
   }
+  if (c->ev_entry) cudaEventDestroy(c->ev_entry);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->plan_stream) cudaStreamDestroy(c->plan_stream);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   delete c;
   return HOLE_OK;
 }
 
-// Workspace for S steps of batch B.  Reallocation synchronises the device.
+// Workspace for chunks of S steps of batch B.  Reallocation synchronises the device.
 int hole_ws_reserve(hole_ctx* c, int64_t B, int64_t S) {
   if (B <= c->cap_B && S <= c->cap_S) return HOLE_OK;
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
@@ -793,6 +803,7 @@ int hole_ws_reserve(hole_ctx* c, int64_t B, int64_t S) {
   S = std::max(S, c->cap_S);
   ws_free(c);
   const size_t M = (size_t)4 * B;
+  const size_t tiles = (M + ST_TILE - 1) / ST_TILE;
 #define WS_ALLOC(ptr, bytes)                                                             \
   do {                                                                                   \
     if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) {                            \
@@ -802,15 +813,20 @@ int hole_ws_reserve(hole_ctx* c, int64_t B, int64_t S) {
     }                                                                                    \
   } while (0)
   WS_ALLOC(c->G, M * c->row_stride * sizeof(float));
-  WS_ALLOC(c->keysA, S * M * 4); WS_ALLOC(c->keysB, S * M * 4);
-  WS_ALLOC(c->valsA, S * M * 4); WS_ALLOC(c->valsB, S * M * 4);
-  WS_ALLOC(c->sstart, S * M * 4); WS_ALLOC(c->slen, S * M * 4);
   WS_ALLOC(c->counters, (size_t)HOLE_TREE_LEVELS * M * 4);
-  WS_ALLOC(c->neg, (size_t)S * B * 4);
   WS_ALLOC(c->loss, (size_t)S * B * 4);
   WS_ALLOC(c->loss_sum, (size_t)S * 4);
-  WS_ALLOC(c->uniq, S * M);
-  WS_ALLOC(c->ghist, (size_t)S * 256 * ((M + ST_TILE - 1) / ST_TILE) * 4);
+  for (int k = 0; k < 2; ++k) {
+    hole_plan& p = c->plan[k];
+    WS_ALLOC(p.keysA, S * M * 4); WS_ALLOC(p.keysB, S * M * 4);
+    WS_ALLOC(p.valsA, S * M * 4); WS_ALLOC(p.valsB, S * M * 4);
+    WS_ALLOC(p.uniq, S * M);
+    WS_ALLOC(p.heads, (size_t)S * (M / 2 + 1) * sizeof(uint4));
+    WS_ALLOC(p.nheads, (size_t)S * 4);
+    WS_ALLOC(p.neg, (size_t)S * B * 4);
+    WS_ALLOC(p.ghist, (size_t)S * 256 * tiles * 4);
+    p.used = false;
+  }
 #undef WS_ALLOC
   HOLE_CUDA_TRY(cudaMemset(c->counters, 0, (size_t)HOLE_TREE_LEVELS * M * 4));
   c->cap_B = B;
@@ -867,35 +883,52 @@ extern "C" int hole_score(hole_ctx* c, const float* table, const int32_t* triple
   return HOLE_OK;
 }
 
-// Plan S steps whose unsorted keys are in keysA[S][M]: stable radix sort by row, then
-// segments.  On return ctx->skey / ctx->spos point at the sorted pairs.
-static int build_plan(hole_ctx* c, int64_t S, int M, cudaStream_t st) {
+// Sort + segment S steps whose unsorted keys are in pl.keysA[S][M] (stream-ordered on st).
+static int build_plan(hole_ctx* c, hole_plan& pl, int64_t S, int M, cudaStream_t st) {
   const int passes = (c->key_bits + 7) / 8;
   const int P = (M + ST_TILE - 1) / ST_TILE;
-  uint32_t *kin = c->keysA, *vin = nullptr, *kout = c->keysB, *vout = c->valsB;
+  uint32_t *kin = pl.keysA, *vin = nullptr, *kout = pl.keysB, *vout = pl.valsB;
   dim3 grid((unsigned)P, (unsigned)S);
   for (int pass = 0; pass < passes; ++pass) {
-    hole_sort_hist_kernel<<<grid, ST_THREADS, 0, st>>>(kin, c->ghist, M, P, 8 * pass);
+    hole_sort_hist_kernel<<<grid, ST_THREADS, 0, st>>>(kin, pl.ghist, M, P, 8 * pass);
     HOLE_LAUNCHED();
-    hole_sort_scan_kernel<<<(unsigned)S, 256, 0, st>>>(c->ghist, P);
+    hole_sort_scan_kernel<<<(unsigned)S, 256, 0, st>>>(pl.ghist, P);
     HOLE_LAUNCHED();
-    hole_sort_scatter_kernel<<<grid, ST_THREADS, 0, st>>>(kin, vin, kout, vout, c->ghist, M, P, 8 * pass);
+    hole_sort_scatter_kernel<<<grid, ST_THREADS, 0, st>>>(kin, vin, kout, vout, pl.ghist, M, P, 8 * pass);
     HOLE_LAUNCHED();
-    uint32_t* nk = (kout == c->keysB) ? c->keysA : c->keysB;
-    uint32_t* nv = (vout == c->valsB) ? c->valsA : c->valsB;
+    uint32_t* nk = (kout == pl.keysB) ? pl.keysA : pl.keysB;
+    uint32_t* nv = (vout == pl.valsB) ? pl.valsA : pl.valsB;
     kin = kout; vin = vout; kout = nk; vout = nv;
   }
-  c->skey = kin;
-  c->spos = vin;
+  pl.skey = kin;
+  pl.spos = vin;
+  pl.heads_cap = M / 2 + 1;
+  HOLE_CUDA_TRY(cudaMemsetAsync(pl.nheads, 0, (size_t)S * 4, st));
   dim3 sgrid((unsigned)std::min<int64_t>((M + 255) / 256, 1024), (unsigned)S);
-  hole_plan_segments_kernel<<<sgrid, 256, 0, st>>>(c->skey, c->spos, c->sstart, c->slen, c->uniq, M);
+  hole_plan_segments_kernel<<<sgrid, 256, 0, st>>>(pl.skey, pl.spos, pl.uniq, pl.heads, pl.nheads, M,
+                                                  pl.heads_cap);
   HOLE_LAUNCHED();
   return HOLE_OK;
 }
 
-// K1 + K3 of one step whose plan (sorted keys, segments) is at plan slot `slot`.
-static int run_step(hole_ctx* c, float* table, const int32_t* pos, const int32_t* neg, int side,
-                    int64_t B, float margin, float lr, float* loss_out, float* sigma_out,
+// Corruption + plan for S steps, enqueued on `ps` (the plan stream, or the caller's stream).
+static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, int64_t B, int64_t S,
+                      const int32_t* type_of, const int64_t* csr_off, const int32_t* csr_ids,
+                      uint64_t seed, uint64_t first_step, cudaStream_t ps) {
+  if (pl.used) HOLE_CUDA_TRY(cudaStreamWaitEvent(ps, pl.released, 0));   // last consumer is done
+  dim3 grid((unsigned)std::min<int64_t>((B + 255) / 256, 4096), (unsigned)S);
+  hole_corrupt_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, (int)S, type_of, csr_off, csr_ids, seed,
+                                            first_step, pl.neg, nullptr, pl.keysA);
+  HOLE_LAUNCHED();
+  int rc = build_plan(c, pl, S, (int)(4 * B), ps);
+  if (rc) return rc;
+  HOLE_CUDA_TRY(cudaEventRecord(pl.ready, ps));
+  return HOLE_OK;
+}
+
+// K1 + K3 of one step whose plan is slot `slot` of pl.
+static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos, const int32_t* neg,
+                    int side, int64_t B, float margin, float lr, float* loss_out, float* sigma_out,
                     int64_t slot, cudaStream_t st) {
   const int M = (int)(4 * B);
   const size_t off = (size_t)slot * M;
@@ -913,11 +946,11 @@ static int run_step(hole_ctx* c, float* table, const int32_t* pos, const int32_t
     HOLE_CUDA_TRY(cudaEventRecord(pe[0], st));
   }
   HOLE_DISPATCH(c, hole_train_fwd_bwd_kernel, grid_for_groups(B, c->gs), 256, st, table, pos, neg,
-                c->uniq + off, side, B, c->nvec, c->row_stride, margin, lr, c->G, loss_out,
+                pl.uniq + off, side, B, c->nvec, c->row_stride, margin, lr, c->G, loss_out,
                 sigma_out);
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[1], st));
-  HOLE_DISPATCH(c, hole_apply_kernel, grid_for_groups(M, c->gs), 256, st, table, c->G,
-                c->skey + off, c->spos + off, c->sstart + off, c->slen + off, c->counters, M,
+  HOLE_DISPATCH(c, hole_apply_kernel, grid_for_groups(pl.heads_cap, c->gs), 256, st, table, c->G,
+                pl.spos + off, pl.heads + (size_t)slot * pl.heads_cap, pl.nheads + slot, c->counters, M,
                 c->nvec, c->row_stride, lr);
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[2], st));
   return HOLE_OK;
@@ -935,7 +968,7 @@ extern "C" int hole_profile_read(hole_ctx* c, double* k1_ms, double* k3_ms, int6
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   HOLE_CUDA_TRY(cudaDeviceSynchronize());
   double a = 0.0, b = 0.0;
-  for (size_t q = 0; q + 2 < c->prof_used + 0 && q + 2 < c->prof_ev.size() + 0; q += 3) {
+  for (size_t q = 0; q + 2 < c->prof_used && q + 2 < c->prof_ev.size(); q += 3) {
     float t1 = 0.f, t3 = 0.f;
     HOLE_CUDA_TRY(cudaEventElapsedTime(&t1, c->prof_ev[q], c->prof_ev[q + 1]));
     HOLE_CUDA_TRY(cudaEventElapsedTime(&t3, c->prof_ev[q + 1], c->prof_ev[q + 2]));
@@ -959,39 +992,34 @@ extern "C" int hole_train_step(hole_ctx* c, float* table, const int32_t* pos, co
   int rc = hole_ws_reserve(c, B, 1);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  hole_keys_kernel<<<(unsigned)std::min<int64_t>((B + 255) / 256, 65535), 256, 0, st>>>(pos, neg_ent, B, c->keysA);
+  hole_plan& pl = c->plan[0];
+  if (pl.used) HOLE_CUDA_TRY(cudaStreamWaitEvent(st, pl.released, 0));
+  hole_keys_kernel<<<(unsigned)std::min<int64_t>((B + 255) / 256, 65535), 256, 0, st>>>(pos, neg_ent, B, pl.keysA);
   HOLE_LAUNCHED();
-  {
-    int rc2 = build_plan(c, 1, (int)(4 * B), st);
-    if (rc2) return rc2;
-  }
-  return run_step(c, table, pos, neg_ent, side, B, margin, lr, loss_out, sigma_out, 0, st);
+  rc = build_plan(c, pl, 1, (int)(4 * B), st);
+  if (rc) return rc;
+  rc = run_step(c, pl, table, pos, neg_ent, side, B, margin, lr, loss_out, sigma_out, 0, st);
+  if (rc) return rc;
+  pl.used = true;
+  HOLE_CUDA_TRY(cudaEventRecord(pl.released, st));
+  return HOLE_OK;
 }
 
-// chunk size (steps planned at once): enough CTAs for the sort to fill the GPU, bounded
-// workspace
-static int64_t plan_chunk(const hole_ctx* c, int64_t B, int64_t n_steps) {
-  int64_t by_mem = std::max<int64_t>(1, (int64_t(1) << 26) / (4 * B));   // <= 64M plan entries
-  return std::max<int64_t>(1, std::min<int64_t>({n_steps, (int64_t)2 * c->sm_count, by_mem}));
+// steps planned per chunk: enough blocks for the plan kernels to fill the GPU, bounded memory
+// (a function of B only, so that the workspace is sized once per batch size)
+static int64_t plan_chunk(int64_t B) {
+  const int64_t M = 4 * B;
+  return std::max<int64_t>(32, std::min<int64_t>(256, (int64_t(1) << 23) / M));
 }
 
-static int train_chunk(hole_ctx* c, float* table, const int32_t* triples_dev, int64_t B, int64_t S,
-                       const int32_t* type_of, const int64_t* csr_off, const int32_t* csr_ids,
-                       uint64_t seed, uint64_t first_step, float margin, const float* lr_host,
-                       float* loss_out /*[S*B] device*/, float* loss_sum_dev /*[S] device or null*/,
-                       cudaStream_t st) {
-  const int M = (int)(4 * B);
-  dim3 grid((unsigned)std::min<int64_t>((B + 255) / 256, 4096), (unsigned)S);
-  hole_corrupt_kernel<<<grid, 256, 0, st>>>(triples_dev, B, (int)S, type_of, csr_off, csr_ids, seed,
-                                            first_step, c->neg, nullptr, c->keysA);
-  HOLE_LAUNCHED();
-  {
-    int rc2 = build_plan(c, S, M, st);
-    if (rc2) return rc2;
-  }
+// the S steps of one planned chunk on the compute stream
+static int run_chunk(hole_ctx* c, hole_plan& pl, float* table, const int32_t* triples_dev, int64_t B,
+                     int64_t S, uint64_t seed, uint64_t first_step, float margin, const float* lr_host,
+                     float* loss_out, float* loss_sum_dev, cudaStream_t st) {
+  HOLE_CUDA_TRY(cudaStreamWaitEvent(st, pl.ready, 0));
   for (int64_t k = 0; k < S; ++k) {
     int side = hole_side_coin(seed, first_step + (uint64_t)k);
-    int rc = run_step(c, table, triples_dev + (size_t)k * B * 3, c->neg + (size_t)k * B, side, B,
+    int rc = run_step(c, pl, table, triples_dev + (size_t)k * B * 3, pl.neg + (size_t)k * B, side, B,
                       margin, lr_host[k], loss_out + (size_t)k * B, nullptr, k, st);
     if (rc) return rc;
   }
@@ -999,6 +1027,8 @@ static int train_chunk(hole_ctx* c, float* table, const int32_t* triples_dev, in
     hole_loss_sum_kernel<<<(unsigned)S, 256, 0, st>>>(loss_out, B, loss_sum_dev);
     HOLE_LAUNCHED();
   }
+  pl.used = true;
+  HOLE_CUDA_TRY(cudaEventRecord(pl.released, st));
   return HOLE_OK;
 }
 
@@ -1012,16 +1042,29 @@ extern "C" int hole_train_steps(hole_ctx* c, float* table, const int32_t* triple
   HOLE_CHECK_ARG(table && triples && type_of && csr_off && csr_ids && lr);
   HOLE_CHECK_ARG(4 * B < (int64_t(1) << 31));
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
-  const int64_t S = plan_chunk(c, B, n_steps);
+  const int64_t S = plan_chunk(B);
   int rc = hole_ws_reserve(c, B, S);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  for (int64_t k0 = 0; k0 < n_steps; k0 += S) {
-    const int64_t s = std::min(S, n_steps - k0);
+  // the plan stream may only read the caller's triples once the caller's stream got here
+  HOLE_CUDA_TRY(cudaEventRecord(c->ev_entry, st));
+  HOLE_CUDA_TRY(cudaStreamWaitEvent(c->plan_stream, c->ev_entry, 0));
+  const int64_t nchunks = (n_steps + S - 1) / S;
+  rc = plan_steps(c, c->plan[0], triples, B, std::min(S, n_steps), type_of, csr_off, csr_ids, seed,
+                  first_step, c->plan_stream);
+  if (rc) return rc;
+  for (int64_t ci = 0; ci < nchunks; ++ci) {
+    const int64_t k0 = ci * S, s = std::min(S, n_steps - k0);
+    if (ci + 1 < nchunks) {   // plan the next chunk while this one trains
+      const int64_t k1 = k0 + S, s1 = std::min(S, n_steps - k1);
+      rc = plan_steps(c, c->plan[(ci + 1) & 1], triples + (size_t)k1 * B * 3, B, s1, type_of, csr_off,
+                      csr_ids, seed, first_step + (uint64_t)k1, c->plan_stream);
+      if (rc) return rc;
+    }
     float* lo = loss_out ? loss_out + (size_t)k0 * B : c->loss;
-    rc = train_chunk(c, table, triples + (size_t)k0 * B * 3, B, s, type_of, csr_off, csr_ids, seed,
-                     first_step + (uint64_t)k0, margin, lr + k0, lo,
-                     loss_sum_out ? loss_sum_out + k0 : nullptr, st);
+    rc = run_chunk(c, c->plan[ci & 1], table, triples + (size_t)k0 * B * 3, B, s, seed,
+                   first_step + (uint64_t)k0, margin, lr + k0, lo,
+                   loss_sum_out ? loss_sum_out + k0 : nullptr, st);
     if (rc) return rc;
   }
   return HOLE_OK;
@@ -1037,7 +1080,7 @@ extern "C" int hole_train_steps_host(hole_ctx* c, float* table, const int32_t* t
   HOLE_CHECK_ARG(table && triples_host && type_of && csr_off && csr_ids && lr && loss_sum_host);
   HOLE_CHECK_ARG(4 * B < (int64_t(1) << 31));
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
-  const int64_t S = plan_chunk(c, B, n_steps);
+  const int64_t S = plan_chunk(B);
   int rc = hole_ws_reserve(c, B, S);
   if (rc) return rc;
   const int64_t stage_elems = S * B * 3;
@@ -1061,23 +1104,37 @@ extern "C" int hole_train_steps_host(hole_ctx* c, float* table, const int32_t* t
     c->cap_pinned = n_steps;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  // copy stream must not overtake work already queued on the compute stream that still
-  // reads a staging buffer: ev_done[b] guards buffer b.
-  int64_t nchunks = (n_steps + S - 1) / S;
-  for (int64_t ci = 0; ci < nchunks; ++ci) {
+  HOLE_CUDA_TRY(cudaEventRecord(c->ev_entry, st));
+  HOLE_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0));
+  const int64_t nchunks = (n_steps + S - 1) / S;
+  // chunk ci: H2D copy into staging buffer ci&1 (copy stream) -> plan (plan stream) -> steps
+  // (caller's stream).  Staging buffer b is free again when plan[b].released fires.
+  auto stage_and_plan = [&](int64_t ci) -> int {
     const int b = (int)(ci & 1);
     const int64_t k0 = ci * S, s = std::min(S, n_steps - k0);
-    if (ci >= 2) HOLE_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+    if (c->plan[b].used) HOLE_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->plan[b].released, 0));
     HOLE_CUDA_TRY(cudaMemcpyAsync(c->triples_stage[b], triples_host + (size_t)k0 * B * 3,
                                   (size_t)s * B * 3 * 4, cudaMemcpyHostToDevice, c->copy_stream));
     HOLE_CUDA_TRY(cudaEventRecord(c->ev_copy[b], c->copy_stream));
-    HOLE_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copy[b], 0));
-    rc = train_chunk(c, table, c->triples_stage[b], B, s, type_of, csr_off, csr_ids, seed,
-                     first_step + (uint64_t)k0, margin, lr + k0, c->loss, c->loss_sum, st);
+    HOLE_CUDA_TRY(cudaStreamWaitEvent(c->plan_stream, c->ev_copy[b], 0));
+    return plan_steps(c, c->plan[b], c->triples_stage[b], B, s, type_of, csr_off, csr_ids, seed,
+                      first_step + (uint64_t)k0, c->plan_stream);
+  };
+  rc = stage_and_plan(0);
+  if (rc) return rc;
+  for (int64_t ci = 0; ci < nchunks; ++ci) {
+    const int b = (int)(ci & 1);
+    const int64_t k0 = ci * S, s = std::min(S, n_steps - k0);
+    if (ci + 1 < nchunks) {
+      rc = stage_and_plan(ci + 1);
+      if (rc) return rc;
+    }
+    rc = run_chunk(c, c->plan[b], table, c->triples_stage[b], B, s, seed, first_step + (uint64_t)k0,
+                   margin, lr + k0, c->loss, c->loss_sum, st);
     if (rc) return rc;
     HOLE_CUDA_TRY(cudaMemcpyAsync(c->loss_sum_pinned + k0, c->loss_sum, (size_t)s * 4,
                                   cudaMemcpyDeviceToHost, st));
-    HOLE_CUDA_TRY(cudaEventRecord(c->ev_done[b], st));
+    // the next chunk's loss_sum kernel is ordered after this copy on st
   }
   HOLE_CUDA_TRY(cudaStreamSynchronize(st));
   for (int64_t k = 0; k < n_steps; ++k) loss_sum_host[k] = c->loss_sum_pinned[k];

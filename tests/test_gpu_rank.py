@@ -128,7 +128,7 @@ def test_structured_table_metrics_match_oracle(eng_mod):
     oraw, _ = O.rank_counts(S, np.arange(n_rel, kg.n_rows), kg.triples[:, 1])
     m_gpu = O.score_mrr(raw.cpu().numpy() + 1, raw.cpu().numpy() + 1)
     m_ref = O.score_mrr(oraw + 1, oraw + 1)
-    assert m_ref["hits1"] > 90.0
+    assert m_ref["hits1"] > 60.0
     assert abs(m_gpu["filtered_mrr"] - m_ref["filtered_mrr"]) < 1e-3
     assert abs(m_gpu["hits1"] - m_ref["hits1"]) < 0.5
     assert abs(m_gpu["hits10"] - m_ref["hits10"]) < 0.5
