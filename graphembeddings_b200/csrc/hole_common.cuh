@@ -54,7 +54,9 @@ struct hole_plan {
   uint4* heads = nullptr;        // [S][heads_cap] leaves of the combine trees {j, seg start, n, row}
   int* nheads = nullptr;         // [S]
   int32_t* neg = nullptr;        // [S*B] corrupt entity per triple
+  int32_t* perm = nullptr;       // [S*B] triples grouped by relation (K1's processing order)
   int heads_cap = 0;
+  int T = 1;                     // triples per K1 lane group
   cudaEvent_t ready = nullptr;     // recorded by the builder when the plan is complete
   cudaEvent_t released = nullptr;  // recorded by the consumer when it no longer needs the plan
   bool used = false;
@@ -70,6 +72,9 @@ struct hole_ctx {
   int gs = 0, v = 0;   // lanes per row and float4s per lane per half (kernel variant)
   int sm_count = 0;
   int key_bits = 0;    // bits needed for a row id
+  int k1_smem = 0;     // dynamic shared memory of K1 (row landing buffers)
+  int row_passes = 1;  // 8-bit radix passes for row keys
+  int rel_passes = 1;  // ... for relation ids (hole_ctx_set_relations)
 
   // ---- training workspace (grown on demand; owned by the context)
   int64_t cap_B = 0, cap_S = 0;

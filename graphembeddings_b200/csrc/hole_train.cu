@@ -151,15 +151,16 @@ __global__ void hole_unpack_rows_kernel(const float* __restrict__ src, float* __
 // ---------------------------------------------------------------------------------------
 // K2: corruption sampler + update-plan keys
 // ---------------------------------------------------------------------------------------
-// For step s (grid.y) and triple i: neg = csr_ids[off[ty] + draw]; emits the four
-// (row, position) sort keys of the step: position = slot*B + i with slots
-// [relation, tail-slot, head-slot, corrupt entity].
+constexpr uint32_t HOLE_KEY_ABSENT = 0xFFFFFFFFu;   // sorts after every real row id
+
+// Stand-alone sampler (hole_corrupt): for step s (grid.y) and triple i,
+// neg = csr_ids[off[ty] + draw] with ty the type of the replaced entity.
 __global__ void hole_corrupt_kernel(const int32_t* __restrict__ triples, int64_t B, int n_steps,
                                     const int32_t* __restrict__ type_of,
                                     const int64_t* __restrict__ csr_off,
                                     const int32_t* __restrict__ csr_ids, uint64_t seed,
                                     uint64_t first_step, int32_t* __restrict__ neg_out,
-                                    int32_t* __restrict__ side_out, uint32_t* __restrict__ keys) {
+                                    int32_t* __restrict__ side_out) {
   int s = blockIdx.y;
   uint64_t step = first_step + (uint64_t)s;
   int side = hole_side_coin(seed, step);
@@ -167,33 +168,60 @@ __global__ void hole_corrupt_kernel(const int32_t* __restrict__ triples, int64_t
   const int32_t* tr = triples + (size_t)s * B * 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int h = tr[3 * i], t = tr[3 * i + 1], r = tr[3 * i + 2];
-    int ent = side ? h : t;
+    int ent = side ? tr[3 * i] : tr[3 * i + 1];
     int ty = type_of[ent];
     int64_t lo = csr_off[ty];
     uint32_t cnt = (uint32_t)(csr_off[ty + 1] - lo);
-    uint32_t j = hole_entity_draw(seed, step, (uint32_t)i, cnt);
-    int n = csr_ids[lo + j];
-    neg_out[(size_t)s * B + i] = n;
-    if (keys != nullptr) {
-      uint32_t* k = keys + (size_t)s * 4 * B;
-      k[i] = (uint32_t)r;
-      k[B + i] = (uint32_t)t;
-      k[2 * B + i] = (uint32_t)h;
-      k[3 * B + i] = (uint32_t)n;
-    }
+    neg_out[(size_t)s * B + i] = csr_ids[lo + hole_entity_draw(seed, step, (uint32_t)i, cnt)];
   }
 }
 
-// Keys for a caller-supplied corruption (hole_train_step).
-__global__ void hole_keys_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ neg,
-                                 int64_t B, uint32_t* __restrict__ k) {
+// relation id of every triple: the key of the per-step "group by relation" sort
+__global__ void hole_rel_keys_kernel(const int32_t* __restrict__ triples, int64_t B,
+                                     uint32_t* __restrict__ relkeys) {
+  const size_t base = (size_t)blockIdx.y * B;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    k[i] = (uint32_t)pos[3 * i + 2];
-    k[B + i] = (uint32_t)pos[3 * i + 1];
-    k[2 * B + i] = (uint32_t)pos[3 * i];
-    k[3 * B + i] = (uint32_t)neg[i];
+       i += (int64_t)gridDim.x * blockDim.x)
+    relkeys[base + i] = (uint32_t)triples[(base + i) * 3 + 2];
+}
+
+// For step s and position g of the relation-grouped order: i = perm[g]; draws (or takes) the
+// corrupt entity and emits the step's four (row, position) sort keys, position = slot*B + i
+// with slots [relation, tail-slot, head-slot, corrupt entity].  K1 gives T consecutive
+// positions to one lane group and pre-sums the relation gradient over runs of equal relation
+// inside that range, so only the first triple of such a run carries a relation key.
+__global__ void hole_plan_keys_kernel(const int32_t* __restrict__ triples, int64_t B, int T,
+                                      const int32_t* __restrict__ perm,
+                                      const int32_t* __restrict__ type_of,
+                                      const int64_t* __restrict__ csr_off,
+                                      const int32_t* __restrict__ csr_ids, uint64_t seed,
+                                      uint64_t first_step, const int32_t* __restrict__ neg_in,
+                                      int32_t* __restrict__ neg_out, uint32_t* __restrict__ keys) {
+  const int s = blockIdx.y;
+  const uint64_t step = first_step + (uint64_t)s;
+  const int side = hole_side_coin(seed, step);
+  const int32_t* tr = triples + (size_t)s * B * 3;
+  const int32_t* pm = perm + (size_t)s * B;
+  uint32_t* k = keys + (size_t)s * 4 * B;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < B;
+       g += (int64_t)gridDim.x * blockDim.x) {
+    const int i = pm[g];
+    const int h = tr[3 * i], t = tr[3 * i + 1], r = tr[3 * i + 2];
+    int n;
+    if (neg_in != nullptr) {
+      n = neg_in[(size_t)s * B + i];
+    } else {
+      const int ty = type_of[side ? h : t];
+      const int64_t lo = csr_off[ty];
+      const uint32_t cnt = (uint32_t)(csr_off[ty + 1] - lo);
+      n = csr_ids[lo + hole_entity_draw(seed, step, (uint32_t)i, cnt)];
+      neg_out[(size_t)s * B + i] = n;
+    }
+    const bool run_head = (g % T == 0) || (tr[3 * pm[g - 1] + 2] != r);
+    k[i] = run_head ? (uint32_t)r : HOLE_KEY_ABSENT;
+    k[B + i] = (uint32_t)t;
+    k[2 * B + i] = (uint32_t)h;
+    k[3 * B + i] = (uint32_t)n;
   }
 }
 
@@ -344,6 +372,7 @@ hole_plan_segments_kernel(const uint32_t* __restrict__ skey, const uint32_t* __r
   const uint32_t* k = skey + base;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
     const uint32_t key = k[j];
+    if (key == HOLE_KEY_ABSENT) continue;      // relation use folded into its run's first triple
     const bool head = (j == 0) || (k[j - 1] != key);
     const bool last = (j == M - 1) || (k[j + 1] != key);
     uniq[base + spos[base + j]] = (head && last) ? 1 : 0;
@@ -403,40 +432,127 @@ hole_score_kernel(const float* __restrict__ E, const int32_t* __restrict__ tripl
 }
 
 // ---------------------------------------------------------------------------------------
-// K1: fused forward + backward of one batch.  One group of GS lanes per positive triple.
-// For each of the triple's four rows [relation, tail-slot, head-slot, corrupt entity]
-// (rows shared by the positive and the negative triple get the sum of both contributions;
-// the clip backward is linear in the incoming gradient, so merging before it is exact in
-// real arithmetic):
+// K1: fused forward + backward of one batch.
+// A group of GS lanes walks T consecutive triples of the step's relation-grouped order
+// (perm), software-pipelined: the next triple's three entity rows are in flight while the
+// current one is computed; the relation row is loaded once per run of equal relation and
+// its gradient is summed over the run in registers.
+// For each row a triple touches [relation, tail-slot, head-slot, corrupt entity] (rows
+// shared by the positive and the negative triple get the sum of both contributions; the
+// clip backward is linear in the incoming gradient, so merging before it is exact in real
+// arithmetic):
 //   * if the row occurs exactly once in this step (uniq flag from the plan) nobody else
 //     reads it during the step, so it is updated in place: E[row] = x - lr * dx;
-//   * otherwise the gradient row is staged at G[slot*B + i] for K3.
-// The four rows are emitted one after the other to keep the register footprint at
-// (4 input rows + 1 gradient row).
+//   * otherwise the gradient row is staged in G (at slot*B + i; for a relation run at the
+//     position of the run's first triple) for K3.
 // ---------------------------------------------------------------------------------------
-enum { ROLE_R = 0, ROLE_T = 1, ROLE_H = 2, ROLE_N = 3 };
+enum { ROLE_T = 1, ROLE_H = 2, ROLE_N = 3 };
 
+template <int GS>
+__device__ __forceinline__ float group_sum_m(float v, unsigned gmask) {
+#pragma unroll
+  for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+
+template <int V>
+__device__ __forceinline__ void row_zero(Row<V>& x) {
+#pragma unroll
+  for (int k = 0; k < 4 * V; ++k) { x.re[k] = 0.f; x.im[k] = 0.f; }
+}
+template <int V>
+__device__ __forceinline__ void row_add(Row<V>& acc, const Row<V>& x) {
+#pragma unroll
+  for (int k = 0; k < 4 * V; ++k) { acc.re[k] += x.re[k]; acc.im[k] += x.im[k]; }
+}
+
+// Asynchronous row fetch into a per-lane landing buffer in shared memory: lane l copies
+// exactly the float4s it will later read itself, so no cross-lane synchronisation is
+// needed -- shared memory only holds the bytes in flight instead of registers.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int GS, int V>
+__device__ __forceinline__ void row_fetch_async(float4* sdst, const float* grow, int lane, int nvec) {
+  const float4* p = reinterpret_cast<const float4*>(grow);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int idx = lane + v * GS;
+    if (idx < nvec) {
+      cp_async16(sdst + idx, p + idx);
+      cp_async16(sdst + nvec + idx, p + nvec + idx);
+    }
+  }
+}
+template <int GS, int V>
+__device__ __forceinline__ void row_from_smem(Row<V>& x, const float4* ssrc, int lane, int nvec) {
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int idx = lane + v * GS;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (idx < nvec) { a = ssrc[idx]; b = ssrc[nvec + idx]; }
+    x.re[4 * v + 0] = a.x; x.re[4 * v + 1] = a.y; x.re[4 * v + 2] = a.z; x.re[4 * v + 3] = a.w;
+    x.im[4 * v + 0] = b.x; x.im[4 * v + 1] = b.y; x.im[4 * v + 2] = b.z; x.im[4 * v + 3] = b.w;
+  }
+}
+
+// through the norm clip (App. A.3): dx = clipped ? (dy - y (y.dy)) * inv : dy (y = clipped
+// row); then in place (unique row: E[row] = x - lr dx, x = y / s recovered as y * rs where
+// rs = 1/s is exact for the unclipped case s == 1) or staged.
+// xraw: the unscaled row as it was fetched (landing buffer), used for the in-place update.
+template <int GS, int V>
+__device__ __forceinline__ void finish_row(Row<V>& d, const Row<V>& y, const float4* xraw,
+                                           float inv_self, bool uniq, bool act, float lr,
+                                           float* erow, float* grow, int lane, int nvec,
+                                           unsigned gmask) {
+  if (inv_self <= 1.0f) {          // group-uniform
+    float proj = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) proj = fmaf(y.re[k], d.re[k], fmaf(y.im[k], d.im[k], proj));
+    proj = group_sum_m<GS>(proj, gmask);
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) {
+      d.re[k] = (d.re[k] - y.re[k] * proj) * inv_self;
+      d.im[k] = (d.im[k] - y.im[k] * proj) * inv_self;
+    }
+  }
+  if (uniq) {
+    if (act) {                     // inactive hinge: zero gradient, row unchanged
+      Row<V> x;
+      row_from_smem<GS, V>(x, xraw, lane, nvec);
+#pragma unroll
+      for (int k = 0; k < 4 * V; ++k) {
+        d.re[k] = x.re[k] - lr * d.re[k];
+        d.im[k] = x.im[k] - lr * d.im[k];
+      }
+      row_store<GS, V>(d, erow, lane, nvec);
+    }
+  } else {
+    row_store<GS, V>(d, grow, lane, nvec);
+  }
+}
+
+// yh, yt, yr, yn: the clipped rows (y = x * s)
 template <int GS, int V, int ROLE>
-__device__ __forceinline__ void emit_row(const Row<V>& xh, const Row<V>& xt, const Row<V>& xr,
-                                         const Row<V>& xn, float sh, float st, float sr, float sn,
-                                         float inv_self, int side, float gp, float gn, bool uniq,
-                                         bool act, float lr, float* erow, float* grow, int lane,
-                                         int nvec, bool valid) {
+__device__ __forceinline__ void emit_row(const Row<V>& yh, const Row<V>& yt, const Row<V>& yr,
+                                         const Row<V>& yn, const float4* xraw, float inv_self,
+                                         int side, float gp, float gn, bool uniq, bool act, float lr,
+                                         float* erow, float* grow, int lane, int nvec,
+                                         unsigned gmask) {
   Row<V> d;
-  float proj = 0.f;
-  const Row<V>& xs = (ROLE == ROLE_R) ? xr : (ROLE == ROLE_T) ? xt : (ROLE == ROLE_H) ? xh : xn;
-  const float ss = (ROLE == ROLE_R) ? sr : (ROLE == ROLE_T) ? st : (ROLE == ROLE_H) ? sh : sn;
+  const Row<V>& ys = (ROLE == ROLE_T) ? yt : (ROLE == ROLE_H) ? yh : yn;
 #pragma unroll
   for (int k = 0; k < 4 * V; ++k) {
-    const float a = xh.re[k] * sh, b = xh.im[k] * sh, c = xr.re[k] * sr, dd = xr.im[k] * sr,
-                e = xt.re[k] * st, f = xt.im[k] * st;
-    const float nr = xn.re[k] * sn, ni = xn.im[k] * sn;
+    const float a = yh.re[k], b = yh.im[k], c = yr.re[k], dd = yr.im[k], e = yt.re[k], f = yt.im[k];
+    const float nr = yn.re[k], ni = yn.im[k];
     float gre, gim;
-    if (ROLE == ROLE_R) {          // d/dr = g+ [a e + b f ; a f - b e] + g- [same with the negative's h,t]
-      const float a2 = side ? nr : a, b2 = side ? ni : b, e2 = side ? e : nr, f2 = side ? f : ni;
-      gre = gp * (a * e + b * f) + gn * (a2 * e2 + b2 * f2);
-      gim = gp * (a * f - b * e) + gn * (a2 * f2 - b2 * e2);
-    } else if (ROLE == ROLE_T) {   // d/dt = g [a c - b d ; a d + b c]
+    if (ROLE == ROLE_T) {          // d/dt = g [a c - b d ; a d + b c]
       gre = gp * (a * c - b * dd);
       gim = gp * (a * dd + b * c);
       if (side) {                  // negative (n, t, r) shares t
@@ -456,102 +572,170 @@ __device__ __forceinline__ void emit_row(const Row<V>& xh, const Row<V>& xt, con
     }
     d.re[k] = gre;
     d.im[k] = gim;
-    proj = fmaf(xs.re[k] * ss, gre, fmaf(xs.im[k] * ss, gim, proj));
   }
-  // through the norm clip: dx = clipped ? (dy - y (y.dy)) * inv : dy, y = x * s   (App. A.3)
-  if (inv_self <= 1.0f) {          // group-uniform
-    proj = group_sum<GS>(proj);
-#pragma unroll
-    for (int k = 0; k < 4 * V; ++k) {
-      d.re[k] = (d.re[k] - (xs.re[k] * ss) * proj) * inv_self;
-      d.im[k] = (d.im[k] - (xs.im[k] * ss) * proj) * inv_self;
-    }
-  }
-  if (!valid) return;
-  if (uniq) {
-    if (act) {                     // inactive hinge: zero gradient, row unchanged
-#pragma unroll
-      for (int k = 0; k < 4 * V; ++k) {
-        d.re[k] = xs.re[k] - lr * d.re[k];
-        d.im[k] = xs.im[k] - lr * d.im[k];
-      }
-      row_store<GS, V>(d, erow, lane, nvec);
-    }
-  } else {
-    row_store<GS, V>(d, grow, lane, nvec);
-  }
+  finish_row<GS, V>(d, ys, xraw, inv_self, uniq, act, lr, erow, grow, lane, nvec, gmask);
 }
+
+struct TripleIds { int i, h, t, r, n; };
+
+__device__ __forceinline__ TripleIds load_ids(const int32_t* __restrict__ tri,
+                                              const int32_t* __restrict__ neg,
+                                              const int32_t* __restrict__ perm, int g) {
+  TripleIds d;
+  d.i = perm[g];
+  d.h = tri[3 * d.i]; d.t = tri[3 * d.i + 1]; d.r = tri[3 * d.i + 2];
+  d.n = neg[d.i];
+  return d;
+}
+
+constexpr int K1_STAGES = 3;   // landing buffers per lane group: the triple being computed (its
+                               // unscaled rows are re-read for the in-place update) + 2 in flight
 
 template <int GS, int V>
 __global__ void __launch_bounds__(256)
-hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ pos,
-                          const int32_t* __restrict__ neg, const uint8_t* __restrict__ uniq,
-                          int side, int64_t B, int nvec, int stride, float margin, float lr,
-                          float* __restrict__ G, float* __restrict__ loss,
-                          float* __restrict__ sigma) {
+hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri,
+                          const int32_t* __restrict__ neg, const int32_t* __restrict__ perm,
+                          const uint8_t* __restrict__ uniq, int side, int B, int T, int nvec,
+                          int stride, float margin, float lr, float* __restrict__ G,
+                          float* __restrict__ loss, float* __restrict__ sigma) {
+  extern __shared__ float4 k1_smem[];
   const int lane = threadIdx.x % GS;
-  int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
-  const bool valid = g < B;
-  const int64_t i = valid ? g : B - 1;
-  const int h = pos[3 * i], t = pos[3 * i + 1], r = pos[3 * i + 2], n = neg[i];
-  const bool uq_r = uniq[i] != 0, uq_t = uniq[B + i] != 0, uq_h = uniq[2 * B + i] != 0,
-             uq_n = uniq[3 * B + i] != 0;
+  const int gbase = (threadIdx.x % 32) / GS * GS;
+  const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << gbase);
+  const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
+  const int64_t g0l = w * T;
+  if (g0l >= B) return;
+  const int g0 = (int)g0l, g1 = min(B, g0 + T);
+  const int row4 = 2 * nvec;                                   // float4s per row
+  // per lane group: K1_STAGES x {h, t, n} landing rows, then one row for the relation
+  float4* my_smem = k1_smem + (size_t)(threadIdx.x / GS) * ((K1_STAGES * 3 + 1) * row4);
+  float4* rel_smem = my_smem + (size_t)K1_STAGES * 3 * row4;
 
-  // unscaled rows stay in registers (needed again for the in-place update); y = x * s
-  Row<V> xh, xt, xr, xn;
-  row_load<GS, V, false>(xh, E + (size_t)h * stride, lane, nvec);
-  row_load<GS, V, false>(xt, E + (size_t)t * stride, lane, nvec);
-  row_load<GS, V, false>(xr, E + (size_t)r * stride, lane, nvec);
-  row_load<GS, V, false>(xn, E + (size_t)n * stride, lane, nvec);
+  auto fetch = [&](const TripleIds& d, int stage) {
+    float4* sb = my_smem + (size_t)stage * 3 * row4;
+    row_fetch_async<GS, V>(sb, E + (size_t)d.h * stride, lane, nvec);
+    row_fetch_async<GS, V>(sb + row4, E + (size_t)d.t * stride, lane, nvec);
+    row_fetch_async<GS, V>(sb + 2 * row4, E + (size_t)d.n * stride, lane, nvec);
+  };
 
-  float ssh = row_sumsq(xh), sst = row_sumsq(xt), ssr = row_sumsq(xr), ssn = row_sumsq(xn);
-#pragma unroll
-  for (int o = GS / 2; o > 0; o >>= 1) {
-    ssh += __shfl_xor_sync(0xffffffffu, ssh, o);
-    sst += __shfl_xor_sync(0xffffffffu, sst, o);
-    ssr += __shfl_xor_sync(0xffffffffu, ssr, o);
-    ssn += __shfl_xor_sync(0xffffffffu, ssn, o);
-  }
-  // clip_by_norm(row, 1): y = x * min(rsqrt(sum x^2), 1)  (App. B)
-  const float ih = __frsqrt_rn(ssh), it = __frsqrt_rn(sst), ir = __frsqrt_rn(ssr),
-              in_ = __frsqrt_rn(ssn);
-  const float sh = fminf(ih, 1.0f), st_ = fminf(it, 1.0f), sr = fminf(ir, 1.0f),
-              sn_ = fminf(in_, 1.0f);
+  TripleIds c = load_ids(tri, neg, perm, g0);
+  TripleIds n1 = (g0 + 1 < g1) ? load_ids(tri, neg, perm, g0 + 1) : c;
+  TripleIds n2 = (g0 + 2 < g1) ? load_ids(tri, neg, perm, g0 + 2) : c;
+  fetch(c, 0);
+  cp_async_commit();
+  if (g0 + 1 < g1) fetch(n1, 1);
+  cp_async_commit();
 
-  // scores: s = sum (a c - b d) e + (a d + b c) f   with h=(a,b) r=(c,d) t=(e,f)
-  float sp = 0.f, sn = 0.f;
+  Row<V> yh, yt, yn, yr, acc;
+  row_zero(yr);
+  row_zero(acc);
+  int r_cur = -1, run_i = 0;
+  float ir = 0.f;
+  bool run_act = false;
+
+  // end of a run of equal relation: clip backward of the summed gradient, then apply / stage
+  auto flush_relation = [&]() {
+    finish_row<GS, V>(acc, yr, rel_smem, ir, uniq[run_i] != 0, run_act, lr,
+                      E + (size_t)r_cur * stride, G + (size_t)run_i * stride, lane, nvec, gmask);
+  };
+
+  int stage = 0;
+  for (int g = g0; g < g1; ++g) {
+    TripleIds n3 = n2;
+    if (g + 3 < g1) n3 = load_ids(tri, neg, perm, g + 3);      // ids three ahead
+    if (g + 2 < g1) fetch(n2, (stage + 2) % K1_STAGES);         // rows two ahead
+    cp_async_commit();
+    cp_async_wait<2>();                                         // rows of triple g have landed
+    const float4* sb = my_smem + (size_t)stage * 3 * row4;
+    row_from_smem<GS, V>(yh, sb, lane, nvec);
+    row_from_smem<GS, V>(yt, sb + row4, lane, nvec);
+    row_from_smem<GS, V>(yn, sb + 2 * row4, lane, nvec);
+
+    if (c.r != r_cur) {                      // group-uniform
+      if (r_cur >= 0) flush_relation();
+      // the relation row: fetched synchronously once per run, unscaled copy kept in smem
+      row_load<GS, V, false>(yr, E + (size_t)c.r * stride, lane, nvec);
+      {
+        float4* rs = rel_smem;
 #pragma unroll
-  for (int k = 0; k < 4 * V; ++k) {
-    const float a = xh.re[k] * sh, b = xh.im[k] * sh, c = xr.re[k] * sr, d = xr.im[k] * sr,
-                e = xt.re[k] * st_, f = xt.im[k] * st_;
-    const float nr = xn.re[k] * sn_, ni = xn.im[k] * sn_;
-    const float pr = a * c - b * d, pi = a * d + b * c;
-    sp += pr * e + pi * f;
-    if (side) sn += (nr * c - ni * d) * e + (nr * d + ni * c) * f;   // negative = (n, t, r)
-    else      sn += pr * nr + pi * ni;                               // negative = (h, n, r)
-  }
+        for (int v = 0; v < V; ++v) {
+          const int idx = lane + v * GS;
+          if (idx < nvec) {
+            rs[idx] = make_float4(yr.re[4 * v], yr.re[4 * v + 1], yr.re[4 * v + 2], yr.re[4 * v + 3]);
+            rs[nvec + idx] = make_float4(yr.im[4 * v], yr.im[4 * v + 1], yr.im[4 * v + 2], yr.im[4 * v + 3]);
+          }
+        }
+      }
+      ir = __frsqrt_rn(group_sum_m<GS>(row_sumsq(yr), gmask));
+      row_clip(yr, ir);
+      r_cur = c.r;
+      run_i = c.i;
+      run_act = false;
+      row_zero(acc);
+    }
+    const int i = c.i;
+    const bool uq_t = uniq[B + i] != 0, uq_h = uniq[2 * B + i] != 0, uq_n = uniq[3 * B + i] != 0;
+
+    float ssh = row_sumsq(yh), sst = row_sumsq(yt), ssn = row_sumsq(yn);
 #pragma unroll
-  for (int o = GS / 2; o > 0; o >>= 1) {
-    sp += __shfl_xor_sync(0xffffffffu, sp, o);
-    sn += __shfl_xor_sync(0xffffffffu, sn, o);
+    for (int o = GS / 2; o > 0; o >>= 1) {
+      ssh += __shfl_xor_sync(gmask, ssh, o);
+      sst += __shfl_xor_sync(gmask, sst, o);
+      ssn += __shfl_xor_sync(gmask, ssn, o);
+    }
+    // clip_by_norm(row, 1): y = x * min(rsqrt(sum x^2), 1)  (App. B)
+    const float ih = __frsqrt_rn(ssh), it = __frsqrt_rn(sst), in_ = __frsqrt_rn(ssn);
+    row_clip(yh, ih); row_clip(yt, it); row_clip(yn, in_);
+
+    // scores: s = sum (a c - b d) e + (a d + b c) f   with h=(a,b) r=(c,d) t=(e,f)
+    float sp = 0.f, sn = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) {
+      const float a = yh.re[k], b = yh.im[k], cc = yr.re[k], d = yr.im[k], e = yt.re[k], f = yt.im[k];
+      const float nr = yn.re[k], ni = yn.im[k];
+      const float pr = a * cc - b * d, pi = a * d + b * cc;
+      sp += pr * e + pi * f;
+      if (side) sn += (nr * cc - ni * d) * e + (nr * d + ni * cc) * f;   // negative = (n, t, r)
+      else      sn += pr * nr + pi * ni;                                 // negative = (h, n, r)
+    }
+#pragma unroll
+    for (int o = GS / 2; o > 0; o >>= 1) {
+      sp += __shfl_xor_sync(gmask, sp, o);
+      sn += __shfl_xor_sync(gmask, sn, o);
+    }
+    const float vp = sigmoidf_precise(sp), vn = sigmoidf_precise(sn);
+    const float pre = vp - vn + margin;
+    const bool act = pre >= 0.0f;                       // TF Maximum grad: GreaterEqual
+    const float gp = act ? vp * (1.0f - vp) : 0.0f;
+    const float gn = act ? -(vn * (1.0f - vn)) : 0.0f;
+    if (lane == 0) {
+      loss[i] = fmaxf(pre, 0.0f);
+      if (sigma != nullptr) { sigma[i] = vp; sigma[B + i] = vn; }
+    }
+    run_act = run_act || act;
+    // relation gradient, summed over the run before the clip backward:
+    // d/dr = g+ [a e + b f ; a f - b e] + g- [same with the negative's h, t]
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) {
+      const float a = yh.re[k], b = yh.im[k], e = yt.re[k], f = yt.im[k];
+      const float nr = yn.re[k], ni = yn.im[k];
+      const float a2 = side ? nr : a, b2 = side ? ni : b, e2 = side ? e : nr, f2 = side ? f : ni;
+      acc.re[k] += gp * (a * e + b * f) + gn * (a2 * e2 + b2 * f2);
+      acc.im[k] += gp * (a * f - b * e) + gn * (a2 * f2 - b2 * e2);
+    }
+    emit_row<GS, V, ROLE_T>(yh, yt, yr, yn, sb + row4, it, side, gp, gn, uq_t, act, lr,
+                            E + (size_t)c.t * stride, G + (size_t)(1 * (int64_t)B + i) * stride, lane, nvec, gmask);
+    emit_row<GS, V, ROLE_H>(yh, yt, yr, yn, sb, ih, side, gp, gn, uq_h, act, lr,
+                            E + (size_t)c.h * stride, G + (size_t)(2 * (int64_t)B + i) * stride, lane, nvec, gmask);
+    emit_row<GS, V, ROLE_N>(yh, yt, yr, yn, sb + 2 * row4, in_, side, gp, gn, uq_n, act, lr,
+                            E + (size_t)c.n * stride, G + (size_t)(3 * (int64_t)B + i) * stride, lane, nvec, gmask);
+    c = n1;
+    n1 = n2;
+    n2 = n3;
+    stage = (stage + 1) % K1_STAGES;
   }
-  const float vp = sigmoidf_precise(sp), vn = sigmoidf_precise(sn);
-  const float pre = vp - vn + margin;
-  const bool act = pre >= 0.0f;                       // TF Maximum grad: GreaterEqual
-  const float gp = act ? vp * (1.0f - vp) : 0.0f;
-  const float gn = act ? -(vn * (1.0f - vn)) : 0.0f;
-  if (valid && lane == 0) {
-    loss[i] = fmaxf(pre, 0.0f);
-    if (sigma != nullptr) { sigma[i] = vp; sigma[B + i] = vn; }
-  }
-  emit_row<GS, V, ROLE_R>(xh, xt, xr, xn, sh, st_, sr, sn_, ir, side, gp, gn, uq_r, act, lr,
-                          E + (size_t)r * stride, G + (size_t)(0 * B + i) * stride, lane, nvec, valid);
-  emit_row<GS, V, ROLE_T>(xh, xt, xr, xn, sh, st_, sr, sn_, it, side, gp, gn, uq_t, act, lr,
-                          E + (size_t)t * stride, G + (size_t)(1 * B + i) * stride, lane, nvec, valid);
-  emit_row<GS, V, ROLE_H>(xh, xt, xr, xn, sh, st_, sr, sn_, ih, side, gp, gn, uq_h, act, lr,
-                          E + (size_t)h * stride, G + (size_t)(2 * B + i) * stride, lane, nvec, valid);
-  emit_row<GS, V, ROLE_N>(xh, xt, xr, xn, sh, st_, sr, sn_, in_, side, gp, gn, uq_n, act, lr,
-                          E + (size_t)n * stride, G + (size_t)(3 * B + i) * stride, lane, nvec, valid);
+  cp_async_wait<0>();
+  flush_relation();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -562,16 +746,6 @@ hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ pos
 // children combines them in child order, so the result does not depend on scheduling.
 // Partials reuse the (already consumed) staged gradient row of a node's first occurrence.
 // ---------------------------------------------------------------------------------------
-template <int V>
-__device__ __forceinline__ void row_zero(Row<V>& x) {
-#pragma unroll
-  for (int k = 0; k < 4 * V; ++k) { x.re[k] = 0.f; x.im[k] = 0.f; }
-}
-template <int V>
-__device__ __forceinline__ void row_add(Row<V>& acc, const Row<V>& x) {
-#pragma unroll
-  for (int k = 0; k < 4 * V; ++k) { acc.re[k] += x.re[k]; acc.im[k] += x.im[k]; }
-}
 
 // acc = sum over q < cnt (<= C) of the staged rows G[idx(q)], in q order, with the loads of
 // NB rows in flight at a time.  idx0/idx1 hold this lane's share of the row indices:
@@ -682,17 +856,19 @@ hole_loss_sum_kernel(const float* __restrict__ loss, int64_t B, float* __restric
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-#define HOLE_DISPATCH(ctx, KERNEL, grid, block, stream, ...)                                 \
+#define HOLE_DISPATCH_SMEM(ctx, KERNEL, grid, block, smem, stream, ...)                      \
   do {                                                                                       \
-    if ((ctx)->gs == 8 && (ctx)->v == 1) KERNEL<8, 1><<<grid, block, 0, stream>>>(__VA_ARGS__);          \
-    else if ((ctx)->gs == 16 && (ctx)->v == 1) KERNEL<16, 1><<<grid, block, 0, stream>>>(__VA_ARGS__);   \
-    else if ((ctx)->gs == 32 && (ctx)->v == 1) KERNEL<32, 1><<<grid, block, 0, stream>>>(__VA_ARGS__);   \
-    else if ((ctx)->gs == 32 && (ctx)->v == 2) KERNEL<32, 2><<<grid, block, 0, stream>>>(__VA_ARGS__);   \
-    else if ((ctx)->gs == 32 && (ctx)->v == 3) KERNEL<32, 3><<<grid, block, 0, stream>>>(__VA_ARGS__);   \
+    if ((ctx)->gs == 8 && (ctx)->v == 1) KERNEL<8, 1><<<grid, block, smem, stream>>>(__VA_ARGS__);          \
+    else if ((ctx)->gs == 16 && (ctx)->v == 1) KERNEL<16, 1><<<grid, block, smem, stream>>>(__VA_ARGS__);   \
+    else if ((ctx)->gs == 32 && (ctx)->v == 1) KERNEL<32, 1><<<grid, block, smem, stream>>>(__VA_ARGS__);   \
+    else if ((ctx)->gs == 32 && (ctx)->v == 2) KERNEL<32, 2><<<grid, block, smem, stream>>>(__VA_ARGS__);   \
+    else if ((ctx)->gs == 32 && (ctx)->v == 3) KERNEL<32, 3><<<grid, block, smem, stream>>>(__VA_ARGS__);   \
     else return hole_set_error(HOLE_ERR_UNSUPPORTED, "no kernel variant for gs=%d v=%d",     \
                                (ctx)->gs, (ctx)->v);                                         \
     HOLE_LAUNCHED();                                                                         \
   } while (0)
+#define HOLE_DISPATCH(ctx, KERNEL, grid, block, stream, ...) \
+  HOLE_DISPATCH_SMEM(ctx, KERNEL, grid, block, 0, stream, __VA_ARGS__)
 
 static inline unsigned grid_for_groups(int64_t groups, int gs, int block = 256) {
   int64_t per_block = block / gs;
@@ -745,6 +921,25 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
   int bits = 1;
   while ((int64_t(1) << bits) < n_rows) ++bits;
   c->key_bits = bits;
+  // radix passes: smallest p with 2^(8p) - 1 >= n_rows, so the "absent" key's low bits sort last
+  c->row_passes = 1;
+  while (((int64_t(1) << (8 * c->row_passes)) - 1) < n_rows) ++c->row_passes;
+  c->rel_passes = c->row_passes;
+  // K1 landing buffers: K1_STAGES triples x 3 entity rows + 1 relation row per lane group
+  c->k1_smem = (256 / c->gs) * (K1_STAGES * 3 + 1) * c->row_stride * (int)sizeof(float);
+  {
+    cudaError_t ea = cudaSuccess;
+    if (c->gs == 8) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+    else if (c->gs == 16) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+    else if (c->v == 1) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+    else if (c->v == 2) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+    else ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+    if (ea != cudaSuccess) {
+      const int want = c->k1_smem;
+      delete c;
+      return hole_set_error(HOLE_ERR_CUDA, "cudaFuncSetAttribute(K1 smem %d) -> %s", want, cudaGetErrorString(ea));
+    }
+  }
   HOLE_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   HOLE_CUDA_TRY(cudaStreamCreateWithFlags(&c->plan_stream, cudaStreamNonBlocking));
   HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
@@ -759,7 +954,8 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
 
 static void plan_free(hole_plan& p) {
   cudaFree(p.keysA); cudaFree(p.keysB); cudaFree(p.valsA); cudaFree(p.valsB);
-  cudaFree(p.uniq); cudaFree(p.heads); cudaFree(p.nheads); cudaFree(p.neg); cudaFree(p.ghist);
+  cudaFree(p.uniq); cudaFree(p.heads); cudaFree(p.nheads); cudaFree(p.neg); cudaFree(p.ghist); cudaFree(p.perm);
+  p.perm = nullptr;
   p.keysA = p.keysB = p.valsA = p.valsB = nullptr;
   p.uniq = nullptr; p.heads = nullptr; p.nheads = nullptr; p.neg = nullptr; p.ghist = nullptr;
   p.skey = p.spos = nullptr;
@@ -771,6 +967,13 @@ static void ws_free(hole_ctx* c) {
   plan_free(c->plan[0]);
   plan_free(c->plan[1]);
   c->cap_B = c->cap_S = 0;
+}
+
+extern "C" int hole_ctx_set_relations(hole_ctx* c, int64_t n_relations) {
+  HOLE_CHECK_ARG(c && n_relations > 0 && n_relations <= c->n_rows);
+  c->rel_passes = 1;
+  while (((int64_t(1) << (8 * c->rel_passes)) - 1) < n_relations) ++c->rel_passes;
+  return HOLE_OK;
 }
 
 extern "C" int hole_ctx_destroy(hole_ctx* c) {
@@ -824,6 +1027,7 @@ int hole_ws_reserve(hole_ctx* c, int64_t B, int64_t S) {
     WS_ALLOC(p.heads, (size_t)S * (M / 2 + 1) * sizeof(uint4));
     WS_ALLOC(p.nheads, (size_t)S * 4);
     WS_ALLOC(p.neg, (size_t)S * B * 4);
+    WS_ALLOC(p.perm, (size_t)S * B * 4);
     WS_ALLOC(p.ghist, (size_t)S * 256 * tiles * 4);
     p.used = false;
   }
@@ -867,7 +1071,7 @@ extern "C" int hole_corrupt(hole_ctx* c, const int32_t* triples, int64_t B, cons
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   dim3 grid((unsigned)std::min<int64_t>((B + 255) / 256, 65535), 1);
   hole_corrupt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(triples, B, 1, type_of, csr_off, csr_ids,
-                                                              seed, step, neg_out, side_out, nullptr);
+                                                              seed, step, neg_out, side_out);
   HOLE_LAUNCHED();
   return HOLE_OK;
 }
@@ -883,45 +1087,69 @@ extern "C" int hole_score(hole_ctx* c, const float* table, const int32_t* triple
   return HOLE_OK;
 }
 
-// Sort + segment S steps whose unsorted keys are in pl.keysA[S][M] (stream-ordered on st).
-static int build_plan(hole_ctx* c, hole_plan& pl, int64_t S, int M, cudaStream_t st) {
-  const int passes = (c->key_bits + 7) / 8;
+// Stable LSD radix sort of S independent arrays of M (key, value = original index) pairs.
+// Keys start in kA (destroyed); kB, vA, vB are scratch; the last pass writes the values to
+// v_final when given.  Returns where the sorted keys / values ended up.
+static int radix_sort(hole_plan& pl, uint32_t* kA, uint32_t* kB, uint32_t* vA, uint32_t* vB,
+                      uint32_t* v_final, int64_t S, int M, int passes, cudaStream_t st,
+                      uint32_t** k_out, uint32_t** v_out) {
   const int P = (M + ST_TILE - 1) / ST_TILE;
-  uint32_t *kin = pl.keysA, *vin = nullptr, *kout = pl.keysB, *vout = pl.valsB;
+  uint32_t *kin = kA, *vin = nullptr, *kout = kB, *vout = vB;
   dim3 grid((unsigned)P, (unsigned)S);
   for (int pass = 0; pass < passes; ++pass) {
+    if (pass == passes - 1 && v_final != nullptr) vout = v_final;
     hole_sort_hist_kernel<<<grid, ST_THREADS, 0, st>>>(kin, pl.ghist, M, P, 8 * pass);
     HOLE_LAUNCHED();
     hole_sort_scan_kernel<<<(unsigned)S, 256, 0, st>>>(pl.ghist, P);
     HOLE_LAUNCHED();
     hole_sort_scatter_kernel<<<grid, ST_THREADS, 0, st>>>(kin, vin, kout, vout, pl.ghist, M, P, 8 * pass);
     HOLE_LAUNCHED();
-    uint32_t* nk = (kout == pl.keysB) ? pl.keysA : pl.keysB;
-    uint32_t* nv = (vout == pl.valsB) ? pl.valsA : pl.valsB;
+    uint32_t* nk = (kout == kB) ? kA : kB;
+    uint32_t* nv = (vout == vB) ? vA : vB;
     kin = kout; vin = vout; kout = nk; vout = nv;
   }
-  pl.skey = kin;
-  pl.spos = vin;
-  pl.heads_cap = M / 2 + 1;
-  HOLE_CUDA_TRY(cudaMemsetAsync(pl.nheads, 0, (size_t)S * 4, st));
-  dim3 sgrid((unsigned)std::min<int64_t>((M + 255) / 256, 1024), (unsigned)S);
-  hole_plan_segments_kernel<<<sgrid, 256, 0, st>>>(pl.skey, pl.spos, pl.uniq, pl.heads, pl.nheads, M,
-                                                  pl.heads_cap);
-  HOLE_LAUNCHED();
+  *k_out = kin;
+  *v_out = vin;
   return HOLE_OK;
 }
 
-// Corruption + plan for S steps, enqueued on `ps` (the plan stream, or the caller's stream).
+// triples per lane group in K1 (and the run length the plan folds relation keys over)
+static int triples_per_group(const hole_ctx* c, int64_t B) {
+  const int64_t wmax = (int64_t)c->sm_count * 2 * (256 / c->gs);   // groups of two resident blocks per SM
+  return (int)std::max<int64_t>(1, (B + wmax - 1) / wmax);
+}
+
+// The integer plan of S steps, enqueued on `ps` (the plan stream, or the caller's stream):
+// group triples by relation -> corruption + row keys -> sort by row -> segments.
+// neg_in != nullptr (single-step API): the caller supplies the corruption.
 static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, int64_t B, int64_t S,
                       const int32_t* type_of, const int64_t* csr_off, const int32_t* csr_ids,
-                      uint64_t seed, uint64_t first_step, cudaStream_t ps) {
+                      uint64_t seed, uint64_t first_step, const int32_t* neg_in, cudaStream_t ps) {
   if (pl.used) HOLE_CUDA_TRY(cudaStreamWaitEvent(ps, pl.released, 0));   // last consumer is done
+  const int M = (int)(4 * B);
   dim3 grid((unsigned)std::min<int64_t>((B + 255) / 256, 4096), (unsigned)S);
-  hole_corrupt_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, (int)S, type_of, csr_off, csr_ids, seed,
-                                            first_step, pl.neg, nullptr, pl.keysA);
+  // 1. perm: triples grouped by relation (stable)
+  hole_rel_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, pl.keysA);
   HOLE_LAUNCHED();
-  int rc = build_plan(c, pl, S, (int)(4 * B), ps);
+  uint32_t *ko, *vo;
+  int rc = radix_sort(pl, pl.keysA, pl.keysB, pl.valsA, pl.valsB, reinterpret_cast<uint32_t*>(pl.perm),
+                      S, (int)B, c->rel_passes, ps, &ko, &vo);
   if (rc) return rc;
+  // 2. corruption + the 4B row keys of every step
+  pl.T = triples_per_group(c, B);
+  hole_plan_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, pl.T, pl.perm, type_of, csr_off, csr_ids,
+                                              seed, first_step, neg_in, pl.neg, pl.keysA);
+  HOLE_LAUNCHED();
+  // 3. sort by row, 4. segments
+  rc = radix_sort(pl, pl.keysA, pl.keysB, pl.valsA, pl.valsB, nullptr, S, M, c->row_passes, ps,
+                  &pl.skey, &pl.spos);
+  if (rc) return rc;
+  pl.heads_cap = M / 2 + 1;
+  HOLE_CUDA_TRY(cudaMemsetAsync(pl.nheads, 0, (size_t)S * 4, ps));
+  dim3 sgrid((unsigned)std::min<int64_t>((M + 255) / 256, 1024), (unsigned)S);
+  hole_plan_segments_kernel<<<sgrid, 256, 0, ps>>>(pl.skey, pl.spos, pl.uniq, pl.heads, pl.nheads, M,
+                                                  pl.heads_cap);
+  HOLE_LAUNCHED();
   HOLE_CUDA_TRY(cudaEventRecord(pl.ready, ps));
   return HOLE_OK;
 }
@@ -945,9 +1173,9 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
     c->prof_used += 3;
     HOLE_CUDA_TRY(cudaEventRecord(pe[0], st));
   }
-  HOLE_DISPATCH(c, hole_train_fwd_bwd_kernel, grid_for_groups(B, c->gs), 256, st, table, pos, neg,
-                pl.uniq + off, side, B, c->nvec, c->row_stride, margin, lr, c->G, loss_out,
-                sigma_out);
+  HOLE_DISPATCH_SMEM(c, hole_train_fwd_bwd_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
+                     c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.uniq + off, side, (int)B, pl.T, c->nvec,
+                c->row_stride, margin, lr, c->G, loss_out, sigma_out);
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[1], st));
   HOLE_DISPATCH(c, hole_apply_kernel, grid_for_groups(pl.heads_cap, c->gs), 256, st, table, c->G,
                 pl.spos + off, pl.heads + (size_t)slot * pl.heads_cap, pl.nheads + slot, c->counters, M,
@@ -993,10 +1221,8 @@ extern "C" int hole_train_step(hole_ctx* c, float* table, const int32_t* pos, co
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   hole_plan& pl = c->plan[0];
-  if (pl.used) HOLE_CUDA_TRY(cudaStreamWaitEvent(st, pl.released, 0));
-  hole_keys_kernel<<<(unsigned)std::min<int64_t>((B + 255) / 256, 65535), 256, 0, st>>>(pos, neg_ent, B, pl.keysA);
-  HOLE_LAUNCHED();
-  rc = build_plan(c, pl, 1, (int)(4 * B), st);
+  // the plan's keys do not depend on the side, and the corruption is the caller's
+  rc = plan_steps(c, pl, pos, B, 1, nullptr, nullptr, nullptr, 0, 0, neg_ent, st);
   if (rc) return rc;
   rc = run_step(c, pl, table, pos, neg_ent, side, B, margin, lr, loss_out, sigma_out, 0, st);
   if (rc) return rc;
@@ -1051,14 +1277,14 @@ extern "C" int hole_train_steps(hole_ctx* c, float* table, const int32_t* triple
   HOLE_CUDA_TRY(cudaStreamWaitEvent(c->plan_stream, c->ev_entry, 0));
   const int64_t nchunks = (n_steps + S - 1) / S;
   rc = plan_steps(c, c->plan[0], triples, B, std::min(S, n_steps), type_of, csr_off, csr_ids, seed,
-                  first_step, c->plan_stream);
+                  first_step, nullptr, c->plan_stream);
   if (rc) return rc;
   for (int64_t ci = 0; ci < nchunks; ++ci) {
     const int64_t k0 = ci * S, s = std::min(S, n_steps - k0);
     if (ci + 1 < nchunks) {   // plan the next chunk while this one trains
       const int64_t k1 = k0 + S, s1 = std::min(S, n_steps - k1);
       rc = plan_steps(c, c->plan[(ci + 1) & 1], triples + (size_t)k1 * B * 3, B, s1, type_of, csr_off,
-                      csr_ids, seed, first_step + (uint64_t)k1, c->plan_stream);
+                      csr_ids, seed, first_step + (uint64_t)k1, nullptr, c->plan_stream);
       if (rc) return rc;
     }
     float* lo = loss_out ? loss_out + (size_t)k0 * B : c->loss;
@@ -1118,7 +1344,7 @@ extern "C" int hole_train_steps_host(hole_ctx* c, float* table, const int32_t* t
     HOLE_CUDA_TRY(cudaEventRecord(c->ev_copy[b], c->copy_stream));
     HOLE_CUDA_TRY(cudaStreamWaitEvent(c->plan_stream, c->ev_copy[b], 0));
     return plan_steps(c, c->plan[b], c->triples_stage[b], B, s, type_of, csr_off, csr_ids, seed,
-                      first_step + (uint64_t)k0, c->plan_stream);
+                      first_step + (uint64_t)k0, nullptr, c->plan_stream);
   };
   rc = stage_and_plan(0);
   if (rc) return rc;

@@ -52,6 +52,11 @@ class HoleEngine:
         self.table = None
         self.type_of = self.csr_off = self.csr_ids = None
 
+    def set_relation_count(self, n_relations):
+        """holE.py:52 relation_count: relation ids are < n_relations (plan-sort hint)."""
+        check(self.lib.hole_ctx_set_relations(self._ctx, int(n_relations)))
+        return self
+
     def close(self):
         if getattr(self, "_ctx", None):
             self.lib.hole_ctx_destroy(self._ctx)

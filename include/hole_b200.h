@@ -70,6 +70,10 @@ HOLE_API int hole_row_stride(int dim);
 HOLE_API int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int dim);
 HOLE_API int hole_ctx_destroy(hole_ctx* ctx);
 
+/* Optional hint: relation ids are < n_relations (holE.py:52 counts relation_ids.txt), which
+ * shortens the per-step "group triples by relation" sort.  Default: n_rows. */
+HOLE_API int hole_ctx_set_relations(hole_ctx* ctx, int64_t n_relations);
+
 /* Checkpoint layout [n, dim] <-> device layout [n, row_stride]. */
 HOLE_API int hole_pack_rows(hole_ctx* ctx, const float* src_nd, float* dst_padded, int64_t n, void* stream);
 HOLE_API int hole_unpack_rows(hole_ctx* ctx, const float* src_padded, float* dst_nd, int64_t n, void* stream);
