@@ -159,7 +159,8 @@ __global__ void hole_corrupt_kernel(const int32_t* __restrict__ triples, int64_t
                                     const int32_t* __restrict__ type_of,
                                     const int64_t* __restrict__ csr_off,
                                     const int32_t* __restrict__ csr_ids, uint64_t seed,
-                                    uint64_t first_step, int32_t* __restrict__ neg_out,
+                                    uint64_t first_step, uint64_t index_base,
+                                    int32_t* __restrict__ neg_out,
                                     int32_t* __restrict__ side_out) {
   int s = blockIdx.y;
   uint64_t step = first_step + (uint64_t)s;
@@ -172,7 +173,7 @@ __global__ void hole_corrupt_kernel(const int32_t* __restrict__ triples, int64_t
     int ty = type_of[ent];
     int64_t lo = csr_off[ty];
     uint32_t cnt = (uint32_t)(csr_off[ty + 1] - lo);
-    neg_out[(size_t)s * B + i] = csr_ids[lo + hole_entity_draw(seed, step, (uint32_t)i, cnt)];
+    neg_out[(size_t)s * B + i] = csr_ids[lo + hole_entity_draw(seed, step, (uint32_t)(index_base + (uint64_t)i), cnt)];
   }
 }
 
@@ -1060,20 +1061,29 @@ extern "C" int hole_unpack_rows(hole_ctx* c, const float* src, float* dst, int64
   return HOLE_OK;
 }
 
-extern "C" int hole_corrupt(hole_ctx* c, const int32_t* triples, int64_t B, const int32_t* type_of,
-                            const int64_t* csr_off, const int32_t* csr_ids, uint64_t seed,
-                            uint64_t step, int32_t* side_out, int32_t* neg_out, int* side_host,
-                            void* stream) {
+extern "C" int hole_corrupt_at(hole_ctx* c, const int32_t* triples, int64_t B, const int32_t* type_of,
+                               const int64_t* csr_off, const int32_t* csr_ids, uint64_t seed,
+                               uint64_t step, uint64_t index_base, int32_t* side_out,
+                               int32_t* neg_out, int* side_host, void* stream) {
   HOLE_CHECK_ARG(c && B >= 0);
   if (side_host) *side_host = hole_side_coin(seed, step);
   if (B == 0) return HOLE_OK;
   HOLE_CHECK_ARG(triples && type_of && csr_off && csr_ids && neg_out);
+  HOLE_CHECK_ARG(index_base + (uint64_t)B <= (uint64_t(1) << 32));
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   dim3 grid((unsigned)std::min<int64_t>((B + 255) / 256, 65535), 1);
   hole_corrupt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(triples, B, 1, type_of, csr_off, csr_ids,
-                                                              seed, step, neg_out, side_out);
+                                                              seed, step, index_base, neg_out, side_out);
   HOLE_LAUNCHED();
   return HOLE_OK;
+}
+
+extern "C" int hole_corrupt(hole_ctx* c, const int32_t* triples, int64_t B, const int32_t* type_of,
+                            const int64_t* csr_off, const int32_t* csr_ids, uint64_t seed,
+                            uint64_t step, int32_t* side_out, int32_t* neg_out, int* side_host,
+                            void* stream) {
+  return hole_corrupt_at(c, triples, B, type_of, csr_off, csr_ids, seed, step, 0, side_out, neg_out,
+                         side_host, stream);
 }
 
 extern "C" int hole_score(hole_ctx* c, const float* table, const int32_t* triples, int64_t B,

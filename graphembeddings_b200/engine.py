@@ -103,15 +103,16 @@ class HoleEngine:
         return t
 
     # ------------------------------------------------------------------ hot path
-    def corrupt_batch(self, triples, seed, step):
-        """holE.py:152 corrupt_batch -> (side, neg_ent int32[B] on device)."""
+    def corrupt_batch(self, triples, seed, step, index_base=0):
+        """holE.py:152 corrupt_batch -> (side, neg_ent int32[B] on device).  index_base: position
+        of triples[0] inside the global (multi-GPU) batch."""
         t = self._triples(triples)
         B = t.shape[0]
         neg = torch.empty(B, dtype=torch.int32, device=self.device)
         side = C.c_int(0)
-        check(self.lib.hole_corrupt(self._ctx, _ptr(t), B, _ptr(self.type_of), _ptr(self.csr_off),
-                                    _ptr(self.csr_ids), seed, step, None, _ptr(neg),
-                                    C.byref(side), _stream()))
+        check(self.lib.hole_corrupt_at(self._ctx, _ptr(t), B, _ptr(self.type_of), _ptr(self.csr_off),
+                                       _ptr(self.csr_ids), seed, step, int(index_base), None, _ptr(neg),
+                                       C.byref(side), _stream()))
         return int(side.value), neg
 
     def evaluate_triples(self, triples):

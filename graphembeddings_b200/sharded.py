@@ -1,0 +1,306 @@
+"""Multi-GPU HolE: entity table row-sharded over the ranks of one node.
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch; gloo in the CPU tests).
+
+Training step (batch-synchronous, same result as one GPU on the concatenated batch up to
+fp32 summation order):
+  1. every rank corrupts its slice of the global batch (Philox keyed on the GLOBAL triple
+     index, so the draw does not depend on the number of ranks);
+  2. all-to-all of the unique entity ids a rank needs -> all-to-all of those rows from their
+     owners (relation rows are replicated);
+  3. the rank assembles a step table W = [relations | fetched rows], remaps its triples into
+     W and runs the single-GPU step kernels on it in place;
+  4. W_after - W_before is the rank's contribution: relation deltas are all-reduced and
+     applied to every replica, entity deltas travel back by all-to-all and the owner adds
+     them in rank order (deterministic).
+Ranking: candidates are sharded by row block; the true candidate's score comes from its
+owner (all-reduce of a zero-initialised vector), the int32 counts are all-reduced.
+
+The local compute is pluggable (`LocalBackend`) so that the routing can be tested on CPU
+with gloo; the CUDA backend calls libhole_b200 through HoleEngine.
+"""
+import json
+import os
+import time
+
+import numpy as np
+import torch
+
+
+def row_partition(n_entities, world):
+    """Contiguous blocks of entity rows; returns rows_per_rank."""
+    return (n_entities + world - 1) // world
+
+
+class CudaBackend:
+    """libhole_b200 on this rank's GPU.  The engine's table is the step table W."""
+
+    def __init__(self, n_relations, dim, max_batch, device_index, type_of=None, csr_off=None, csr_ids=None):
+        from .engine import HoleEngine
+        self.R = n_relations
+        self.eng = HoleEngine(n_relations + 3 * max_batch, dim, device_index)
+        self.eng.set_relation_count(n_relations)
+        self.width = self.eng.row_stride
+        self.dim = dim
+        self.device = self.eng.device
+        self.W = torch.zeros((n_relations + 3 * max_batch, self.width), dtype=torch.float32, device=self.device)
+        self.eng.table = self.W
+        if type_of is not None:
+            self.eng.set_types(type_of, csr_off, csr_ids)
+
+    def pad_rows(self, E):
+        """checkpoint layout [n, dim] -> device layout [n, width]"""
+        E = torch.as_tensor(E, dtype=torch.float32, device=self.device)
+        H, Hp = self.dim // 2, self.width // 2
+        out = torch.zeros((E.shape[0], self.width), dtype=torch.float32, device=self.device)
+        out[:, :H] = E[:, :H]
+        out[:, Hp:Hp + H] = E[:, H:]
+        return out
+
+    def unpad_rows(self, P):
+        H, Hp = self.dim // 2, self.width // 2
+        return torch.cat([P[:, :H], P[:, Hp:Hp + H]], dim=1)
+
+    def corrupt(self, triples, seed, step, index_base):
+        side, neg = self.eng.corrupt_batch(triples, seed, step, index_base)
+        return side, neg.long()
+
+    def step(self, n_rows, pos, neg, side, margin, lr):
+        return self.eng.train_step(pos.to(torch.int32), neg.to(torch.int32), side, margin, lr)
+
+
+class RowShardedTrainer:
+    def __init__(self, n_relations, n_entities, dim, backend, dist=None, max_batch=None):
+        self.R, self.n_ent, self.dim = int(n_relations), int(n_entities), int(dim)
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rows_per = row_partition(self.n_ent, self.world)
+        self.begin = self.R + self.rank * self.rows_per                   # first global row I own
+        self.end = min(self.R + self.n_ent, self.begin + self.rows_per)
+        self.be = backend
+        self.shard = None          # [R + n_mine, width]: replicated relations, then my block
+
+    # ------------------------------------------------------------------ table
+    def load_embeddings(self, E):
+        """E: full [N, dim] table (checkpoint layout) available on every rank; keeps my part."""
+        E = torch.as_tensor(E)
+        mine = torch.cat([E[: self.R], E[self.begin:self.end]], dim=0)
+        self.shard = self.be.pad_rows(mine)
+        return self
+
+    def gather_embeddings(self):
+        """Full [N, dim] table on every rank (tests / checkpointing)."""
+        mine = self.be.unpad_rows(self.shard[self.R:]).contiguous()
+        if self.world == 1:
+            ents = mine
+        else:
+            pad = torch.zeros((self.rows_per - mine.shape[0], mine.shape[1]), dtype=mine.dtype, device=mine.device)
+            buf = torch.cat([mine, pad], dim=0)
+            out = [torch.empty_like(buf) for _ in range(self.world)]
+            self.dist.all_gather(out, buf)
+            ents = torch.cat(out, dim=0)[: self.n_ent]
+        return torch.cat([self.be.unpad_rows(self.shard[: self.R]), ents], dim=0)
+
+    # ------------------------------------------------------------------ exchange helpers
+    def _a2a(self, send, send_counts, recv_counts):
+        if self.world == 1:
+            return send
+        shape = (int(sum(recv_counts)),) + tuple(send.shape[1:])
+        recv = torch.empty(shape, dtype=send.dtype, device=send.device)
+        self.dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=list(recv_counts),
+                                    input_split_sizes=list(send_counts))
+        return recv
+
+    def _route(self, uniq):
+        """uniq: sorted unique global entity rows I need.  -> (send_counts, recv_counts) lists."""
+        dev = uniq.device
+        bounds = self.R + self.rows_per * torch.arange(1, self.world + 1, device=dev)
+        cut = torch.searchsorted(uniq, bounds)
+        send = torch.diff(cut, prepend=torch.zeros(1, dtype=cut.dtype, device=dev))
+        if self.world == 1:
+            sc = [int(send[0])]
+            return sc, sc
+        recv = torch.empty_like(send)
+        self.dist.all_to_all_single(recv, send)
+        return [int(x) for x in send.tolist()], [int(x) for x in recv.tolist()]
+
+    # ------------------------------------------------------------------ training
+    def train_step(self, pos_local, seed, step, margin, lr):
+        """pos_local: this rank's [B,3] slice (global row ids) of the global batch of
+        world*B triples.  Returns the per-triple hinge loss of the slice."""
+        dev = self.shard.device
+        pos = torch.as_tensor(pos_local).to(dev).long()
+        B, R = pos.shape[0], self.R
+        side, neg = self.be.corrupt(pos.to(torch.int32), seed, step, self.rank * B)
+        neg = neg.to(dev)
+        ents = torch.cat([pos[:, 0], pos[:, 1], neg])
+        uniq, inv = torch.unique(ents, return_inverse=True)
+        U = uniq.shape[0]
+        send_counts, recv_counts = self._route(uniq)
+        ids_in = self._a2a(uniq, send_counts, recv_counts)              # rows others want from me
+        rows_out = self.shard.index_select(0, ids_in - self.begin + R)
+        rows_in = self._a2a(rows_out, recv_counts, send_counts)         # in `uniq` order
+        W = self.be.W
+        W[:R].copy_(self.shard[:R])
+        W[R:R + U].copy_(rows_in)
+        W0 = W[: R + U].clone()
+        pos_w = torch.stack([R + inv[:B], R + inv[B:2 * B], pos[:, 2]], dim=1)
+        neg_w = R + inv[2 * B:]
+        loss = self.be.step(R + U, pos_w, neg_w, side, margin, lr)
+        delta = W[: R + U] - W0
+        d_rel = delta[:R].contiguous()
+        if self.world > 1:
+            self.dist.all_reduce(d_rel)
+        self.shard[:R] += d_rel
+        d_in = self._a2a(delta[R:], send_counts, recv_counts)           # grouped by source rank
+        off = 0
+        for k in range(self.world):                                     # rank order: deterministic
+            n_k = recv_counts[k]
+            if n_k:
+                self.shard.index_add_(0, ids_in[off:off + n_k] - self.begin + R, d_in[off:off + n_k])
+            off += n_k
+        return loss
+
+    # ------------------------------------------------------------------ ranking
+    def rank(self, queries, side, filter_off=None, filter_ids=None):
+        """All-entity ranking of (replicated) queries [Q,3] with candidates sharded by row
+        block.  Returns (raw_before, filt_before) int32[Q], identical on every rank."""
+        from .engine import HOLE_SIDE_TAIL, HoleEngine
+        dev = self.shard.device
+        q = torch.as_tensor(queries).to(dev).long()
+        Q, R = q.shape[0], self.R
+        other_col, true_col = (0, 1) if side == HOLE_SIDE_TAIL else (1, 0)
+        uniq, inv = torch.unique(q[:, other_col], return_inverse=True)
+        send_counts, recv_counts = self._route(uniq)
+        ids_in = self._a2a(uniq, send_counts, recv_counts)
+        rows_in = self._a2a(self.shard.index_select(0, ids_in - self.begin + R), recv_counts, send_counts)
+        n_mine = self.shard.shape[0] - R
+        table = torch.cat([self.shard, rows_in], dim=0)                 # [R | my block | fetched]
+        tr = q[:, true_col]
+        # true candidate: local index if mine, else below / above my candidate range
+        tr_loc = torch.where(tr < self.begin, torch.zeros_like(tr) - 1 + R,       # < ent_begin
+                             torch.where(tr >= self.end, torch.full_like(tr, R + n_mine + 1),
+                                         tr - self.begin + R))
+        ql = torch.empty_like(q)
+        ql[:, other_col] = R + n_mine + inv
+        ql[:, true_col] = tr_loc
+        ql[:, 2] = q[:, 2]
+        fo = fi = None
+        if filter_off is not None:
+            fo = torch.as_tensor(filter_off).to(dev)
+            fi = (torch.as_tensor(filter_ids).to(dev).long() - self.begin + R).to(torch.int32)
+        # a ranking context sized for [relations | my block | fetched rows]
+        eng = getattr(self, "_rank_eng", None)
+        if eng is None or eng.n_rows < table.shape[0]:
+            if eng is not None:
+                eng.close()
+            eng = self._rank_eng = HoleEngine(int(table.shape[0] * 1.25) + 1024, self.dim, dev.index or 0)
+        eng.table = table
+        try:
+            ts = torch.zeros(Q, dtype=torch.float32, device=dev)
+            scratch = torch.zeros(Q, dtype=torch.int32, device=dev)
+            eng.rank(ql.to(torch.int32), side, R, R + n_mine, None, None, true_score=ts,
+                     compute_true=True, raw_before=scratch, filt_before=scratch.clone())
+            if self.world > 1:
+                self.dist.all_reduce(ts)          # exactly one owner wrote each entry, others hold 0
+            raw = torch.zeros(Q, dtype=torch.int32, device=dev)
+            filt = torch.zeros(Q, dtype=torch.int32, device=dev)
+            eng.rank(ql.to(torch.int32), side, R, R + n_mine, fo, fi, true_score=ts,
+                     compute_true=False, raw_before=raw, filt_before=filt)
+            if self.world > 1:
+                self.dist.all_reduce(raw)
+                self.dist.all_reduce(filt)
+        finally:
+            eng.table = None
+        return raw, filt
+
+
+# --------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1)
+# --------------------------------------------------------------------------------------
+def bench(args, dist, rank, world, local_rank):
+    """Weak scaling: every rank trains `--batch` triples per step on the row-sharded
+    BASELINE config 1 table.  Device time, max over ranks; rank 0 prints the JSON line."""
+    import bench as B_
+    from . import data as D
+    from .engine import HOLE_SIDE_TAIL
+
+    Bl, K, W = args.batch, args.steps, args.warmup
+    kg = D.make_config(B_.WORKLOAD, n_triples=(K + W) * Bl * world)
+    off, ids = D.build_type_csr(kg.type_of)
+    be = CudaBackend(kg.n_relations, kg.dim, Bl, local_rank, kg.type_of, off, ids)
+    tr = RowShardedTrainer(kg.n_relations, kg.n_entities, kg.dim, be, dist).load_embeddings(kg.E)
+    # step s, rank r takes triples [(s*world + r)*Bl, +Bl)
+    mine = torch.from_numpy(kg.triples).view(K + W, world, Bl, 3)[:, rank].contiguous()
+    dev_tri = mine.cuda()
+    host_tri = mine.pin_memory()
+    lrs = B_.lr_schedule(3 * (K + W), 0, 30_000_000 // (Bl * world))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for s in range(W):
+        tr.train_step(dev_tri[s], 1, s, B_.MARGIN, float(lrs[s]))
+    sampler = B_.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    be.eng.reset_launch_count()
+    ms = timed(lambda: [tr.train_step(dev_tri[W + s], 1, W + s, B_.MARGIN, float(lrs[W + s])) for s in range(K)])
+    launches = be.eng.launch_count()
+    value = K * Bl * world / (ms * 1e-3)
+
+    losses = []
+
+    def e2e_pass():
+        for s in range(K):
+            t = host_tri[W + s].cuda(non_blocking=True)
+            loss = tr.train_step(t, 1, K + W + s, B_.MARGIN, float(lrs[K + W + s]))
+            losses.append(float(loss.sum().item()))        # device -> host read of the step's result
+
+    ms_e2e = timed(e2e_pass)
+    e2e = K * Bl * world / (ms_e2e * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # sharded ranking: 20k replicated queries x 1.2M candidates split over the ranks
+    rng = np.random.default_rng(20170906)
+    q = torch.from_numpy(kg.triples[rng.integers(0, len(kg.triples), size=20000)])
+    tr.rank(q, HOLE_SIDE_TAIL)
+    ms_rank = timed(lambda: tr.rank(q, HOLE_SIDE_TAIL))
+    if rank == 0:
+        peak, src, _ = B_.peaks()
+        alg = (32 * kg.dim + 20)
+        print(json.dumps({
+            "metric": "HolE train triples/s", "value": value, "unit": "triples/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{B_.WORKLOAD}: BASELINE.json configs[1] table row-sharded over {world} GPUs "
+                                   "(relations replicated), NCCL all-to-all of rows and row deltas",
+                       "batch_per_gpu": Bl, "global_batch": Bl * world, "margin": B_.MARGIN, "lr0": B_.LR0,
+                       "parallelism": f"rowshard{world}", "l2": "table shard larger than L2; no flush",
+                       "mean_loss_last_step": losses[-1] / Bl if losses else None},
+            "e2e": {"value": e2e, "unit": "triples/s", "h2d_bytes_per_step": 12 * Bl, "d2h_bytes_per_step": 4,
+                    "call": "RowShardedTrainer.train_step (pinned host triples in, loss sum out), per rank"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": value * alg / 1e9 / world, "peak": peak, "unit": "GB/s",
+                         "frac": value * alg / 1e9 / world / peak, "traffic": None, "peak_source": src,
+                         "kernel": "whole sharded step per GPU (NVLink exchange included)"},
+            "cpu_baseline": None,
+            "ranking": {"workload": f"20000 queries x 1,200,000 candidates sharded over {world} GPUs (tail side)",
+                        "ms": ms_rank, "scores_per_s": 20000 * 1.2e6 / (ms_rank * 1e-3)},
+        }))
+    dist.barrier()
+    dist.destroy_process_group()

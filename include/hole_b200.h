@@ -91,6 +91,14 @@ HOLE_API int hole_corrupt(hole_ctx* ctx, const int32_t* triples, int64_t B,
                  uint64_t seed, uint64_t step,
                  int32_t* side_out, int32_t* neg_out, int* side_host, void* stream);
 
+/* Same draw for a batch that is a slice of a larger (multi-GPU) batch: triple i of this call
+ * is triple index_base + i of the global batch, so the result does not depend on how the
+ * global batch is split over ranks. */
+HOLE_API int hole_corrupt_at(hole_ctx* ctx, const int32_t* triples, int64_t B,
+                 const int32_t* type_of, const int64_t* csr_off, const int32_t* csr_ids,
+                 uint64_t seed, uint64_t step, uint64_t index_base,
+                 int32_t* side_out, int32_t* neg_out, int* side_host, void* stream);
+
 /* ---- forward: replaces evaluate_triples (holE.py:179-202): out_sigma[i] =
  * sigmoid(sum_k Re(h_k * r_k * conj(t_k))) on norm-clipped rows (holE.py:161-168). */
 HOLE_API int hole_score(hole_ctx* ctx, const float* table, const int32_t* triples, int64_t B,

@@ -196,3 +196,15 @@ def test_empty_queries_and_errors(eng_mod):
         e.rank(kg.triples, 0, 3, 99999)          # range outside the table
     with pytest.raises(eng_mod.HoleError):
         e.rank(kg.triples, 0, 3, 303, precision=eng_mod.HOLE_RANK_BF16X3)
+
+
+def test_sharded_rank_single_rank_matches_engine(eng_mod):
+    from graphembeddings_b200.sharded import CudaBackend, RowShardedTrainer
+    kg, e = _setup(eng_mod, 6, 2500, 300, 150, seed=33)
+    known = D.synthetic_kg(6, 2500, 8000, 4, 8, seed=98, with_embeddings=False).triples
+    foff, fids = D.build_filter_csr(kg.triples, known, "tail")
+    raw1, filt1, _ = e.rank(kg.triples, 0, kg.n_relations, kg.n_rows, foff, fids)
+    be = CudaBackend(kg.n_relations, kg.dim, 64, 0)
+    tr = RowShardedTrainer(kg.n_relations, kg.n_entities, kg.dim, be, None).load_embeddings(kg.E)
+    raw2, filt2 = tr.rank(torch.from_numpy(kg.triples), 0, foff, fids)
+    assert torch.equal(raw1, raw2) and torch.equal(filt1, filt2)

@@ -211,3 +211,24 @@ def test_full_size_properties_config0(eng_mod):
     assert np.all(np.abs(mean_loss - 0.2) < 0.05)
     assert not torch.equal(res[0][1], torch.from_numpy(kg.E))
     assert torch.isfinite(res[0][1]).all()
+
+
+def test_sharded_trainer_single_rank_matches_engine(eng_mod):
+    """RowShardedTrainer with one rank (no process group) routes everything through the
+    step table W and the delta application; it must agree with the plain engine step."""
+    from graphembeddings_b200.sharded import CudaBackend, RowShardedTrainer
+    kg = D.synthetic_kg(6, 3000, 1500, 4, 150, seed=41, trained_scale=True, zipf_entities=True)
+    off, ids = D.build_type_csr(kg.type_of)
+    be = CudaBackend(kg.n_relations, kg.dim, 500, 0, kg.type_of, off, ids)
+    tr = RowShardedTrainer(kg.n_relations, kg.n_entities, kg.dim, be, None).load_embeddings(kg.E)
+    e, _, _ = _engine(eng_mod, kg)
+    for s in range(3):
+        pos = kg.triples[s * 500:(s + 1) * 500]
+        loss_s = tr.train_step(torch.from_numpy(pos), 5, s, 0.2, 0.1)
+        side, neg = e.corrupt_batch(pos, 5, s)
+        loss_e = e.train_step(pos, neg, side, 0.2, 0.1)
+        assert torch.allclose(loss_s, loss_e, atol=2e-6, rtol=0)
+    got = tr.gather_embeddings().cpu().numpy()
+    want = e.embeddings().cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-6
+    assert np.abs(want - kg.E).max() > 1e-4
