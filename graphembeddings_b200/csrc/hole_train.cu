@@ -11,6 +11,7 @@
 // matching V float4s of the imaginary half, so every complex product is lane-local and
 // every global access is a coalesced 16-byte vector.
 #include <stdarg.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -1375,4 +1376,43 @@ extern "C" int hole_train_steps_host(hole_ctx* c, float* table, const int32_t* t
   HOLE_CUDA_TRY(cudaStreamSynchronize(st));
   for (int64_t k = 0; k < n_steps; ++k) loss_sum_host[k] = c->loss_sum_pinned[k];
   return HOLE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// CRC32C (Castagnoli) for the TF tensor-bundle checkpoint writer (host code; holE.py:359
+// saver.save writes a masked crc32c per tensor and per SSTable block).
+// ---------------------------------------------------------------------------------------
+static uint32_t g_crc32c_table[8][256];
+static bool g_crc32c_ready = false;
+
+static void crc32c_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : (c >> 1);
+    g_crc32c_table[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t)
+      g_crc32c_table[t][i] = (g_crc32c_table[t - 1][i] >> 8) ^ g_crc32c_table[0][g_crc32c_table[t - 1][i] & 0xFF];
+  g_crc32c_ready = true;
+}
+
+extern "C" uint32_t hole_crc32c(uint32_t crc, const void* data, uint64_t n) {
+  if (!g_crc32c_ready) crc32c_init();
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = crc ^ 0xFFFFFFFFu;
+  while (n >= 8) {   // slice-by-8
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = g_crc32c_table[7][lo & 0xFF] ^ g_crc32c_table[6][(lo >> 8) & 0xFF] ^
+        g_crc32c_table[5][(lo >> 16) & 0xFF] ^ g_crc32c_table[4][lo >> 24] ^
+        g_crc32c_table[3][hi & 0xFF] ^ g_crc32c_table[2][(hi >> 8) & 0xFF] ^
+        g_crc32c_table[1][(hi >> 16) & 0xFF] ^ g_crc32c_table[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ g_crc32c_table[0][(c ^ *p++) & 0xFF];
+  return c ^ 0xFFFFFFFFu;
 }

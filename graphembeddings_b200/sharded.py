@@ -73,10 +73,10 @@ class RowShardedTrainer:
     def __init__(self, n_relations, n_entities, dim, backend, dist=None, max_batch=None):
         self.R, self.n_ent, self.dim = int(n_relations), int(n_entities), int(dim)
         self.dist = dist
-        self.rank = dist.get_rank() if dist is not None else 0
+        self.my_rank = dist.get_rank() if dist is not None else 0
         self.world = dist.get_world_size() if dist is not None else 1
         self.rows_per = row_partition(self.n_ent, self.world)
-        self.begin = self.R + self.rank * self.rows_per                   # first global row I own
+        self.begin = self.R + self.my_rank * self.rows_per                   # first global row I own
         self.end = min(self.R + self.n_ent, self.begin + self.rows_per)
         self.be = backend
         self.shard = None          # [R + n_mine, width]: replicated relations, then my block
@@ -132,7 +132,7 @@ class RowShardedTrainer:
         dev = self.shard.device
         pos = torch.as_tensor(pos_local).to(dev).long()
         B, R = pos.shape[0], self.R
-        side, neg = self.be.corrupt(pos.to(torch.int32), seed, step, self.rank * B)
+        side, neg = self.be.corrupt(pos.to(torch.int32), seed, step, self.my_rank * B)
         neg = neg.to(dev)
         ents = torch.cat([pos[:, 0], pos[:, 1], neg])
         uniq, inv = torch.unique(ents, return_inverse=True)

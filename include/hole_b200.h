@@ -169,6 +169,10 @@ HOLE_API int hole_rank_debug_operands(hole_ctx* ctx, void* cand_out, void* query
 HOLE_API int hole_profile_enable(hole_ctx* ctx, int on);
 HOLE_API int hole_profile_read(hole_ctx* ctx, double* k1_ms, double* k3_ms, int64_t* n_steps);
 
+/* Host helper for the checkpoint writer: CRC32C (Castagnoli) of a HOST buffer, continuing
+ * from `crc` (0 to start).  TF's tensor bundle stores it masked (holE.py:359 saver.save). */
+HOLE_API uint32_t hole_crc32c(uint32_t crc, const void* data_host, uint64_t n);
+
 /* Number of kernels this library has launched on this thread's contexts since the last
  * reset (bench.py's "gpu_launches"). */
 HOLE_API int64_t hole_launch_count(void);

@@ -1,0 +1,84 @@
+"""End to end through the holE.py-compatible driver on a synthetic --data_dir."""
+import os
+
+import numpy as np
+import pytest
+
+from graphembeddings_b200 import data as D
+from oracle import hole_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_data_dir(d, kg, n_valid, n_test):
+    with open(os.path.join(d, "entity_metadata.tsv"), "w") as f:
+        f.write("Index\tId\tName\tType\n")
+        for i in range(kg.n_rows):
+            f.write(f"{i}\tid{i}\tname{i}\t{'RELATION' if i < kg.n_relations else 'T%d' % kg.type_of[i]}\n")
+    with open(os.path.join(d, "relation_ids.txt"), "w") as f:
+        for r in range(kg.n_relations):
+            f.write(f"rel{r}\t{r}\n")
+    n = len(kg.triples)
+    parts = {"triples.txt": kg.triples[: n - n_valid - n_test],
+             "triples-valid.txt": kg.triples[n - n_valid - n_test: n - n_test],
+             "test_positive_triples.txt": kg.triples[n - n_test:]}
+    for name, tr in parts.items():
+        np.savetxt(os.path.join(d, name), tr, fmt="%d", delimiter="\t")
+    return parts
+
+
+def test_train_checkpoint_resume_infer(tmp_path):
+    from graphembeddings_b200 import build, hole, tf_bundle
+    build.build()
+    kg = D.synthetic_kg(8, 1500, 9000, 4, 64, seed=3, with_embeddings=False)
+    d = tmp_path / "data"; d.mkdir()
+    parts = _write_data_dir(str(d), kg, 600, 400)
+    out = str(tmp_path / "run")
+    args = ["--data_dir", str(d), "--output_dir", out, "--batch_size", "256", "--embedding_dim", "64",
+            "--num_epochs", "2"]
+    hole.main(args)
+    for name in ("model.ckpt.index", "model.ckpt.data-00000-of-00001", "checkpoint",
+                 "projector_config.pbtxt", "summaries.tsv"):
+        assert os.path.exists(os.path.join(out, name)), name
+    b = tf_bundle.load_bundle(os.path.join(out, "model.ckpt"))
+    assert b["embeddings"].shape == (kg.n_rows, 64) and np.isfinite(b["embeddings"]).all()
+    # refuses to clobber an existing output_dir (holE.py:254-255) ...
+    with pytest.raises(Exception, match="already exists"):
+        hole.main(args)
+    # ... unless resuming
+    hole.main(args + ["--resume_checkpoint", "--max_steps", "5"])
+    # --infer: all-entity filtered ranking, agrees with the oracle's heap on the saved table
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        flags = hole.build_parser().parse_args(args + ["--infer"])
+        m = hole.infer_triples(flags, log=lambda *a: None)
+    finally:
+        os.chdir(cwd)
+    assert 0 < m["filtered_mrr"] <= 1 and m["raw_mean_pos"] >= m["filtered_mean_pos"]
+    assert os.path.exists(tmp_path / "inference_results.tsv")
+    E = tf_bundle.load_bundle(os.path.join(out, "model.ckpt"))["embeddings"]
+    test = np.unique(parts["test_positive_triples.txt"], axis=0)[:40]
+    known = np.concatenate([parts["triples.txt"], parts["triples-valid.txt"]])
+    cand = np.arange(kg.n_relations, kg.n_rows)
+    S = O.sigmoid(O.all_scores(E, test, "tail", cand, np.float32))
+    true_t, test_t = {}, {}
+    for h, t, r in known.tolist():
+        true_t.setdefault(h, {}).setdefault(r, set()).add(t)
+    got_r, got_f = [], []
+    from graphembeddings_b200.engine import HoleEngine
+    eng = HoleEngine(kg.n_rows, 64).set_embeddings(E)
+    raw, filt = hole.eval_link_prediction(eng, test, known, kg.n_relations, kg.n_rows, sides=("tail",))
+    # oracle heap per query (single test tail per group so ranks are per-triple)
+    keep = [tuple(q) not in set(map(tuple, known.tolist())) for q in test.tolist()]
+    want_r, want_f = [], []
+    for q, (h, t, r) in enumerate(test.tolist()):
+        if not keep[q]:
+            continue
+        triples = [(h, int(c), r) for c in cand]
+        rr, ff = O.eval_link_prediction_heap(S[q], triples, true_t, {h: {r: {t}}})
+        want_r += rr; want_f += ff
+    assert len(raw) == len(want_r)
+    # bf16 scores vs fp32 sigma: ranks agree up to near-ties
+    assert np.mean(np.abs(np.array(raw) - np.array(want_r)) <= 3) > 0.9
+    assert np.mean(np.abs(np.array(filt) - np.array(want_f)) <= 3) > 0.9

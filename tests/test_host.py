@@ -1,0 +1,92 @@
+"""Host-side mirror of holE.py: loaders, flags, metrics (no GPU needed)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from graphembeddings_b200 import data as D
+from graphembeddings_b200 import hole
+
+
+def test_load_triples_real_fb15k_head(golden_dir):
+    t = D.load_triples(os.path.join(golden_dir, "fb15k_test_positive_triples_head.txt"))
+    assert t.dtype == np.int32 and t.shape == (2000, 3)
+    assert tuple(t[0]) == (13839, 4403, 733)              # diffbot_data/FB15k/test_positive_triples.txt:1
+    # column order (head, tail, relation): relations are rows 0..1344, entities 1345..16295
+    assert t[:, 2].max() < 1345 and t[:, :2].min() >= 1345
+
+
+def test_load_triples_empty_file(tmp_path):
+    p = tmp_path / "triples-valid.txt"                    # prepareSubset-20170712/triples-valid.txt is empty
+    p.write_text("")
+    assert D.load_triples(str(p)).shape == (0, 3)
+
+
+def test_metadata_accepts_4_and_6_columns(golden_dir, tmp_path):
+    md = D.load_entity_metadata(os.path.join(golden_dir, "fb15k_metadata_head.tsv"))
+    assert md.entity_count == 100 and md.id_to_type[0] == "RELATION"
+    assert all(v == 0 for v in md.mentions.values())
+    p = tmp_path / "entity_metadata.tsv"
+    p.write_text("Index\tId\tName\tType\tMentions\tIsTail\n0\t!r0\trel\t!\t0\tfalse\n1\tP1\tAnn\tP\t70000\ttrue\n")
+    md6 = D.load_entity_metadata(str(p))
+    assert md6.entity_count == 2 and md6.mentions[1] == 70000 and md6.id_to_type[1] == "P"
+
+
+def test_type_csr_and_filter_csr():
+    type_of = np.array([0, 0, 1, 2, 1, 1, 2], dtype=np.int32)
+    off, ids = D.build_type_csr(type_of)
+    assert off.tolist() == [0, 2, 5, 7] and ids.tolist() == [0, 1, 2, 4, 5, 3, 6]
+    q = np.array([[10, 20, 1], [11, 21, 2]])
+    known = np.array([[10, 22, 1], [10, 23, 1], [10, 22, 1], [12, 21, 2], [10, 24, 3]])
+    fo, fi = D.build_filter_csr(q, known, "tail")
+    assert fo.tolist() == [0, 2, 2] and fi.tolist() == [22, 23]
+    fo, fi = D.build_filter_csr(q, known, "head")
+    assert fo.tolist() == [0, 0, 1] and fi.tolist() == [12]
+
+
+def test_flags_match_reference_defaults():
+    f = hole.build_parser().parse_args(["--output_dir", "o", "--data_dir", "d"])
+    want = dict(learning_rate=0.1, learning_decay_steps=32, learning_decay_rate=0.5, batch_size=512,
+                num_epochs=1000, embedding_dim=128, log_loss=False, l2_regularization=0.1,
+                negative_ratio=1, margin=0.2, padded_size=1024, reader_threads=4,
+                resume_checkpoint=False, save_embeddings=False, infer=False, infer_threshold=0.05,
+                min_mentions=50000)                       # holE.py:598-619
+    for k, v in want.items():
+        assert getattr(f, k) == v, k
+
+
+def test_score_mrr_matches_reference_stdout(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "ranking_ref.json")))
+    raw = [x for c in g["cases"] for x in c["raw_positions"]]
+    filt = [x for c in g["cases"] for x in c["filtered_positions"]]
+    lines = []
+    hole.score_mrr(raw, filt, log=lines.append)
+    assert "\n".join(lines) + "\n" == g["score_mrr_stdout"]      # byte-identical report
+
+
+def test_init_inference_data_semantics(tmp_path):
+    d = tmp_path
+    (d / "entity_metadata.tsv").write_text(
+        "Index\tId\tName\tType\tMentions\tIsTail\n"
+        "0\t!a\tr0\t!\t0\tf\n1\tP1\tAnn\tP\t0\tt\n2\tS2\tjava\tS\t60000\tt\n3\tS3\tcobol\tS\t10\tt\n")
+    (d / "relation_ids.txt").write_text("r0\t0\n")
+    (d / "triples.txt").write_text("1\t2\t0\n3\t2\t0\n")
+    (d / "triples-valid.txt").write_text("")
+    (d / "test_positive_triples.txt").write_text("1\t3\t0\n")
+    flags = hole.build_parser().parse_args(["--output_dir", "o", "--data_dir", str(d)])
+    inf = hole.init_inference_data(flags)
+    assert inf.relation_count == 1 and inf.entity_count == 4
+    assert inf.type_to_ids["S"] == [2]                    # min_mentions filter (holE.py:397)
+    assert inf.type_to_ids["P"] == [1]                    # ids starting with 'P' always kept
+    assert inf.test_triples[1][0] == {3}
+    assert inf.true_triples[1][0] == {2}                  # only (h, r) pairs present in test (holE.py:421)
+    assert 3 not in inf.true_triples
+
+
+def test_lr_schedule_matches_oracle():
+    from graphembeddings_b200.engine import inverse_time_decay
+    from oracle import hole_oracle as O
+    for step in (0, 1, 1000, 123456):
+        assert inverse_time_decay(0.1, step, 32 * 943, 0.5) == O.inverse_time_decay(0.1, step, 32 * 943, 0.5)
