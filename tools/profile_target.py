@@ -1,0 +1,24 @@
+"""Short workload for ncu: a few training steps of BASELINE config 1 at the bench batch size,
+then one 20k-query ranking call on the same 1.2M-row table."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from graphembeddings_b200 import data as D
+from graphembeddings_b200.engine import HoleEngine
+
+B, steps = 32768, 6
+kg = D.make_config("diffbot_d256", n_triples=B * steps)
+off, ids = D.build_type_csr(kg.type_of)
+e = HoleEngine(kg.n_rows, kg.dim).set_embeddings(kg.E).set_types(kg.type_of, off, ids)
+e.set_relation_count(kg.n_relations)
+tri = torch.from_numpy(kg.triples).cuda()
+sums = e.train_steps(tri, B, 1, 0, 0.2, [0.1] * steps)
+torch.cuda.synchronize()
+q = kg.triples[:20000]
+raw, filt, ts = e.rank(q, 0, kg.n_relations, kg.n_rows)
+torch.cuda.synchronize()
+print("ok", float(sums.mean()) / B, int(raw.max()))
