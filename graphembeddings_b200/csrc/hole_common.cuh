@@ -50,7 +50,7 @@ struct hole_plan {
   uint32_t* ghist = nullptr;     // [S][256][tiles] radix histograms
   uint32_t* skey = nullptr;      // sorted keys (points into keysA or keysB)
   uint32_t* spos = nullptr;      // sorted original positions (points into valsA or valsB)
-  uint8_t* uniq = nullptr;       // [S][4B] per ORIGINAL position: row occurs once in the step
+  uint32_t* gslot = nullptr;     // [S][4B] per ORIGINAL position: G row of that use, or UNIQUE
   uint4* heads = nullptr;        // [S][heads_cap] leaves of the combine trees {j, seg start, n, row}
   int* nheads = nullptr;         // [S]
   int32_t* neg = nullptr;        // [S*B] corrupt entity per triple
@@ -100,8 +100,8 @@ struct hole_ctx {
   size_t prof_used = 0;
 };
 
-constexpr int HOLE_TREE_C = 16;      // fan-in of the deterministic gradient combine tree
-constexpr int HOLE_TREE_LEVELS = 6;  // 16^6 > any 4B
+constexpr int HOLE_TREE_C = 32;      // fan-in of the deterministic gradient combine tree
+constexpr int HOLE_TREE_LEVELS = 6;  // 32^6 > any 4B
 
 int hole_ws_reserve(hole_ctx* ctx, int64_t B, int64_t S);
 void hole_rank_ws_free(hole_ctx* ctx);

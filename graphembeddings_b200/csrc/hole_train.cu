@@ -58,13 +58,13 @@ __device__ __forceinline__ void row_load(Row<V>& x, const float* base, int lane,
   }
 }
 
-template <int GS, int V>
+template <int GS, int V, bool FULL = false>
 __device__ __forceinline__ void row_store(const Row<V>& x, float* base, int lane, int nvec) {
   float4* p = reinterpret_cast<float4*>(base);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     int idx = lane + v * GS;
-    if (idx < nvec) {
+    if (FULL || idx < nvec) {
       p[idx] = make_float4(x.re[4 * v], x.re[4 * v + 1], x.re[4 * v + 2], x.re[4 * v + 3]);
       p[nvec + idx] = make_float4(x.im[4 * v], x.im[4 * v + 1], x.im[4 * v + 2], x.im[4 * v + 3]);
     }
@@ -153,6 +153,7 @@ __global__ void hole_unpack_rows_kernel(const float* __restrict__ src, float* __
 // K2: corruption sampler + update-plan keys
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t HOLE_KEY_ABSENT = 0xFFFFFFFFu;   // sorts after every real row id
+constexpr uint32_t HOLE_SLOT_UNIQUE = 0xFFFFFFFFu;  // gslot value: row used once in the step
 
 // Stand-alone sampler (hole_corrupt): for step s (grid.y) and triple i,
 // neg = csr_ids[off[ty] + draw] with ty the type of the replaced entity.
@@ -360,14 +361,16 @@ hole_sort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* _
   }
 }
 
-// Segments of the sorted keys.  uniq[original position] = row occurs exactly once in the
-// step (such rows are updated in place by K1; nobody else reads them during the step).
+// Segments of the sorted keys.  gslot[original position] = HOLE_SLOT_UNIQUE if the row occurs
+// exactly once in the step (such rows are updated in place by K1; nobody else reads them
+// during the step), else the sorted index of that use = the row of G its gradient goes to
+// (so K3 reads the gradients of one table row from consecutive G rows).
 // For rows that occur n >= 2 times, every sorted entry that heads a chunk of C occurrences
 // is appended to the step's compact work list heads[] = {sorted index, segment start, n, row}
 // (list order is irrelevant: each entry is an independent leaf of the combine tree).
 __global__ void __launch_bounds__(256)
 hole_plan_segments_kernel(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ spos,
-                          uint8_t* __restrict__ uniq, uint4* __restrict__ heads,
+                          uint32_t* __restrict__ gslot, uint4* __restrict__ heads,
                           int* __restrict__ nheads, int M, int heads_cap) {
   constexpr int C = HOLE_TREE_C;
   const size_t base = (size_t)blockIdx.y * M;
@@ -377,7 +380,7 @@ hole_plan_segments_kernel(const uint32_t* __restrict__ skey, const uint32_t* __r
     if (key == HOLE_KEY_ABSENT) continue;      // relation use folded into its run's first triple
     const bool head = (j == 0) || (k[j - 1] != key);
     const bool last = (j == M - 1) || (k[j + 1] != key);
-    uniq[base + spos[base + j]] = (head && last) ? 1 : 0;
+    gslot[base + spos[base + j]] = (head && last) ? HOLE_SLOT_UNIQUE : (uint32_t)j;
     if (head && last) continue;
     int s = j;
     if (!head) {          // lower_bound(key) in [0, j)
@@ -480,25 +483,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int GS, int V>
+template <int GS, int V, bool FULL = false>
 __device__ __forceinline__ void row_fetch_async(float4* sdst, const float* grow, int lane, int nvec) {
   const float4* p = reinterpret_cast<const float4*>(grow);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const int idx = lane + v * GS;
-    if (idx < nvec) {
+    if (FULL || idx < nvec) {
       cp_async16(sdst + idx, p + idx);
       cp_async16(sdst + nvec + idx, p + nvec + idx);
     }
   }
 }
-template <int GS, int V>
+template <int GS, int V, bool FULL = false>
 __device__ __forceinline__ void row_from_smem(Row<V>& x, const float4* ssrc, int lane, int nvec) {
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const int idx = lane + v * GS;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (idx < nvec) { a = ssrc[idx]; b = ssrc[nvec + idx]; }
+    if (FULL || idx < nvec) { a = ssrc[idx]; b = ssrc[nvec + idx]; }
     x.re[4 * v + 0] = a.x; x.re[4 * v + 1] = a.y; x.re[4 * v + 2] = a.z; x.re[4 * v + 3] = a.w;
     x.im[4 * v + 0] = b.x; x.im[4 * v + 1] = b.y; x.im[4 * v + 2] = b.z; x.im[4 * v + 3] = b.w;
   }
@@ -508,7 +511,7 @@ __device__ __forceinline__ void row_from_smem(Row<V>& x, const float4* ssrc, int
 // row); then in place (unique row: E[row] = x - lr dx, x = y / s recovered as y * rs where
 // rs = 1/s is exact for the unclipped case s == 1) or staged.
 // xraw: the unscaled row as it was fetched (landing buffer), used for the in-place update.
-template <int GS, int V>
+template <int GS, int V, bool FULL>
 __device__ __forceinline__ void finish_row(Row<V>& d, const Row<V>& y, const float4* xraw,
                                            float inv_self, bool uniq, bool act, float lr,
                                            float* erow, float* grow, int lane, int nvec,
@@ -527,24 +530,24 @@ __device__ __forceinline__ void finish_row(Row<V>& d, const Row<V>& y, const flo
   if (uniq) {
     if (act) {                     // inactive hinge: zero gradient, row unchanged
       Row<V> x;
-      row_from_smem<GS, V>(x, xraw, lane, nvec);
+      row_from_smem<GS, V, FULL>(x, xraw, lane, nvec);
 #pragma unroll
       for (int k = 0; k < 4 * V; ++k) {
         d.re[k] = x.re[k] - lr * d.re[k];
         d.im[k] = x.im[k] - lr * d.im[k];
       }
-      row_store<GS, V>(d, erow, lane, nvec);
+      row_store<GS, V, FULL>(d, erow, lane, nvec);
     }
   } else {
-    row_store<GS, V>(d, grow, lane, nvec);
+    row_store<GS, V, FULL>(d, grow, lane, nvec);
   }
 }
 
 // yh, yt, yr, yn: the clipped rows (y = x * s)
-template <int GS, int V, int ROLE>
+template <int GS, int V, int ROLE, int side, bool FULL>
 __device__ __forceinline__ void emit_row(const Row<V>& yh, const Row<V>& yt, const Row<V>& yr,
                                          const Row<V>& yn, const float4* xraw, float inv_self,
-                                         int side, float gp, float gn, bool uniq, bool act, float lr,
+                                         float gp, float gn, bool uniq, bool act, float lr,
                                          float* erow, float* grow, int lane, int nvec,
                                          unsigned gmask) {
   Row<V> d;
@@ -575,7 +578,7 @@ __device__ __forceinline__ void emit_row(const Row<V>& yh, const Row<V>& yt, con
     d.re[k] = gre;
     d.im[k] = gim;
   }
-  finish_row<GS, V>(d, ys, xraw, inv_self, uniq, act, lr, erow, grow, lane, nvec, gmask);
+  finish_row<GS, V, FULL>(d, ys, xraw, inv_self, uniq, act, lr, erow, grow, lane, nvec, gmask);
 }
 
 struct TripleIds { int i, h, t, r, n; };
@@ -593,11 +596,11 @@ __device__ __forceinline__ TripleIds load_ids(const int32_t* __restrict__ tri,
 constexpr int K1_STAGES = 3;   // landing buffers per lane group: the triple being computed (its
                                // unscaled rows are re-read for the in-place update) + 2 in flight
 
-template <int GS, int V>
-__global__ void __launch_bounds__(256)
-hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri,
+template <int GS, int V, int side, bool FULL>
+__device__ __forceinline__ void
+hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
                           const int32_t* __restrict__ neg, const int32_t* __restrict__ perm,
-                          const uint8_t* __restrict__ uniq, int side, int B, int T, int nvec,
+                          const uint32_t* __restrict__ gslot, int B, int T, int nvec,
                           int stride, float margin, float lr, float* __restrict__ G,
                           float* __restrict__ loss, float* __restrict__ sigma) {
   extern __shared__ float4 k1_smem[];
@@ -615,9 +618,9 @@ hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri
 
   auto fetch = [&](const TripleIds& d, int stage) {
     float4* sb = my_smem + (size_t)stage * 3 * row4;
-    row_fetch_async<GS, V>(sb, E + (size_t)d.h * stride, lane, nvec);
-    row_fetch_async<GS, V>(sb + row4, E + (size_t)d.t * stride, lane, nvec);
-    row_fetch_async<GS, V>(sb + 2 * row4, E + (size_t)d.n * stride, lane, nvec);
+    row_fetch_async<GS, V, FULL>(sb, E + (size_t)d.h * stride, lane, nvec);
+    row_fetch_async<GS, V, FULL>(sb + row4, E + (size_t)d.t * stride, lane, nvec);
+    row_fetch_async<GS, V, FULL>(sb + 2 * row4, E + (size_t)d.n * stride, lane, nvec);
   };
 
   TripleIds c = load_ids(tri, neg, perm, g0);
@@ -637,8 +640,9 @@ hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri
 
   // end of a run of equal relation: clip backward of the summed gradient, then apply / stage
   auto flush_relation = [&]() {
-    finish_row<GS, V>(acc, yr, rel_smem, ir, uniq[run_i] != 0, run_act, lr,
-                      E + (size_t)r_cur * stride, G + (size_t)run_i * stride, lane, nvec, gmask);
+    const uint32_t sl = gslot[run_i];
+    finish_row<GS, V, FULL>(acc, yr, rel_smem, ir, sl == HOLE_SLOT_UNIQUE, run_act, lr,
+                      E + (size_t)r_cur * stride, G + (size_t)sl * stride, lane, nvec, gmask);
   };
 
   int stage = 0;
@@ -649,9 +653,9 @@ hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri
     cp_async_commit();
     cp_async_wait<2>();                                         // rows of triple g have landed
     const float4* sb = my_smem + (size_t)stage * 3 * row4;
-    row_from_smem<GS, V>(yh, sb, lane, nvec);
-    row_from_smem<GS, V>(yt, sb + row4, lane, nvec);
-    row_from_smem<GS, V>(yn, sb + 2 * row4, lane, nvec);
+    row_from_smem<GS, V, FULL>(yh, sb, lane, nvec);
+    row_from_smem<GS, V, FULL>(yt, sb + row4, lane, nvec);
+    row_from_smem<GS, V, FULL>(yn, sb + 2 * row4, lane, nvec);
 
     if (c.r != r_cur) {                      // group-uniform
       if (r_cur >= 0) flush_relation();
@@ -676,7 +680,7 @@ hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri
       row_zero(acc);
     }
     const int i = c.i;
-    const bool uq_t = uniq[B + i] != 0, uq_h = uniq[2 * B + i] != 0, uq_n = uniq[3 * B + i] != 0;
+    const uint32_t sl_t = gslot[B + i], sl_h = gslot[2 * B + i], sl_n = gslot[3 * B + i];
 
     float ssh = row_sumsq(yh), sst = row_sumsq(yt), ssn = row_sumsq(yn);
 #pragma unroll
@@ -725,12 +729,12 @@ hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri
       acc.re[k] += gp * (a * e + b * f) + gn * (a2 * e2 + b2 * f2);
       acc.im[k] += gp * (a * f - b * e) + gn * (a2 * f2 - b2 * e2);
     }
-    emit_row<GS, V, ROLE_T>(yh, yt, yr, yn, sb + row4, it, side, gp, gn, uq_t, act, lr,
-                            E + (size_t)c.t * stride, G + (size_t)(1 * (int64_t)B + i) * stride, lane, nvec, gmask);
-    emit_row<GS, V, ROLE_H>(yh, yt, yr, yn, sb, ih, side, gp, gn, uq_h, act, lr,
-                            E + (size_t)c.h * stride, G + (size_t)(2 * (int64_t)B + i) * stride, lane, nvec, gmask);
-    emit_row<GS, V, ROLE_N>(yh, yt, yr, yn, sb + 2 * row4, in_, side, gp, gn, uq_n, act, lr,
-                            E + (size_t)c.n * stride, G + (size_t)(3 * (int64_t)B + i) * stride, lane, nvec, gmask);
+    emit_row<GS, V, ROLE_T, side, FULL>(yh, yt, yr, yn, sb + row4, it, gp, gn, sl_t == HOLE_SLOT_UNIQUE, act, lr,
+                            E + (size_t)c.t * stride, G + (size_t)sl_t * stride, lane, nvec, gmask);
+    emit_row<GS, V, ROLE_H, side, FULL>(yh, yt, yr, yn, sb, ih, gp, gn, sl_h == HOLE_SLOT_UNIQUE, act, lr,
+                            E + (size_t)c.h * stride, G + (size_t)sl_h * stride, lane, nvec, gmask);
+    emit_row<GS, V, ROLE_N, side, FULL>(yh, yt, yr, yn, sb + 2 * row4, in_, gp, gn, sl_n == HOLE_SLOT_UNIQUE, act, lr,
+                            E + (size_t)c.n * stride, G + (size_t)sl_n * stride, lane, nvec, gmask);
     c = n1;
     n1 = n2;
     n2 = n3;
@@ -738,6 +742,24 @@ hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri
   }
   cp_async_wait<0>();
   flush_relation();
+}
+
+template <int GS, int V>
+__global__ void __launch_bounds__(256)
+hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri,
+                          const int32_t* __restrict__ neg, const int32_t* __restrict__ perm,
+                          const uint32_t* __restrict__ gslot, int side, int B, int T, int nvec,
+                          int stride, float margin, float lr, float* __restrict__ G,
+                          float* __restrict__ loss, float* __restrict__ sigma) {
+  // specialise on the corruption side and on "every lane owns valid float4s" (nvec == GS*V)
+  const bool full = (nvec == GS * V);
+  if (side) {
+    if (full) hole_train_fwd_bwd_body<GS, V, 1, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma);
+    else      hole_train_fwd_bwd_body<GS, V, 1, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma);
+  } else {
+    if (full) hole_train_fwd_bwd_body<GS, V, 0, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma);
+    else      hole_train_fwd_bwd_body<GS, V, 0, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -749,13 +771,11 @@ hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri
 // Partials reuse the (already consumed) staged gradient row of a node's first occurrence.
 // ---------------------------------------------------------------------------------------
 
-// acc = sum over q < cnt (<= C) of the staged rows G[idx(q)], in q order, with the loads of
-// NB rows in flight at a time.  idx0/idx1 hold this lane's share of the row indices:
-// lane l has idx(l) in idx0 and idx(l + GS) in idx1.
+// acc = sum over q < cnt (<= C) of the staged rows G[first + q*step], in q order, NB row
+// loads in flight at a time.
 template <int GS, int V>
-__device__ __forceinline__ void sum_rows(Row<V>& acc, const float* __restrict__ G, uint32_t idx0,
-                                         uint32_t idx1, int cnt, int stride, int lane, int nvec,
-                                         unsigned gmask, int gbase) {
+__device__ __forceinline__ void sum_rows(Row<V>& acc, const float* __restrict__ G, int64_t first,
+                                         int64_t step, int cnt, int stride, int lane, int nvec) {
   constexpr int C = HOLE_TREE_C;
   constexpr int NB = (V == 1) ? 8 : 4;
   row_zero(acc);
@@ -766,8 +786,7 @@ __device__ __forceinline__ void sum_rows(Row<V>& acc, const float* __restrict__ 
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
       const int q = q0 + u;
-      const uint32_t p = __shfl_sync(gmask, (q < GS) ? idx0 : idx1, gbase + (q % GS));
-      if (q < cnt) row_load<GS, V, false>(x[u], G + (size_t)p * stride, lane, nvec);
+      if (q < cnt) row_load<GS, V, false>(x[u], G + (size_t)(first + q * step) * stride, lane, nvec);
       else row_zero(x[u]);
     }
 #pragma unroll
@@ -777,67 +796,63 @@ __device__ __forceinline__ void sum_rows(Row<V>& acc, const float* __restrict__ 
 
 template <int GS, int V>
 __global__ void __launch_bounds__(256)
-hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint32_t* __restrict__ spos,
-                  const uint4* __restrict__ heads, const int* __restrict__ nheads,
-                  int* __restrict__ counters, int M, int nvec, int stride, float lr) {
+hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __restrict__ heads,
+                  const int* __restrict__ nheads, int* __restrict__ counters, int M, int nvec,
+                  int stride, float lr) {
   constexpr int C = HOLE_TREE_C;
-  static_assert(C <= 2 * GS, "index broadcast assumes C <= 2*GS");
   const int lane = threadIdx.x % GS;
   const int gbase = (threadIdx.x % 32) / GS * GS;
   const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << gbase);
-  const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
-  if (g >= *nheads) return;
-  const uint4 hd = heads[g];
-  const int j = (int)hd.x, s = (int)hd.y, n = (int)hd.z, row = (int)hd.w;
-  const int rel = j - s;
-  const int cnt = min(C, n - rel);
-
-  Row<V> acc;
-  {
-    const uint32_t i0 = (lane < cnt) ? spos[j + lane] : 0u;
-    const uint32_t i1 = (lane + GS < cnt) ? spos[j + lane + GS] : 0u;
-    sum_rows<GS, V>(acc, G, i0, i1, cnt, stride, lane, nvec, gmask, gbase);
-  }
-  int level = 0, idx = rel / C, nl = (n + C - 1) / C;
-  int64_t span = C;   // sorted entries covered by one node of this level
-  while (true) {
-    if (nl == 1) {    // root: apply   E[row] -= lr * acc   (holE.py:296)
-      float* erow = E + (size_t)row * stride;
-      Row<V> x;
-      row_load<GS, V, false>(x, erow, lane, nvec);
+  // persistent: a fixed grid strides over the step's work list (its length is only known on
+  // the device)
+  const int nh = *nheads;
+  const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / GS;
+  for (int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS; g < nh; g += gstride) {
+    const uint4 hd = heads[g];
+    const int j = (int)hd.x, s = (int)hd.y, n = (int)hd.z, row = (int)hd.w;
+    const int rel = j - s;
+    const int cnt = min(C, n - rel);
+    float* erow = E + (size_t)row * stride;
+    Row<V> acc, x;
+    const bool single = n <= C;      // this leaf is also the root: fetch the table row alongside
+    if (single) row_load<GS, V, false>(x, erow, lane, nvec);
+    sum_rows<GS, V>(acc, G, j, 1, cnt, stride, lane, nvec);
+    int level = 0, idx = rel / C, nl = (n + C - 1) / C;
+    int64_t span = C;   // sorted entries covered by one node of this level
+    while (true) {
+      if (nl == 1) {    // root: apply   E[row] -= lr * acc   (holE.py:296)
+        if (!single) row_load<GS, V, false>(x, erow, lane, nvec);
 #pragma unroll
-      for (int k = 0; k < 4 * V; ++k) {
-        x.re[k] -= lr * acc.re[k];
-        x.im[k] -= lr * acc.im[k];
+        for (int k = 0; k < 4 * V; ++k) {
+          x.re[k] -= lr * acc.re[k];
+          x.im[k] -= lr * acc.im[k];
+        }
+        row_store<GS, V>(x, erow, lane, nvec);
+        break;
       }
-      row_store<GS, V>(x, erow, lane, nvec);
-      return;
+      // partial of node (level, idx) overwrites the (consumed) first gradient row of the node
+      row_store<GS, V>(acc, G + (size_t)(s + idx * span) * stride, lane, nvec);
+      __threadfence();
+      __syncwarp(gmask);
+      const int parent = idx / C;
+      const int nchild = min(C, nl - parent * C);
+      int* ctr = counters + (size_t)level * M + (s + parent * span * C);
+      int ticket = 0;
+      if (lane == 0) ticket = atomicAdd(ctr, 1);
+      ticket = __shfl_sync(gmask, ticket, gbase);
+      if (ticket != nchild - 1) break;
+      if (lane == 0) *ctr = 0;          // self-reset for the next step
+      __threadfence();
+      sum_rows<GS, V>(acc, G, s + (parent * (int64_t)C) * span, span, nchild, stride, lane, nvec);
+      ++level;
+      idx = parent;
+      nl = (nl + C - 1) / C;
+      span *= C;
     }
-    row_store<GS, V>(acc, G + (size_t)spos[s + idx * span] * stride, lane, nvec);
-    __threadfence();
-    __syncwarp(gmask);
-    const int parent = idx / C;
-    const int nchild = min(C, nl - parent * C);
-    int* ctr = counters + (size_t)level * M + (s + parent * span * C);
-    int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(ctr, 1);
-    ticket = __shfl_sync(gmask, ticket, gbase);
-    if (ticket != nchild - 1) return;
-    if (lane == 0) *ctr = 0;          // self-reset for the next step
-    __threadfence();
-    {
-      const int64_t cb = s + (parent * (int64_t)C) * span;
-      const uint32_t i0 = (lane < nchild) ? spos[cb + lane * span] : 0u;
-      const uint32_t i1 = (lane + GS < nchild) ? spos[cb + (lane + GS) * span] : 0u;
-      sum_rows<GS, V>(acc, G, i0, i1, nchild, stride, lane, nvec, gmask, gbase);
-    }
-    ++level;
-    idx = parent;
-    nl = (nl + C - 1) / C;
-    span *= C;
   }
 }
 
+// ---------------------------------------------------------------------------------------
 
 // deterministic per-step loss sum: one CTA per step, fixed-shape tree
 __global__ void __launch_bounds__(256)
@@ -956,10 +971,10 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
 
 static void plan_free(hole_plan& p) {
   cudaFree(p.keysA); cudaFree(p.keysB); cudaFree(p.valsA); cudaFree(p.valsB);
-  cudaFree(p.uniq); cudaFree(p.heads); cudaFree(p.nheads); cudaFree(p.neg); cudaFree(p.ghist); cudaFree(p.perm);
+  cudaFree(p.gslot); cudaFree(p.heads); cudaFree(p.nheads); cudaFree(p.neg); cudaFree(p.ghist); cudaFree(p.perm);
   p.perm = nullptr;
   p.keysA = p.keysB = p.valsA = p.valsB = nullptr;
-  p.uniq = nullptr; p.heads = nullptr; p.nheads = nullptr; p.neg = nullptr; p.ghist = nullptr;
+  p.gslot = nullptr; p.heads = nullptr; p.nheads = nullptr; p.neg = nullptr; p.ghist = nullptr;
   p.skey = p.spos = nullptr;
 }
 
@@ -1025,7 +1040,7 @@ int hole_ws_reserve(hole_ctx* c, int64_t B, int64_t S) {
     hole_plan& p = c->plan[k];
     WS_ALLOC(p.keysA, S * M * 4); WS_ALLOC(p.keysB, S * M * 4);
     WS_ALLOC(p.valsA, S * M * 4); WS_ALLOC(p.valsB, S * M * 4);
-    WS_ALLOC(p.uniq, S * M);
+    WS_ALLOC(p.gslot, S * M * 4);
     WS_ALLOC(p.heads, (size_t)S * (M / 2 + 1) * sizeof(uint4));
     WS_ALLOC(p.nheads, (size_t)S * 4);
     WS_ALLOC(p.neg, (size_t)S * B * 4);
@@ -1158,7 +1173,7 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
   pl.heads_cap = M / 2 + 1;
   HOLE_CUDA_TRY(cudaMemsetAsync(pl.nheads, 0, (size_t)S * 4, ps));
   dim3 sgrid((unsigned)std::min<int64_t>((M + 255) / 256, 1024), (unsigned)S);
-  hole_plan_segments_kernel<<<sgrid, 256, 0, ps>>>(pl.skey, pl.spos, pl.uniq, pl.heads, pl.nheads, M,
+  hole_plan_segments_kernel<<<sgrid, 256, 0, ps>>>(pl.skey, pl.spos, pl.gslot, pl.heads, pl.nheads, M,
                                                   pl.heads_cap);
   HOLE_LAUNCHED();
   HOLE_CUDA_TRY(cudaEventRecord(pl.ready, ps));
@@ -1185,12 +1200,13 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
     HOLE_CUDA_TRY(cudaEventRecord(pe[0], st));
   }
   HOLE_DISPATCH_SMEM(c, hole_train_fwd_bwd_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
-                     c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.uniq + off, side, (int)B, pl.T, c->nvec,
+                     c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
                 c->row_stride, margin, lr, c->G, loss_out, sigma_out);
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[1], st));
-  HOLE_DISPATCH(c, hole_apply_kernel, grid_for_groups(pl.heads_cap, c->gs), 256, st, table, c->G,
-                pl.spos + off, pl.heads + (size_t)slot * pl.heads_cap, pl.nheads + slot, c->counters, M,
-                c->nvec, c->row_stride, lr);
+  const unsigned k3_grid = std::min<unsigned>(grid_for_groups(pl.heads_cap, c->gs), (unsigned)c->sm_count * 4);
+  HOLE_DISPATCH(c, hole_apply_kernel, k3_grid, 256, st, table, c->G,
+                pl.heads + (size_t)slot * pl.heads_cap, pl.nheads + slot, c->counters, M, c->nvec,
+                c->row_stride, lr);
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[2], st));
   return HOLE_OK;
 }
