@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhole_b200.so")
 
-HOLE_SIDE_TAIL, HOLE_SIDE_HEAD = 0, 1
+HOLE_SIDE_TAIL, HOLE_SIDE_HEAD, HOLE_SIDE_BOTH = 0, 1, 2
 HOLE_RANK_BF16, HOLE_RANK_BF16X3 = 0, 1
 ABI_VERSION = 1
 

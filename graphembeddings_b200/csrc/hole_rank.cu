@@ -37,6 +37,7 @@ enum { MODE_COUNT = 0, MODE_DIAG = 1 };
 struct RankParams {
   int mode;
   int num_kb;        // K / 64
+  int last_kb_mmas;  // K=16 slices of the last k-block that hold real columns (the rest is zero padding)
   int stages;        // ring depth for candidate k-blocks
   int m_tiles;       // query tiles
   int n_tiles;       // candidate tiles (COUNT mode)
@@ -235,11 +236,14 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
             const uint32_t a_addr = smem_u32(sA + (size_t)kb * A_KB_BYTES);
             const uint32_t b_addr = smem_u32(sB + (size_t)stage * B_KB_BYTES);
+            const int nk = (kb == p.num_kb - 1) ? p.last_kb_mmas : BK / UMMA_K;   // skip all-zero slices
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2);
-              const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2);
-              umma_bf16(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (k < nk) {
+                const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2);
+                const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2);
+                umma_bf16(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
             }
             umma_commit(&sl->empty[stage]);          // frees the smem slot when the MMAs retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -368,7 +372,14 @@ hole_rank_pack_query_kernel(const float* __restrict__ table, int stride, int H,
     if (lane == 0) true_idx[qi] = -1;
     return;
   }
-  const int h = queries[3 * qi], t = queries[3 * qi + 1], r = queries[3 * qi + 2];
+  // HOLE_SIDE_BOTH: Q = 2 * Qsrc rows, the first half ranks tails, the second half heads
+  int64_t src = qi;
+  if (side == HOLE_SIDE_BOTH) {
+    const int64_t half = Q / 2;
+    side = (qi < half) ? HOLE_SIDE_TAIL : HOLE_SIDE_HEAD;
+    src = (qi < half) ? qi : qi - half;
+  }
+  const int h = queries[3 * src], t = queries[3 * src + 1], r = queries[3 * src + 2];
   const int Hp = stride / 2;
   const float* x1 = table + (size_t)(side == HOLE_SIDE_TAIL ? h : r) * stride;   // first factor
   const float* x2 = table + (size_t)(side == HOLE_SIDE_TAIL ? r : t) * stride;   // second factor
@@ -498,8 +509,9 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
                          const int64_t* filter_off, const int32_t* filter_ids, float* true_score_io,
                          int compute_true, int32_t* raw_before, int32_t* filt_before, void* stream) {
   HOLE_CHECK_ARG(c && Q >= 0 && ent_begin >= 0 && ent_end >= ent_begin && ent_end <= c->n_rows);
-  HOLE_CHECK_ARG(side == HOLE_SIDE_TAIL || side == HOLE_SIDE_HEAD);
+  HOLE_CHECK_ARG(side == HOLE_SIDE_TAIL || side == HOLE_SIDE_HEAD || side == HOLE_SIDE_BOTH);
   if (Q == 0 || ent_end == ent_begin) return HOLE_OK;
+  if (side == HOLE_SIDE_BOTH) Q *= 2;    // output rows: [tail ranks of all queries | head ranks]
   HOLE_CHECK_ARG(table && queries && true_score_io && raw_before && filt_before);
   HOLE_CHECK_ARG((filter_off == nullptr) == (filter_ids == nullptr));
   if (precision != HOLE_RANK_BF16)
@@ -561,6 +573,7 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
 
   RankParams p{};
   p.num_kb = num_kb;
+  p.last_kb_mmas = (c->dim - (num_kb - 1) * BK + UMMA_K - 1) / UMMA_K;
   p.stages = stages;
   p.m_tiles = Qpad / BM;
   p.Q = (int)Q;

@@ -11,9 +11,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import HOLE_RANK_BF16, HOLE_RANK_BF16X3, HOLE_SIDE_HEAD, HOLE_SIDE_TAIL, HoleError, check
+from ._lib import (HOLE_RANK_BF16, HOLE_RANK_BF16X3, HOLE_SIDE_BOTH, HOLE_SIDE_HEAD, HOLE_SIDE_TAIL,
+                   HoleError, check)
 
-__all__ = ["HoleEngine", "HoleError", "inverse_time_decay", "HOLE_SIDE_TAIL", "HOLE_SIDE_HEAD",
+__all__ = ["HoleEngine", "HoleError", "inverse_time_decay", "HOLE_SIDE_TAIL", "HOLE_SIDE_HEAD", "HOLE_SIDE_BOTH",
            "HOLE_RANK_BF16", "HOLE_RANK_BF16X3"]
 
 
@@ -183,6 +184,9 @@ class HoleEngine:
         Counts are accumulated into raw_before / filt_before when given (candidate shards)."""
         q = self._triples(queries)
         Q = q.shape[0]
+        nq = Q
+        if int(side) == HOLE_SIDE_BOTH:
+            Q = 2 * Q          # rows [0,nq) tail ranks, [nq,2nq) head ranks
         if raw_before is None:
             raw_before = torch.zeros(Q, dtype=torch.int32, device=self.device)
         if filt_before is None:
@@ -194,7 +198,7 @@ class HoleEngine:
             fo = torch.as_tensor(filter_off).to(torch.int64).to(self.device).contiguous()
             fi = torch.as_tensor(filter_ids).to(torch.int32).to(self.device).contiguous()
         check(self.lib.hole_rank(self._ctx, _ptr(self.table), int(ent_begin), int(ent_end), _ptr(q),
-                                 Q, int(side), int(precision), _ptr(fo), _ptr(fi), _ptr(true_score),
+                                 nq, int(side), int(precision), _ptr(fo), _ptr(fi), _ptr(true_score),
                                  1 if compute_true else 0, _ptr(raw_before), _ptr(filt_before),
                                  _stream()))
         return raw_before, filt_before, true_score

@@ -50,6 +50,7 @@ typedef struct hole_ctx hole_ctx;
 
 #define HOLE_SIDE_TAIL 0         /* corrupt / rank tails */
 #define HOLE_SIDE_HEAD 1         /* corrupt / rank heads */
+#define HOLE_SIDE_BOTH 2         /* hole_rank only: tails then heads in one pass */
 
 /* Operand precision of the tensor-core ranking contraction. */
 #define HOLE_RANK_BF16   0       /* bf16 operands, fp32 accumulate                      */
@@ -149,7 +150,10 @@ HOLE_API int hole_train_steps_host(hole_ctx* ctx, float* table, const int32_t* t
  * true_score_io float32[Q]: if compute_true != 0 it is written for queries whose true
  * candidate lies in [ent_begin, ent_end) and left untouched otherwise (so candidate shards
  * on several GPUs can be combined by the caller); if compute_true == 0 it is read.
- * Counts are ADDED to raw_before / filt_before (caller zeroes them), so shards accumulate. */
+ * Counts are ADDED to raw_before / filt_before (caller zeroes them), so shards accumulate.
+ * side == HOLE_SIDE_BOTH ranks both sides in one pass (candidates packed once): every
+ * per-query array (true_score_io, raw_before, filt_before, and filter_off with 2Q+1 entries)
+ * then has 2Q rows -- rows [0,Q) are the tail ranks, rows [Q,2Q) the head ranks. */
 HOLE_API int hole_rank(hole_ctx* ctx, const float* table, int64_t ent_begin, int64_t ent_end,
               const int32_t* queries, int64_t Q, int side, int precision,
               const int64_t* filter_off, const int32_t* filter_ids,

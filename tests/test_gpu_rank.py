@@ -208,3 +208,19 @@ def test_sharded_rank_single_rank_matches_engine(eng_mod):
     tr = RowShardedTrainer(kg.n_relations, kg.n_entities, kg.dim, be, None).load_embeddings(kg.E)
     raw2, filt2 = tr.rank(torch.from_numpy(kg.triples), 0, foff, fids)
     assert torch.equal(raw1, raw2) and torch.equal(filt1, filt2)
+
+
+def test_both_sides_in_one_pass_equals_two_calls(eng_mod):
+    kg, e = _setup(eng_mod, 6, 2500, 300, 150, seed=35)
+    known = D.synthetic_kg(6, 2500, 8000, 4, 8, seed=97, with_embeddings=False).triples
+    ft = D.build_filter_csr(kg.triples, known, "tail")
+    fh = D.build_filter_csr(kg.triples, known, "head")
+    rt, flt, tst = e.rank(kg.triples, 0, kg.n_relations, kg.n_rows, *ft)
+    rh, flh, tsh = e.rank(kg.triples, 1, kg.n_relations, kg.n_rows, *fh)
+    fo = np.concatenate([ft[0], fh[0][1:] + ft[0][-1]])
+    fi = np.concatenate([ft[1], fh[1]])
+    rb, flb, tsb = e.rank(kg.triples, eng_mod.HOLE_SIDE_BOTH, kg.n_relations, kg.n_rows, fo, fi)
+    Q = len(kg.triples)
+    assert torch.equal(rb[:Q], rt) and torch.equal(rb[Q:], rh)
+    assert torch.equal(flb[:Q], flt) and torch.equal(flb[Q:], flh)
+    assert torch.equal(tsb[:Q], tst) and torch.equal(tsb[Q:], tsh)
