@@ -27,6 +27,26 @@ import numpy as np
 import torch
 
 
+TIMING = None      # set to a dict to collect a per-section breakdown (tools/sharded_breakdown.py)
+
+
+class _Section:
+    """Synchronising section timer, active only when sharded.TIMING is a dict."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMING is not None:
+            torch.cuda.synchronize()
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *a):
+        if TIMING is not None:
+            torch.cuda.synchronize()
+            TIMING[self.name] = TIMING.get(self.name, 0.0) + (time.perf_counter() - self.t0) * 1e3
+
+
 def row_partition(n_entities, world):
     """Contiguous blocks of entity rows; returns rows_per_rank."""
     return (n_entities + world - 1) // world
@@ -132,34 +152,46 @@ class RowShardedTrainer:
         dev = self.shard.device
         pos = torch.as_tensor(pos_local).to(dev).long()
         B, R = pos.shape[0], self.R
-        side, neg = self.be.corrupt(pos.to(torch.int32), seed, step, self.my_rank * B)
-        neg = neg.to(dev)
-        ents = torch.cat([pos[:, 0], pos[:, 1], neg])
-        uniq, inv = torch.unique(ents, return_inverse=True)
-        U = uniq.shape[0]
-        send_counts, recv_counts = self._route(uniq)
-        ids_in = self._a2a(uniq, send_counts, recv_counts)              # rows others want from me
-        rows_out = self.shard.index_select(0, ids_in - self.begin + R)
-        rows_in = self._a2a(rows_out, recv_counts, send_counts)         # in `uniq` order
-        W = self.be.W
-        W[:R].copy_(self.shard[:R])
-        W[R:R + U].copy_(rows_in)
-        W0 = W[: R + U].clone()
-        pos_w = torch.stack([R + inv[:B], R + inv[B:2 * B], pos[:, 2]], dim=1)
-        neg_w = R + inv[2 * B:]
-        loss = self.be.step(R + U, pos_w, neg_w, side, margin, lr)
-        delta = W[: R + U] - W0
-        d_rel = delta[:R].contiguous()
-        if self.world > 1:
-            self.dist.all_reduce(d_rel)
-        self.shard[:R] += d_rel
-        d_in = self._a2a(delta[R:], send_counts, recv_counts)           # grouped by source rank
-        off = 0
-        for k in range(self.world):                                     # rank order: deterministic
-            n_k = recv_counts[k]
-            if n_k:
-                self.shard.index_add_(0, ids_in[off:off + n_k] - self.begin + R, d_in[off:off + n_k])
-            off += n_k
+        with _Section("corrupt"):
+            side, neg = self.be.corrupt(pos.to(torch.int32), seed, step, self.my_rank * B)
+            neg = neg.to(dev)
+        with _Section("unique"):
+            ents = torch.cat([pos[:, 0], pos[:, 1], neg])
+            uniq, inv = torch.unique(ents, return_inverse=True)
+            U = uniq.shape[0]
+        with _Section("route (counts, host sync)"):
+            send_counts, recv_counts = self._route(uniq)
+        with _Section("a2a ids"):
+            ids_in = self._a2a(uniq, send_counts, recv_counts)              # rows others want from me
+        with _Section("gather rows"):
+            rows_out = self.shard.index_select(0, ids_in - self.begin + R)
+        with _Section("a2a rows"):
+            rows_in = self._a2a(rows_out, recv_counts, send_counts)         # in `uniq` order
+        with _Section("assemble W, W0"):
+            W = self.be.W
+            W[:R].copy_(self.shard[:R])
+            W[R:R + U].copy_(rows_in)
+            W0 = W[: R + U].clone()
+            pos_w = torch.stack([R + inv[:B], R + inv[B:2 * B], pos[:, 2]], dim=1)
+            neg_w = R + inv[2 * B:]
+        with _Section("local step (plan+K1+K3)"):
+            loss = self.be.step(R + U, pos_w, neg_w, side, margin, lr)
+        with _Section("delta"):
+            delta = W[: R + U] - W0
+            d_rel = delta[:R].contiguous()
+        with _Section("allreduce relations"):
+            if self.world > 1:
+                self.dist.all_reduce(d_rel)
+            self.shard[:R] += d_rel
+        with _Section("a2a deltas"):
+            d_in = self._a2a(delta[R:], send_counts, recv_counts)           # grouped by source rank
+        with _Section("apply deltas"):
+            off = 0
+            for k in range(self.world):                                     # rank order: deterministic
+                n_k = recv_counts[k]
+                if n_k:
+                    self.shard.index_add_(0, ids_in[off:off + n_k] - self.begin + R, d_in[off:off + n_k])
+                off += n_k
         return loss
 
     # ------------------------------------------------------------------ ranking
