@@ -15,6 +15,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "hole_common.cuh"
@@ -29,7 +31,7 @@ constexpr int A_KB_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_KB_BYTES = BN * BK * 2;   // 32 KB
 constexpr int RANK_THREADS = 320;
 constexpr int EPI_WARPS = 8;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;     // barrier slots; the single-CTA kernel uses at most 4 (32 KB stages)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 enum { MODE_COUNT = 0, MODE_DIAG = 1 };
@@ -136,6 +138,67 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+
+// ---- CTA-pair (cta_group::2) variants
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by either CTA of the pair; the transaction bytes are credited to the barrier
+// at the same offset in CTA 0 (peer bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                 int c0, int c1) {
+  uint32_t bar0;   // shared::cluster address of the same barrier in CTA 0
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar0) : "r"(smem_u32(bar)), "r"(0));
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(bar0), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (128 rows per CTA) * B^T (N/2 rows per CTA), issued by CTA 0 only
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs when the pair's MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// arrive on the barrier at this offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
 }
 
 // K-major, 128-byte-swizzled operand tile whose rows are 128 bytes (64 bf16): 8-row groups
@@ -323,9 +386,190 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   }
+  __syncwarp();          // the single-lane roles rejoin their warps
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------ CTA-pair kernel
+// Same contraction with cta_group::2: a cluster of two CTAs (one SM pair) computes a
+// 256-query x 256-candidate tile per MMA.  Each CTA keeps its own 128 query rows and loads only
+// HALF of every candidate k-block (128 rows), which halves the per-SM operand traffic that
+// bounds the single-CTA kernel; CTA 0 issues the MMAs for both, every CTA runs the epilogue
+// on its own TMEM (its 128 rows x all 256 columns).
+constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;   // 16 KB
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RANK_THREADS, 1)
+hole_rank_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const RankParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                       // num_kb x 16 KB (my 128 query rows)
+  uint8_t* sB = smem + (size_t)p.num_kb * A_KB_BYTES;       // stages x 16 KB (my half of the tile)
+  SmemLayout* sl = reinterpret_cast<SmemLayout*>(sB + (size_t)p.stages * B_HALF_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();                   // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_items = p.m_tiles * p.n_chunks;               // m_tiles counts 256-row query pairs here
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&sl->full[s], 1); mbar_init(&sl->empty[s], 1); }
+    mbar_init(&sl->a_full, 1);
+    mbar_init(&sl->a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sl->tmem_full[s], 1);
+      mbar_init(&sl->tmem_empty[s], 2 * EPI_WARPS);         // both CTAs' epilogue warps (used in CTA 0)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(&sl->tmem_base, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = sl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
+      for (int item = pair; item < n_items; item += n_pairs) {
+        const int m_pair = item / p.n_chunks, chunk = item % p.n_chunks;
+        const int m_tile = m_pair * 2 + (int)cta;
+        mbar_wait(&sl->a_empty, a_phase ^ 1);
+        if (cta == 0) mbar_expect_tx(&sl->a_full, (uint32_t)(2 * p.num_kb * A_KB_BYTES));
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_2d_pair(sA + (size_t)kb * A_KB_BYTES, &tmA, &sl->a_full, kb * BK, m_tile * BM);
+        a_phase ^= 1;
+        const int t0 = (p.mode == MODE_DIAG) ? 0 : chunk * p.chunk_tiles;
+        const int t1 = (p.mode == MODE_DIAG) ? 1 : min(p.n_tiles, t0 + p.chunk_tiles);
+        for (int t = t0; t < t1; ++t) {
+          const int row0 = ((p.mode == MODE_DIAG) ? m_pair * BN : t * BN) + (int)cta * (BN / 2);
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&sl->empty[stage], phase ^ 1);
+            if (cta == 0) mbar_expect_tx(&sl->full[stage], 2 * B_HALF_BYTES);
+            tma_load_2d_pair(sB + (size_t)stage * B_HALF_BYTES, &tmB, &sl->full[stage], kb * BK, row0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (CTA 0 only) =====================
+    if (lane == 0 && cta == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = pair; item < n_items; item += n_pairs) {
+        const int chunk = item % p.n_chunks;
+        mbar_wait(&sl->a_full, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+        const int t0 = (p.mode == MODE_DIAG) ? 0 : chunk * p.chunk_tiles;
+        const int t1 = (p.mode == MODE_DIAG) ? 1 : min(p.n_tiles, t0 + p.chunk_tiles);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&sl->tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_addr = tmem_base + (uint32_t)acc * BN;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&sl->full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + (size_t)kb * A_KB_BYTES);
+            const uint32_t b_addr = smem_u32(sB + (size_t)stage * B_HALF_BYTES);
+            const int nk = (kb == p.num_kb - 1) ? p.last_kb_mmas : BK / UMMA_K;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (k < nk) {
+                const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2);
+                const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2);
+                umma_bf16_pair(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit_pair(&sl->empty[stage]);     // frees the stage in both CTAs
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_pair(&sl->tmem_full[acc]);     // accumulators of both CTAs ready
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        umma_commit_pair(&sl->a_empty);              // query tiles of both CTAs may be overwritten
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own TMEM) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const int row_in_tile = quarter * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = pair; item < n_items; item += n_pairs) {
+      const int m_pair = item / p.n_chunks, chunk = item % p.n_chunks;
+      const int q = (m_pair * 2 + (int)cta) * BM + row_in_tile;
+      const bool qok = q < p.Q;
+      float thr = -INFINITY, thr_hi = -INFINITY;
+      int tie = 0;
+      if (p.mode == MODE_COUNT && qok) {
+        thr = p.true_score[q];
+        thr_hi = nextafterf(thr, INFINITY);
+        const int ti = p.true_idx[q];
+        tie = ti < 0 ? 0 : (ti > p.Nc ? p.Nc : ti);
+      }
+      int cnt = 0;
+      const int t0 = (p.mode == MODE_DIAG) ? 0 : chunk * p.chunk_tiles;
+      const int t1 = (p.mode == MODE_DIAG) ? 1 : min(p.n_tiles, t0 + p.chunk_tiles);
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&sl->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+        if (p.mode == MODE_COUNT) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(taddr0 + c * 32, v);
+            const int j0 = t * BN + half * 128 + c * 32;
+            const bool slow = (j0 < tie && tie < j0 + 32) || (j0 + 32 > p.Nc);
+            if (!__any_sync(0xffffffffu, slow)) {
+              const float tt = (j0 + 32 <= tie) ? thr_hi : thr;
+#pragma unroll
+              for (int k = 0; k < 32; ++k) cnt += (__uint_as_float(v[k]) < tt) ? 1 : 0;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const int j = j0 + k;
+                const float tt = (j < tie) ? thr_hi : thr;
+                cnt += (j < p.Nc && __uint_as_float(v[k]) < tt) ? 1 : 0;
+              }
+            }
+          }
+        } else if (half == (int)cta) {
+          // DIAG: the tile's columns [cta*128, +128) are the true rows of this CTA's queries
+          uint32_t v[32];
+          tmem_ld32(taddr0 + quarter * 32, v);
+          float sc = 0.f;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) sc = (k == lane) ? __uint_as_float(v[k]) : sc;
+          if (qok) {
+            const int ti = p.true_idx[q];
+            if (ti >= 0 && ti < p.Nc) p.true_out[q] = sc;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&sl->tmem_empty[acc], 0);   // the MMA issuer lives in CTA 0
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (p.mode == MODE_COUNT && qok && cnt != 0) {
+        atomicAdd(&p.raw_cnt[q], cnt);
+        atomicAdd(&p.filt_cnt[q], cnt);
+      }
+    }
+  }
+  __syncwarp();          // the single-lane roles rejoin their warps
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------ operand packing
@@ -520,17 +764,23 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
 
+  static const bool use_pair = []() {
+    const char* e = getenv("HOLE_RANK_PAIR");      // experimental cta_group::2 kernel
+    return e != nullptr && e[0] == '1';
+  }();
   const int Nc = (int)(ent_end - ent_begin);
   const int K = (c->dim + BK - 1) / BK * BK;
   const int num_kb = K / BK;
   const int Npad = (Nc + BN - 1) / BN * BN;
-  const int Qpad = (int)((Q + BM - 1) / BM * BM);
+  const int qtile = use_pair ? 2 * BM : BM;
+  const int Qpad = (int)((Q + qtile - 1) / qtile * qtile);
   const int a_bytes = num_kb * A_KB_BYTES;
-  int stages = (SMEM_LIMIT - a_bytes - 2048) / B_KB_BYTES;
-  stages = std::min(stages, MAX_STAGES);
+  const int b_stage_bytes = use_pair ? B_HALF_BYTES : B_KB_BYTES;
+  int stages = (SMEM_LIMIT - a_bytes - 2048) / b_stage_bytes;
+  stages = std::min(stages, use_pair ? MAX_STAGES : 4);
   if (stages < 2)
     return hole_set_error(HOLE_ERR_UNSUPPORTED, "embedding_dim %d too large for the ranking kernel's smem budget", c->dim);
-  const int smem_bytes = a_bytes + stages * B_KB_BYTES + 2048;   // + alignment slack + barriers
+  const int smem_bytes = a_bytes + stages * b_stage_bytes + 2048;   // + alignment slack + barriers
 
   if (c->rank == nullptr) c->rank = new hole_rank_ws();
   hole_rank_ws* w = c->rank;
@@ -557,6 +807,7 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
   }
   if (!w->attr_set) {
     HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_rank_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     w->attr_set = true;
   }
 
@@ -575,7 +826,7 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
   p.num_kb = num_kb;
   p.last_kb_mmas = (c->dim - (num_kb - 1) * BK + UMMA_K - 1) / UMMA_K;
   p.stages = stages;
-  p.m_tiles = Qpad / BM;
+  p.m_tiles = Qpad / qtile;
   p.Q = (int)Q;
   p.Nc = Nc;
   p.true_idx = w->true_idx;
@@ -585,17 +836,22 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
     hole_rank_gather_true_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w->cand, w->true_idx, Nc, Qpad, K, w->tq);
     HOLE_LAUNCHED();
     HOLE_CUDA_TRY(cudaMemsetAsync(w->tq + (size_t)Qpad * K, 0, (size_t)BN * K * 2, st));
-    rc = make_map(&mapB, w->tq, rows, K, BN);
+    rc = make_map(&mapB, w->tq, rows, K, use_pair ? BN / 2 : BN);
     if (rc) return rc;
     p.mode = MODE_DIAG;
     p.n_tiles = 1; p.chunk_tiles = 1; p.n_chunks = 1;
     p.true_out = true_score_io;
-    const int grid = std::min(p.m_tiles, c->sm_count);
-    hole_rank_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    if (use_pair) {
+      const int grid = 2 * std::min(p.m_tiles, c->sm_count / 2);
+      hole_rank_pair_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    } else {
+      const int grid = std::min(p.m_tiles, c->sm_count);
+      hole_rank_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    }
     HOLE_LAUNCHED();
   }
 
-  rc = make_map(&mapB, w->cand, Npad, K, BN);
+  rc = make_map(&mapB, w->cand, Npad, K, use_pair ? BN / 2 : BN);
   if (rc) return rc;
   p.mode = MODE_COUNT;
   p.n_tiles = Npad / BN;
@@ -611,8 +867,13 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
   p.filt_cnt = filt_before;
   {
     const int n_items = p.m_tiles * p.n_chunks;
-    const int grid = std::min(n_items, c->sm_count);
-    hole_rank_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    if (use_pair) {
+      const int grid = 2 * std::min(n_items, c->sm_count / 2);
+      hole_rank_pair_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    } else {
+      const int grid = std::min(n_items, c->sm_count);
+      hole_rank_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+    }
     HOLE_LAUNCHED();
   }
   if (filter_off != nullptr) {
