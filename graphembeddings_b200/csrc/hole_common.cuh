@@ -60,6 +60,10 @@ struct hole_plan {
   cudaEvent_t ready = nullptr;     // recorded by the builder when the plan is complete
   cudaEvent_t released = nullptr;  // recorded by the consumer when it no longer needs the plan
   bool used = false;
+  // hole_train_step_plan: plan built ahead for exactly these buffers
+  const int32_t* prepared_pos = nullptr;
+  const int32_t* prepared_neg = nullptr;
+  int64_t prepared_B = -1;
 };
 
 struct hole_ctx {

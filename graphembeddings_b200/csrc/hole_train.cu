@@ -515,7 +515,7 @@ template <int GS, int V, bool FULL>
 __device__ __forceinline__ void finish_row(Row<V>& d, const Row<V>& y, const float4* xraw,
                                            float inv_self, bool uniq, bool act, float lr,
                                            float* erow, float* grow, int lane, int nvec,
-                                           unsigned gmask) {
+                                           unsigned gmask, bool delta) {
   if (inv_self <= 1.0f) {          // group-uniform
     float proj = 0.f;
 #pragma unroll
@@ -529,12 +529,17 @@ __device__ __forceinline__ void finish_row(Row<V>& d, const Row<V>& y, const flo
   }
   if (uniq) {
     if (act) {                     // inactive hinge: zero gradient, row unchanged
-      Row<V> x;
-      row_from_smem<GS, V, FULL>(x, xraw, lane, nvec);
+      if (delta) {                 // delta mode: erow points into the (pre-zeroed) delta table
 #pragma unroll
-      for (int k = 0; k < 4 * V; ++k) {
-        d.re[k] = x.re[k] - lr * d.re[k];
-        d.im[k] = x.im[k] - lr * d.im[k];
+        for (int k = 0; k < 4 * V; ++k) { d.re[k] = -lr * d.re[k]; d.im[k] = -lr * d.im[k]; }
+      } else {
+        Row<V> x;
+        row_from_smem<GS, V, FULL>(x, xraw, lane, nvec);
+#pragma unroll
+        for (int k = 0; k < 4 * V; ++k) {
+          d.re[k] = x.re[k] - lr * d.re[k];
+          d.im[k] = x.im[k] - lr * d.im[k];
+        }
       }
       row_store<GS, V, FULL>(d, erow, lane, nvec);
     }
@@ -549,7 +554,7 @@ __device__ __forceinline__ void emit_row(const Row<V>& yh, const Row<V>& yt, con
                                          const Row<V>& yn, const float4* xraw, float inv_self,
                                          float gp, float gn, bool uniq, bool act, float lr,
                                          float* erow, float* grow, int lane, int nvec,
-                                         unsigned gmask) {
+                                         unsigned gmask, bool delta) {
   Row<V> d;
   const Row<V>& ys = (ROLE == ROLE_T) ? yt : (ROLE == ROLE_H) ? yh : yn;
 #pragma unroll
@@ -578,7 +583,7 @@ __device__ __forceinline__ void emit_row(const Row<V>& yh, const Row<V>& yt, con
     d.re[k] = gre;
     d.im[k] = gim;
   }
-  finish_row<GS, V, FULL>(d, ys, xraw, inv_self, uniq, act, lr, erow, grow, lane, nvec, gmask);
+  finish_row<GS, V, FULL>(d, ys, xraw, inv_self, uniq, act, lr, erow, grow, lane, nvec, gmask, delta);
 }
 
 struct TripleIds { int i, h, t, r, n; };
@@ -602,8 +607,12 @@ hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
                           const int32_t* __restrict__ neg, const int32_t* __restrict__ perm,
                           const uint32_t* __restrict__ gslot, int B, int T, int nvec,
                           int stride, float margin, float lr, float* __restrict__ G,
-                          float* __restrict__ loss, float* __restrict__ sigma) {
+                          float* __restrict__ loss, float* __restrict__ sigma, float* __restrict__ Dtab) {
   extern __shared__ float4 k1_smem[];
+  // delta mode (multi-GPU step tables): unique rows write -lr*dx into Dtab instead of
+  // updating E in place
+  const bool delta = Dtab != nullptr;
+  float* const Eout = delta ? Dtab : E;
   const int lane = threadIdx.x % GS;
   const int gbase = (threadIdx.x % 32) / GS * GS;
   const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << gbase);
@@ -642,7 +651,7 @@ hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
   auto flush_relation = [&]() {
     const uint32_t sl = gslot[run_i];
     finish_row<GS, V, FULL>(acc, yr, rel_smem, ir, sl == HOLE_SLOT_UNIQUE, run_act, lr,
-                      E + (size_t)r_cur * stride, G + (size_t)sl * stride, lane, nvec, gmask);
+                      Eout + (size_t)r_cur * stride, G + (size_t)sl * stride, lane, nvec, gmask, delta);
   };
 
   int stage = 0;
@@ -730,11 +739,11 @@ hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
       acc.im[k] += gp * (a * f - b * e) + gn * (a2 * f2 - b2 * e2);
     }
     emit_row<GS, V, ROLE_T, side, FULL>(yh, yt, yr, yn, sb + row4, it, gp, gn, sl_t == HOLE_SLOT_UNIQUE, act, lr,
-                            E + (size_t)c.t * stride, G + (size_t)sl_t * stride, lane, nvec, gmask);
+                            Eout + (size_t)c.t * stride, G + (size_t)sl_t * stride, lane, nvec, gmask, delta);
     emit_row<GS, V, ROLE_H, side, FULL>(yh, yt, yr, yn, sb, ih, gp, gn, sl_h == HOLE_SLOT_UNIQUE, act, lr,
-                            E + (size_t)c.h * stride, G + (size_t)sl_h * stride, lane, nvec, gmask);
+                            Eout + (size_t)c.h * stride, G + (size_t)sl_h * stride, lane, nvec, gmask, delta);
     emit_row<GS, V, ROLE_N, side, FULL>(yh, yt, yr, yn, sb + 2 * row4, in_, gp, gn, sl_n == HOLE_SLOT_UNIQUE, act, lr,
-                            E + (size_t)c.n * stride, G + (size_t)sl_n * stride, lane, nvec, gmask);
+                            Eout + (size_t)c.n * stride, G + (size_t)sl_n * stride, lane, nvec, gmask, delta);
     c = n1;
     n1 = n2;
     n2 = n3;
@@ -750,15 +759,15 @@ hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri
                           const int32_t* __restrict__ neg, const int32_t* __restrict__ perm,
                           const uint32_t* __restrict__ gslot, int side, int B, int T, int nvec,
                           int stride, float margin, float lr, float* __restrict__ G,
-                          float* __restrict__ loss, float* __restrict__ sigma) {
+                          float* __restrict__ loss, float* __restrict__ sigma, float* __restrict__ Dtab) {
   // specialise on the corruption side and on "every lane owns valid float4s" (nvec == GS*V)
   const bool full = (nvec == GS * V);
   if (side) {
-    if (full) hole_train_fwd_bwd_body<GS, V, 1, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma);
-    else      hole_train_fwd_bwd_body<GS, V, 1, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma);
+    if (full) hole_train_fwd_bwd_body<GS, V, 1, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab);
+    else      hole_train_fwd_bwd_body<GS, V, 1, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab);
   } else {
-    if (full) hole_train_fwd_bwd_body<GS, V, 0, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma);
-    else      hole_train_fwd_bwd_body<GS, V, 0, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma);
+    if (full) hole_train_fwd_bwd_body<GS, V, 0, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab);
+    else      hole_train_fwd_bwd_body<GS, V, 0, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab);
   }
 }
 
@@ -798,7 +807,7 @@ template <int GS, int V>
 __global__ void __launch_bounds__(256)
 hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __restrict__ heads,
                   const int* __restrict__ nheads, int* __restrict__ counters, int M, int nvec,
-                  int stride, float lr) {
+                  int stride, float lr, float* __restrict__ Dtab) {
   constexpr int C = HOLE_TREE_C;
   const int lane = threadIdx.x % GS;
   const int gbase = (threadIdx.x % 32) / GS * GS;
@@ -814,13 +823,20 @@ hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __r
     const int cnt = min(C, n - rel);
     float* erow = E + (size_t)row * stride;
     Row<V> acc, x;
-    const bool single = n <= C;      // this leaf is also the root: fetch the table row alongside
+    const bool delta = Dtab != nullptr;   // delta mode: write -lr * sum into Dtab, leave E alone
+    const bool single = n <= C && !delta; // this leaf is also the root: fetch the table row alongside
     if (single) row_load<GS, V, false>(x, erow, lane, nvec);
     sum_rows<GS, V>(acc, G, j, 1, cnt, stride, lane, nvec);
     int level = 0, idx = rel / C, nl = (n + C - 1) / C;
     int64_t span = C;   // sorted entries covered by one node of this level
     while (true) {
       if (nl == 1) {    // root: apply   E[row] -= lr * acc   (holE.py:296)
+        if (delta) {
+#pragma unroll
+          for (int k = 0; k < 4 * V; ++k) { x.re[k] = -lr * acc.re[k]; x.im[k] = -lr * acc.im[k]; }
+          row_store<GS, V>(x, Dtab + (size_t)row * stride, lane, nvec);
+          break;
+        }
         if (!single) row_load<GS, V, false>(x, erow, lane, nvec);
 #pragma unroll
         for (int k = 0; k < 4 * V; ++k) {
@@ -853,6 +869,23 @@ hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __r
 }
 
 // ---------------------------------------------------------------------------------------
+
+// table[ids[k]] += rows[k] for UNIQUE ids (multi-GPU: the owner applies one source rank's
+// row deltas; ranks are applied one after the other, so the sum order is fixed)
+template <int GS, int V>
+__global__ void __launch_bounds__(256)
+hole_add_rows_kernel(float* __restrict__ E, const int64_t* __restrict__ ids, const float* __restrict__ rows,
+                     int64_t n, int64_t id_offset, int nvec, int stride) {
+  const int lane = threadIdx.x % GS;
+  const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
+  if (k >= n) return;
+  float* erow = E + (size_t)(ids[k] + id_offset) * stride;
+  Row<V> x, d;
+  row_load<GS, V, false>(x, erow, lane, nvec);
+  row_load<GS, V, true>(d, rows + (size_t)k * stride, lane, nvec);
+  row_add(x, d);
+  row_store<GS, V>(x, erow, lane, nvec);
+}
 
 // deterministic per-step loss sum: one CTA per step, fixed-shape tree
 __global__ void __launch_bounds__(256)
@@ -1183,7 +1216,7 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
 // K1 + K3 of one step whose plan is slot `slot` of pl.
 static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos, const int32_t* neg,
                     int side, int64_t B, float margin, float lr, float* loss_out, float* sigma_out,
-                    int64_t slot, cudaStream_t st) {
+                    int64_t slot, cudaStream_t st, float* delta_out = nullptr) {
   const int M = (int)(4 * B);
   const size_t off = (size_t)slot * M;
   cudaEvent_t* pe = nullptr;
@@ -1201,12 +1234,12 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
   }
   HOLE_DISPATCH_SMEM(c, hole_train_fwd_bwd_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
                      c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
-                c->row_stride, margin, lr, c->G, loss_out, sigma_out);
+                c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out);
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[1], st));
   const unsigned k3_grid = std::min<unsigned>(grid_for_groups(pl.heads_cap, c->gs), (unsigned)c->sm_count * 4);
   HOLE_DISPATCH(c, hole_apply_kernel, k3_grid, 256, st, table, c->G,
                 pl.heads + (size_t)slot * pl.heads_cap, pl.nheads + slot, c->counters, M, c->nvec,
-                c->row_stride, lr);
+                c->row_stride, lr, delta_out);
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[2], st));
   return HOLE_OK;
 }
@@ -1236,9 +1269,30 @@ extern "C" int hole_profile_read(hole_ctx* c, double* k1_ms, double* k3_ms, int6
   return HOLE_OK;
 }
 
-extern "C" int hole_train_step(hole_ctx* c, float* table, const int32_t* pos, const int32_t* neg_ent,
-                               int side, int64_t B, float margin, float lr, float* loss_out,
-                               float* sigma_out, void* stream) {
+extern "C" int hole_train_step_plan(hole_ctx* c, const int32_t* pos, const int32_t* neg_ent, int64_t B,
+                                    void* stream) {
+  HOLE_CHECK_ARG(c && B >= 0);
+  if (B == 0) return HOLE_OK;
+  HOLE_CHECK_ARG(pos && neg_ent && 4 * B < (int64_t(1) << 31));
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  int rc = hole_ws_reserve(c, B, 1);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // the plan stream reads pos / neg_ent once the caller's stream has produced them
+  HOLE_CUDA_TRY(cudaEventRecord(c->ev_entry, st));
+  HOLE_CUDA_TRY(cudaStreamWaitEvent(c->plan_stream, c->ev_entry, 0));
+  hole_plan& pl = c->plan[0];
+  rc = plan_steps(c, pl, pos, B, 1, nullptr, nullptr, nullptr, 0, 0, neg_ent, c->plan_stream);
+  if (rc) return rc;
+  pl.prepared_pos = pos;
+  pl.prepared_neg = neg_ent;
+  pl.prepared_B = B;
+  return HOLE_OK;
+}
+
+extern "C" int hole_train_step_ex(hole_ctx* c, float* table, float* delta_out, const int32_t* pos,
+                                  const int32_t* neg_ent, int side, int64_t B, float margin, float lr,
+                                  float* loss_out, float* sigma_out, void* stream) {
   HOLE_CHECK_ARG(c && B >= 0 && (side == 0 || side == 1));
   if (B == 0) return HOLE_OK;   // an empty batch is a no-op
   HOLE_CHECK_ARG(table && pos && neg_ent && loss_out);
@@ -1248,13 +1302,37 @@ extern "C" int hole_train_step(hole_ctx* c, float* table, const int32_t* pos, co
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   hole_plan& pl = c->plan[0];
-  // the plan's keys do not depend on the side, and the corruption is the caller's
-  rc = plan_steps(c, pl, pos, B, 1, nullptr, nullptr, nullptr, 0, 0, neg_ent, st);
-  if (rc) return rc;
-  rc = run_step(c, pl, table, pos, neg_ent, side, B, margin, lr, loss_out, sigma_out, 0, st);
+  if (pl.prepared_B == B && pl.prepared_pos == pos && pl.prepared_neg == neg_ent) {
+    HOLE_CUDA_TRY(cudaStreamWaitEvent(st, pl.ready, 0));     // planned ahead by hole_train_step_plan
+  } else {
+    // the plan's keys do not depend on the side, and the corruption is the caller's
+    rc = plan_steps(c, pl, pos, B, 1, nullptr, nullptr, nullptr, 0, 0, neg_ent, st);
+    if (rc) return rc;
+  }
+  pl.prepared_B = -1;
+  pl.prepared_pos = pl.prepared_neg = nullptr;
+  rc = run_step(c, pl, table, pos, neg_ent, side, B, margin, lr, loss_out, sigma_out, 0, st, delta_out);
   if (rc) return rc;
   pl.used = true;
   HOLE_CUDA_TRY(cudaEventRecord(pl.released, st));
+  return HOLE_OK;
+}
+
+extern "C" int hole_train_step(hole_ctx* c, float* table, const int32_t* pos, const int32_t* neg_ent,
+                               int side, int64_t B, float margin, float lr, float* loss_out,
+                               float* sigma_out, void* stream) {
+  return hole_train_step_ex(c, table, nullptr, pos, neg_ent, side, B, margin, lr, loss_out, sigma_out,
+                            stream);
+}
+
+extern "C" int hole_add_rows(hole_ctx* c, float* table, const int64_t* ids, int64_t id_offset,
+                             const float* rows, int64_t n, void* stream) {
+  HOLE_CHECK_ARG(c && n >= 0);
+  if (n == 0) return HOLE_OK;
+  HOLE_CHECK_ARG(table && ids && rows);
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  HOLE_DISPATCH(c, hole_add_rows_kernel, grid_for_groups(n, c->gs), 256, (cudaStream_t)stream, table, ids,
+                rows, n, id_offset, c->nvec, c->row_stride);
   return HOLE_OK;
 }
 

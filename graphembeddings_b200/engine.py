@@ -137,6 +137,26 @@ class HoleEngine:
             return loss, sig[:B], sig[B:]
         return loss
 
+    def train_step_plan(self, pos_i32, neg_i32):
+        """Build the update plan of the next train_step_delta call (same tensors) on a side
+        stream, overlapping whatever is enqueued in between."""
+        check(self.lib.hole_train_step_plan(self._ctx, _ptr(pos_i32), _ptr(neg_i32), pos_i32.shape[0], _stream()))
+
+    def train_step_delta(self, pos_i32, neg_i32, side, margin, lr, delta_out):
+        """One step that leaves the table untouched and writes every row's change into
+        delta_out [n_rows, row_stride] (zeroed by the caller).  pos/neg: int32 CUDA tensors."""
+        B = pos_i32.shape[0]
+        loss = torch.empty(B, dtype=torch.float32, device=self.device)
+        check(self.lib.hole_train_step_ex(self._ctx, _ptr(self.table), _ptr(delta_out), _ptr(pos_i32),
+                                          _ptr(neg_i32), int(side), B, float(margin), float(lr),
+                                          _ptr(loss), None, _stream()))
+        return loss
+
+    def add_rows(self, table, ids_i64, id_offset, rows):
+        """table[ids + id_offset] += rows, ids unique (the owner applies one rank's deltas)."""
+        check(self.lib.hole_add_rows(self._ctx, _ptr(table), _ptr(ids_i64), int(id_offset), _ptr(rows),
+                                     ids_i64.shape[0], _stream()))
+
     def train_steps(self, triples, batch_size, seed, first_step, margin, lrs, want_loss=False):
         """n_steps = len(triples) // batch_size consecutive steps on device-resident triples
         (the loop body holE.py:340-362).  Returns per-step loss sums (device float32)."""

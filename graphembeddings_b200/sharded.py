@@ -64,6 +64,7 @@ class CudaBackend:
         self.dim = dim
         self.device = self.eng.device
         self.W = torch.zeros((n_relations + 3 * max_batch, self.width), dtype=torch.float32, device=self.device)
+        self.D = torch.zeros_like(self.W)          # row deltas of one step (delta-mode kernels)
         self.eng.table = self.W
         if type_of is not None:
             self.eng.set_types(type_of, csr_off, csr_ids)
@@ -87,6 +88,17 @@ class CudaBackend:
 
     def step(self, n_rows, pos, neg, side, margin, lr):
         return self.eng.train_step(pos.to(torch.int32), neg.to(torch.int32), side, margin, lr)
+
+    # fast path: plan on a side stream, deltas written by the kernels, owner-side row adds
+    def plan(self, pos_i32, neg_i32):
+        self.eng.train_step_plan(pos_i32, neg_i32)
+
+    def step_delta(self, n_rows, pos_i32, neg_i32, side, margin, lr):
+        self.D[:n_rows].zero_()
+        return self.eng.train_step_delta(pos_i32, neg_i32, side, margin, lr, self.D)
+
+    def add_rows(self, table, ids, id_offset, rows):
+        self.eng.add_rows(table, ids.contiguous(), id_offset, rows.contiguous())
 
 
 class RowShardedTrainer:
@@ -123,11 +135,14 @@ class RowShardedTrainer:
         return torch.cat([self.be.unpad_rows(self.shard[: self.R]), ents], dim=0)
 
     # ------------------------------------------------------------------ exchange helpers
-    def _a2a(self, send, send_counts, recv_counts):
+    def _a2a(self, send, send_counts, recv_counts, out=None):
         if self.world == 1:
+            if out is not None:
+                out.copy_(send)
+                return out
             return send
         shape = (int(sum(recv_counts)),) + tuple(send.shape[1:])
-        recv = torch.empty(shape, dtype=send.dtype, device=send.device)
+        recv = out if out is not None else torch.empty(shape, dtype=send.dtype, device=send.device)
         self.dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=list(recv_counts),
                                     input_split_sizes=list(send_counts))
         return recv
@@ -163,34 +178,51 @@ class RowShardedTrainer:
             send_counts, recv_counts = self._route(uniq)
         with _Section("a2a ids"):
             ids_in = self._a2a(uniq, send_counts, recv_counts)              # rows others want from me
+        fast = hasattr(self.be, "step_delta")
+        if fast:
+            with _Section("plan (side stream)"):
+                pos_w = torch.stack([R + inv[:B], R + inv[B:2 * B], pos[:, 2]], dim=1).to(torch.int32)
+                neg_w = (R + inv[2 * B:]).to(torch.int32)
+                self.be.plan(pos_w, neg_w)        # overlaps the row exchange below
         with _Section("gather rows"):
             rows_out = self.shard.index_select(0, ids_in - self.begin + R)
-        with _Section("a2a rows"):
-            rows_in = self._a2a(rows_out, recv_counts, send_counts)         # in `uniq` order
-        with _Section("assemble W, W0"):
-            W = self.be.W
-            W[:R].copy_(self.shard[:R])
-            W[R:R + U].copy_(rows_in)
-            W0 = W[: R + U].clone()
-            pos_w = torch.stack([R + inv[:B], R + inv[B:2 * B], pos[:, 2]], dim=1)
-            neg_w = R + inv[2 * B:]
-        with _Section("local step (plan+K1+K3)"):
-            loss = self.be.step(R + U, pos_w, neg_w, side, margin, lr)
-        with _Section("delta"):
-            delta = W[: R + U] - W0
-            d_rel = delta[:R].contiguous()
+        W = self.be.W
+        if fast:
+            with _Section("a2a rows"):
+                self._a2a(rows_out, recv_counts, send_counts, out=W[R:R + U])   # lands in the step table
+                W[:R].copy_(self.shard[:R])
+            with _Section("local step (K1+K3, delta mode)"):
+                loss = self.be.step_delta(R + U, pos_w, neg_w, side, margin, lr)
+                delta = self.be.D
+        else:
+            with _Section("a2a rows"):
+                rows_in = self._a2a(rows_out, recv_counts, send_counts)         # in `uniq` order
+            with _Section("assemble W, W0"):
+                W[:R].copy_(self.shard[:R])
+                W[R:R + U].copy_(rows_in)
+                W0 = W[: R + U].clone()
+                pos_w = torch.stack([R + inv[:B], R + inv[B:2 * B], pos[:, 2]], dim=1)
+                neg_w = R + inv[2 * B:]
+            with _Section("local step (plan+K1+K3)"):
+                loss = self.be.step(R + U, pos_w, neg_w, side, margin, lr)
+            with _Section("delta"):
+                delta = W[: R + U] - W0
         with _Section("allreduce relations"):
+            d_rel = delta[:R].contiguous()
             if self.world > 1:
                 self.dist.all_reduce(d_rel)
             self.shard[:R] += d_rel
         with _Section("a2a deltas"):
-            d_in = self._a2a(delta[R:], send_counts, recv_counts)           # grouped by source rank
+            d_in = self._a2a(delta[R:R + U], send_counts, recv_counts)      # grouped by source rank
         with _Section("apply deltas"):
             off = 0
             for k in range(self.world):                                     # rank order: deterministic
                 n_k = recv_counts[k]
                 if n_k:
-                    self.shard.index_add_(0, ids_in[off:off + n_k] - self.begin + R, d_in[off:off + n_k])
+                    if fast:
+                        self.be.add_rows(self.shard, ids_in[off:off + n_k], R - self.begin, d_in[off:off + n_k])
+                    else:
+                        self.shard.index_add_(0, ids_in[off:off + n_k] - self.begin + R, d_in[off:off + n_k])
                 off += n_k
         return loss
 

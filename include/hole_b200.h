@@ -115,6 +115,22 @@ HOLE_API int hole_train_step(hole_ctx* ctx, float* table, const int32_t* pos, co
                     int side, int64_t B, float margin, float lr,
                     float* loss_out, float* sigma_out, void* stream);
 
+/* Multi-GPU building blocks (graphembeddings_b200/sharded.py).
+ * hole_train_step_ex: as hole_train_step; when delta_out != NULL the table is left untouched
+ * and every row a step would change receives its change (-lr * summed gradient) at the same
+ * row of delta_out (float32 [n_rows, row_stride], zero-initialised by the caller).
+ * hole_train_step_plan: optionally builds the integer update plan for the next
+ * hole_train_step(_ex) call with the same pos / neg_ent / B on a side stream, so that it
+ * overlaps whatever the caller enqueues in between (e.g. the row exchange).
+ * hole_add_rows: table[ids[k] + id_offset] += rows[k] for k < n, ids unique within a call. */
+HOLE_API int hole_train_step_ex(hole_ctx* ctx, float* table, float* delta_out, const int32_t* pos,
+                       const int32_t* neg_ent, int side, int64_t B, float margin, float lr,
+                       float* loss_out, float* sigma_out, void* stream);
+HOLE_API int hole_train_step_plan(hole_ctx* ctx, const int32_t* pos, const int32_t* neg_ent, int64_t B,
+                         void* stream);
+HOLE_API int hole_add_rows(hole_ctx* ctx, float* table, const int64_t* ids, int64_t id_offset,
+                  const float* rows, int64_t n, void* stream);
+
 /* ---- the training loop body for n_steps consecutive batches: replaces
  * `for batch in range(1, batch_count): sess.run([optimizer])` (holE.py:340-362) without
  * returning to the host between steps.  Step k uses triples[k*B .. (k+1)*B), draws its
