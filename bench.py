@@ -51,33 +51,73 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clocks / throttle reasons during the timed region, polled every 100 ms through NVML
+    in a background thread (an `nvidia-smi -lms` child process takes driver locks often enough
+    to slow a launch-heavy multi-GPU step; NVML calls from this process are far lighter).
+    Falls back to nvidia-smi when pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index=0, period=0.1):
+        self.index, self.period = index, period
+        self.proc, self.lines, self.samples, self.reason_bits = None, [], [], 0
+        self.max_clock, self.thread, self.stop_flag, self.nvml = None, None, False, None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_clock = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                try:
+                    self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                except Exception:
+                    pass
+            time.sleep(self.period)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                    "sw_power_cap": 0x4}
+            reasons = sorted(k for k, v in bits.items() if self.reason_bits & v)
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                    "sm_max_mhz": self.max_clock, "samples": len(self.samples), "reasons": reasons,
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         self.thread.join(timeout=2)
         sm, mx, reasons = [], None, set()
@@ -94,7 +134,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def make_workload(n_triples, with_embeddings=True):
@@ -195,10 +235,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
-    eng.train_steps(dev_tri[: W * B], B, 1, 0, MARGIN, lr_schedule(W, 0, batch_count))
-    barrier()
+    # (nvidia-smi's start-up disturbs running GPU work for a few hundred ms: the clock sampler
+    # starts before the warm-up, not inside the timed region)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    time.sleep(1.0)
+    eng.train_steps(dev_tri[: W * B], B, 1, 0, MARGIN, lr_schedule(W, 0, batch_count))
+    barrier()
     eng.reset_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
