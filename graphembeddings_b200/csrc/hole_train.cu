@@ -33,6 +33,13 @@ int hole_set_error(int code, const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------
+// Programmatic dependent launch: K1 and K3 of consecutive steps form a dependent chain; each
+// is launched with programmatic stream serialization so that its prologue (plan / triple
+// loads that do not depend on the table) overlaps the tail of its predecessor, and waits
+// here before touching anything the predecessor writes.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <int V>
 struct Row {
   float re[4 * V];
@@ -635,6 +642,7 @@ hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
   TripleIds c = load_ids(tri, neg, perm, g0);
   TripleIds n1 = (g0 + 1 < g1) ? load_ids(tri, neg, perm, g0 + 1) : c;
   TripleIds n2 = (g0 + 2 < g1) ? load_ids(tri, neg, perm, g0 + 2) : c;
+  pdl_wait();                 // the previous step's K3 has finished updating the table
   fetch(c, 0);
   cp_async_commit();
   if (g0 + 1 < g1) fetch(n1, 1);
@@ -750,6 +758,7 @@ hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
     stage = (stage + 1) % K1_STAGES;
   }
   cp_async_wait<0>();
+  pdl_launch_dependents();    // K3 of this step may start its prologue
   flush_relation();
 }
 
@@ -815,6 +824,8 @@ hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __r
   // persistent: a fixed grid strides over the step's work list (its length is only known on
   // the device)
   const int nh = *nheads;
+  pdl_launch_dependents();    // the next step's K1 may run its (table-independent) prologue
+  pdl_wait();                 // K1 of this step has staged every gradient row
   const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / GS;
   for (int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS; g < nh; g += gstride) {
     const uint4 hd = heads[g];
@@ -919,6 +930,31 @@ hole_loss_sum_kernel(const float* __restrict__ loss, int64_t B, float* __restric
   } while (0)
 #define HOLE_DISPATCH(ctx, KERNEL, grid, block, stream, ...) \
   HOLE_DISPATCH_SMEM(ctx, KERNEL, grid, block, 0, stream, __VA_ARGS__)
+
+// same, launched with programmatic stream serialization (see pdl_wait)
+#define HOLE_DISPATCH_PDL(ctx, KERNEL, grid_, block_, smem_, stream_, ...)                   \
+  do {                                                                                       \
+    cudaLaunchConfig_t cfg_ = {};                                                            \
+    cfg_.gridDim = dim3(grid_);                                                              \
+    cfg_.blockDim = dim3(block_);                                                            \
+    cfg_.dynamicSmemBytes = (size_t)(smem_);                                                 \
+    cfg_.stream = stream_;                                                                   \
+    cudaLaunchAttribute at_[1];                                                              \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                          \
+    at_[0].val.programmaticStreamSerializationAllowed = 1;                                   \
+    cfg_.attrs = at_;                                                                        \
+    cfg_.numAttrs = 1;                                                                       \
+    cudaError_t le_ = cudaSuccess;                                                           \
+    if ((ctx)->gs == 8 && (ctx)->v == 1) le_ = cudaLaunchKernelEx(&cfg_, KERNEL<8, 1>, __VA_ARGS__);        \
+    else if ((ctx)->gs == 16 && (ctx)->v == 1) le_ = cudaLaunchKernelEx(&cfg_, KERNEL<16, 1>, __VA_ARGS__); \
+    else if ((ctx)->gs == 32 && (ctx)->v == 1) le_ = cudaLaunchKernelEx(&cfg_, KERNEL<32, 1>, __VA_ARGS__); \
+    else if ((ctx)->gs == 32 && (ctx)->v == 2) le_ = cudaLaunchKernelEx(&cfg_, KERNEL<32, 2>, __VA_ARGS__); \
+    else if ((ctx)->gs == 32 && (ctx)->v == 3) le_ = cudaLaunchKernelEx(&cfg_, KERNEL<32, 3>, __VA_ARGS__); \
+    else return hole_set_error(HOLE_ERR_UNSUPPORTED, "no kernel variant for gs=%d v=%d",     \
+                               (ctx)->gs, (ctx)->v);                                         \
+    HOLE_CUDA_TRY(le_);                                                                      \
+    HOLE_LAUNCHED();                                                                         \
+  } while (0)
 
 static inline unsigned grid_for_groups(int64_t groups, int gs, int block = 256) {
   int64_t per_block = block / gs;
@@ -1216,7 +1252,7 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
 // K1 + K3 of one step whose plan is slot `slot` of pl.
 static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos, const int32_t* neg,
                     int side, int64_t B, float margin, float lr, float* loss_out, float* sigma_out,
-                    int64_t slot, cudaStream_t st, float* delta_out = nullptr) {
+                    int64_t slot, cudaStream_t st, float* delta_out = nullptr, bool k1_follows_k3 = false) {
   const int M = (int)(4 * B);
   const size_t off = (size_t)slot * M;
   cudaEvent_t* pe = nullptr;
@@ -1232,12 +1268,20 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
     c->prof_used += 3;
     HOLE_CUDA_TRY(cudaEventRecord(pe[0], st));
   }
-  HOLE_DISPATCH_SMEM(c, hole_train_fwd_bwd_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
-                     c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
+  // K1's prologue reads plan data before griddepcontrol.wait: only overlap it with a
+  // predecessor that does not write the plan, i.e. the previous step's K3 of the same chunk
+  if (k1_follows_k3 && !c->profile) {
+    HOLE_DISPATCH_PDL(c, hole_train_fwd_bwd_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
+                      c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
                 c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out);
+  } else {
+    HOLE_DISPATCH_SMEM(c, hole_train_fwd_bwd_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
+                       c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
+                c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out);
+  }
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[1], st));
   const unsigned k3_grid = std::min<unsigned>(grid_for_groups(pl.heads_cap, c->gs), (unsigned)c->sm_count * 4);
-  HOLE_DISPATCH(c, hole_apply_kernel, k3_grid, 256, st, table, c->G,
+  HOLE_DISPATCH_PDL(c, hole_apply_kernel, k3_grid, 256, 0, st, table, c->G,
                 pl.heads + (size_t)slot * pl.heads_cap, pl.nheads + slot, c->counters, M, c->nvec,
                 c->row_stride, lr, delta_out);
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[2], st));
@@ -1351,7 +1395,7 @@ static int run_chunk(hole_ctx* c, hole_plan& pl, float* table, const int32_t* tr
   for (int64_t k = 0; k < S; ++k) {
     int side = hole_side_coin(seed, first_step + (uint64_t)k);
     int rc = run_step(c, pl, table, triples_dev + (size_t)k * B * 3, pl.neg + (size_t)k * B, side, B,
-                      margin, lr_host[k], loss_out + (size_t)k * B, nullptr, k, st);
+                      margin, lr_host[k], loss_out + (size_t)k * B, nullptr, k, st, nullptr, k > 0);
     if (rc) return rc;
   }
   if (loss_sum_dev != nullptr) {

@@ -164,7 +164,7 @@ def save_checkpoint(eng, output_dir, global_step, metadata_names=None):
 def load_checkpoint(output_dir):
     """saver.restore(sess, output_dir + '/model.ckpt') (holE.py:313-314)."""
     b = tf_bundle.load_bundle(os.path.join(output_dir, 'model.ckpt'), names={"embeddings", "batch/Variable"})
-    return b["embeddings"], int(b.get("batch/Variable", np.array(0)))
+    return b["embeddings"], int(np.asarray(b.get("batch/Variable", 0)).reshape(-1)[0])
 
 
 # --------------------------------------------------------------------------------------
@@ -279,14 +279,19 @@ def score_mrr(raw_positions, filtered_positions, log=print):
             "hits1": float(hits1), "hits3": float(hits3), "hits10": float(hits10)}
 
 
+def _logit(p):
+    return float(np.log(p) - np.log1p(-p))
+
+
 def eval_link_prediction(eng, queries, known, relation_count, entity_count, sides=("tail", "head"),
                          threshold=None, results_path=None):
     """All-entity generalisation of holE.py:427-472 on the tensor cores: every test triple is
     ranked against all entity rows on each requested side, ascending by (score, id).
     Train/valid-true candidates do not advance the filtered rank (holE.py:454-463); a test
     triple that is itself in-sample is skipped, as the reference's `continue` does.
-    threshold: the reference's confidence gate min sigma < infer_threshold (holE.py:438); None
-    disables it (it cannot fire for the live model).
+    threshold: the reference's confidence gate `min sigma over the candidates < infer_threshold`
+    (holE.py:438), evaluated as "some candidate scores below logit(threshold)"; None disables
+    it (it cannot fire for the live model).
     Returns (raw_positions, filtered_positions) lists."""
     queries = np.unique(np.asarray(queries, dtype=np.int32).reshape(-1, 3), axis=0)   # test sets dedupe
     raw_positions, filtered_positions = [], []
@@ -299,9 +304,14 @@ def eval_link_prediction(eng, queries, known, relation_count, entity_count, side
         side = HOLE_SIDE_TAIL if side_name == "tail" else HOLE_SIDE_HEAD
         foff, fids = D.build_filter_csr(queries, known, side_name)
         raw, filt, ts = eng.rank(queries, side, relation_count, entity_count, foff, fids)
+        ok = np.ones(len(queries), bool)
+        if threshold is not None:
+            gate = torch.full((len(queries),), _logit(threshold), dtype=torch.float32, device=eng.device)
+            below, _, _ = eng.rank(queries, side, relation_count, entity_count, true_score=gate,
+                                   compute_true=False)
+            ok = below.cpu().numpy() > 0
         raw, filt, ts = raw.cpu().numpy(), filt.cpu().numpy(), ts.cpu().numpy()
         sig = 1.0 / (1.0 + np.exp(-ts.astype(np.float64)))
-        ok = np.ones(len(queries), bool) if threshold is None else (sig < threshold)
         raw_positions += (raw[ok] + 1).tolist()
         filtered_positions += (filt[ok] + 1).tolist()
         if results_path:
@@ -309,6 +319,67 @@ def eval_link_prediction(eng, queries, known, relation_count, entity_count, side
                 for (h, t, r), s in zip(queries[ok].tolist(), sig[ok]):
                     output.write('{:.6f}\t{}\t{}\t{}\t{}\n'.format(s, h, t, r, False))
     return raw_positions, filtered_positions
+
+
+def eval_link_prediction_typed(eng, heads, candidate, true_triples, test_triples, threshold=None):
+    """The reference's own protocol (holE.py:564-573 + 427-469): for every head, the triples
+    product([head], candidate.tail_candidates, candidate.relations) are ranked JOINTLY,
+    ascending by (sigma, (head, tail, relation)); in-sample tails are skipped without
+    advancing the filtered rank; every test-true (tail, relation) records its ranks.
+    Implemented as tensor-core counts: one query row per (test item, relation of the group),
+    thresholded at the test item's own score, ties resolved by the (tail, relation) order.
+    Returns (raw_positions, filtered_positions)."""
+    rels = sorted(int(r) for r in candidate.relations)
+    tails = np.array(sorted(set(int(t) for t in candidate.tail_candidates)), dtype=np.int64)
+    heads = [int(h) for h in heads]
+    if not rels or len(tails) == 0 or not heads:
+        return [], []
+    R = int(max(rels)) + 1
+    dev = eng.device
+    tail_pos = {int(t): i for i, t in enumerate(tails)}
+    # temporary table [relation rows 0..R-1 | candidate tails (ascending id) | heads]
+    rows = torch.cat([torch.arange(R), torch.from_numpy(tails), torch.tensor(heads, dtype=torch.int64)]).to(dev)
+    table = eng.table.index_select(0, rows)
+    tmp = HoleEngine(int(table.shape[0]), eng.dim, dev.index or 0)
+    tmp.table = table
+    c0, c1 = R, R + len(tails)
+    items = []            # (head slot, t*, r*) of every recorded test item
+    for hi, h in enumerate(heads):
+        for r in rels:
+            for t in sorted(test_triples.get(h, {}).get(r, ())):
+                if t in tail_pos and t not in true_triples.get(h, {}).get(r, ()):
+                    items.append((hi, t, r))
+    if not items:
+        tmp.close()
+        return [], []
+    # 1. the test items' own scores through the same MMA path
+    q_true = np.array([[c1 + hi, c0 + tail_pos[t], r] for hi, t, r in items], dtype=np.int32)
+    _, _, s_true = tmp.rank(q_true, HOLE_SIDE_TAIL, c0, c1)
+    # 2. one counting row per (item, relation r'): candidates (t, r') before (t*, r*)
+    q_rows, thr, foff, fids = [], [], [0], []
+    for k, (hi, t, r) in enumerate(items):
+        h = heads[hi]
+        for r2 in rels:
+            # ties: (t, r2) < (t*, r*)  <=>  t < t*  or  (t == t* and r2 < r*)
+            q_rows.append([c1 + hi, c0 + tail_pos[t] + (1 if r2 < r else 0), r2])
+            thr.append(k)
+            f = sorted(tail_pos[x] + c0 for x in true_triples.get(h, {}).get(r2, ()) if x in tail_pos)
+            fids += f
+            foff.append(len(fids))
+    q_rows = np.array(q_rows, dtype=np.int32)
+    thr_t = s_true[torch.as_tensor(thr, device=dev)].contiguous()
+    raw, filt, _ = tmp.rank(q_rows, HOLE_SIDE_TAIL, c0, c1, np.array(foff, dtype=np.int64),
+                            np.array(fids, dtype=np.int32), true_score=thr_t, compute_true=False)
+    raw = raw.cpu().numpy().reshape(len(items), len(rels)).sum(1)
+    filt = filt.cpu().numpy().reshape(len(items), len(rels)).sum(1)
+    ok = np.ones(len(items), bool)
+    if threshold is not None:      # min sigma over the head's whole candidate product < threshold
+        gate = torch.full((len(q_rows),), _logit(threshold), dtype=torch.float32, device=dev)
+        below, _, _ = tmp.rank(q_rows, HOLE_SIDE_TAIL, c0, c1, true_score=gate, compute_true=False)
+        ok = below.cpu().numpy().reshape(len(items), len(rels)).sum(1) > 0
+    tmp.table = None
+    tmp.close()
+    return (raw[ok] + 1).tolist(), (filt[ok] + 1).tolist()
 
 
 def infer_triples(flags=None, log=print):

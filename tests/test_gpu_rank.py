@@ -224,3 +224,36 @@ def test_both_sides_in_one_pass_equals_two_calls(eng_mod):
     assert torch.equal(rb[:Q], rt) and torch.equal(rb[Q:], rh)
     assert torch.equal(flb[:Q], flt) and torch.equal(flb[Q:], flh)
     assert torch.equal(tsb[:Q], tst) and torch.equal(tsb[Q:], tsh)
+
+
+def test_full_size_config3_sample_against_fp64_contraction(eng_mod):
+    """BASELINE config 3 shape (1,200,000 candidates, d=256): rank 2,048 queries and check a
+    sample of them exactly against an fp64 contraction of the kernel's own bf16 operands
+    (done on the GPU with torch), plus size-independent invariants for all of them."""
+    kg = D.make_config("rank_diffbot_d256", n_triples=2048, trained_scale=True)
+    e = eng_mod.HoleEngine(kg.n_rows, kg.dim).set_embeddings(kg.E)
+    b, en = kg.n_relations, kg.n_rows
+    raw, filt, ts = e.rank(kg.triples, 0, b, en)
+    N = kg.n_entities
+    assert int(raw.min()) >= 0 and int(raw.max()) <= N - 1
+    assert torch.equal(raw, filt)                       # no filter given
+    cand, qp = e.rank_debug_operands()
+    idx = torch.arange(0, 2048, 32, device="cuda")      # 64 sampled queries
+    S = qp[idx].double() @ cand[:N].double().T           # [64, 1.2M] fp64
+    tj = torch.as_tensor(kg.triples[idx.cpu().numpy(), 1] - b, device="cuda").long()
+    thr = S[torch.arange(len(idx)), tj]
+    assert float((ts[idx].double() - thr).abs().max()) < 2e-6
+    eps = 2e-6
+    lo = (S < (thr - eps)[:, None]).sum(1)
+    hi = (S <= (thr + eps)[:, None]).sum(1) - 1
+    r = raw[idx].long()
+    assert bool(((r >= lo) & (r <= hi)).all())
+    ids = torch.arange(N, device="cuda")
+    exact = ((S < thr[:, None]) | ((S == thr[:, None]) & (ids[None, :] < tj[:, None]))).sum(1)
+    assert float((r == exact).double().mean()) > 0.9
+    # candidate-shard invariance at full size: two halves accumulate to the same counts
+    raw2 = torch.zeros_like(raw); f2 = torch.zeros_like(raw)
+    mid = b + 600_123
+    e.rank(kg.triples, 0, b, mid, true_score=ts.clone(), compute_true=False, raw_before=raw2, filt_before=f2)
+    e.rank(kg.triples, 0, mid, en, true_score=ts.clone(), compute_true=False, raw_before=raw2, filt_before=f2)
+    assert torch.equal(raw2, raw)

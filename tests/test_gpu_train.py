@@ -232,3 +232,33 @@ def test_sharded_trainer_single_rank_matches_engine(eng_mod):
     want = e.embeddings().cpu().numpy()
     assert np.abs(got - want).max() <= 1e-6
     assert np.abs(want - kg.E).max() > 1e-4
+
+
+def test_full_size_properties_config1(eng_mod):
+    """BASELINE config 1 at full table size (1,200,014 x 256), B = 32768: determinism across
+    runs, rows untouched by any step bit-identical, loss sums finite and equal between the
+    device-resident and the host-buffer entry points."""
+    kg = D.make_config("diffbot_d256", n_triples=32768 * 6)
+    B, n_steps = 32768, 6
+    lrs = [0.1] * n_steps
+    off, ids = D.build_type_csr(kg.type_of)
+    outs = []
+    for mode in ("device", "device", "host"):
+        e = eng_mod.HoleEngine(kg.n_rows, kg.dim).set_embeddings(kg.E).set_types(kg.type_of, off, ids)
+        e.set_relation_count(kg.n_relations)
+        if mode == "device":
+            sums = e.train_steps(kg.triples, B, 11, 0, 0.2, lrs).cpu().numpy()
+        else:
+            sums = e.train_steps_host(kg.triples, B, 11, 0, 0.2, lrs)
+        outs.append((sums, e.embeddings().cpu()))
+        e.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
+    assert np.isfinite(outs[0][0]).all() and np.all(np.abs(outs[0][0] / B - 0.2) < 0.01)
+    E0 = torch.from_numpy(kg.E)
+    changed = (outs[0][1] != E0).any(dim=1)
+    used = torch.zeros(kg.n_rows, dtype=torch.bool)
+    used[torch.from_numpy(kg.triples.reshape(-1).astype(np.int64))] = True
+    # every changed row was used by a triple or drawn as a corrupt entity (same type => entity row)
+    assert not bool(changed[: kg.n_relations][~used[: kg.n_relations]].any())
+    assert int(changed.sum()) > 3 * B          # most touched rows really moved
