@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhole_b200.so")
+LIB_PATH = os.environ.get("HOLE_B200_LIB", os.path.join(_HERE, "libhole_b200.so"))   # override: A/B experiments
 
 HOLE_SIDE_TAIL, HOLE_SIDE_HEAD, HOLE_SIDE_BOTH = 0, 1, 2
 HOLE_RANK_BF16, HOLE_RANK_BF16X3 = 0, 1
