@@ -44,7 +44,9 @@ enum { MODE_COUNT = 0, MODE_DIAG = 1 };
 
 struct RankParams {
   int mode;
-  int num_kb;        // K / 64
+  int num_kb;        // k-blocks of ONE operand part: round_up(D, 64) / 64
+  int parts;         // 1 = bf16 operands; 2 = split-bf16: operand columns are [hi | lo] and the
+                     //     contraction is hi.hi + lo.hi + hi.lo (HOLE_RANK_BF16X3)
   int last_kb_mmas;  // K=16 slices of the last k-block that hold real columns (the rest is zero padding)
   int stages;        // ring depth for candidate k-blocks
   int m_tiles;       // query tiles
@@ -237,8 +239,9 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms repeat every 1024 bytes: align the operand area explicitly
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;                                       // num_kb x 16 KB
-  uint8_t* sB = smem + (size_t)p.num_kb * A_KB_BYTES;       // stages x 32 KB
+  const int nkb_all = p.num_kb * p.parts;                   // k-blocks of a whole operand row
+  uint8_t* sA = smem;                                       // nkb_all x 16 KB
+  uint8_t* sB = smem + (size_t)nkb_all * A_KB_BYTES;        // stages x 32 KB
   SmemLayout* sl = reinterpret_cast<SmemLayout*>(sB + (size_t)p.stages * B_KB_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -266,15 +269,15 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int m_tile = item / p.n_chunks, chunk = item % p.n_chunks;
         mbar_wait(&sl->a_empty, a_phase ^ 1);
-        mbar_expect_tx(&sl->a_full, (uint32_t)p.num_kb * A_KB_BYTES);
-        for (int kb = 0; kb < p.num_kb; ++kb)
+        mbar_expect_tx(&sl->a_full, (uint32_t)nkb_all * A_KB_BYTES);
+        for (int kb = 0; kb < nkb_all; ++kb)
           tma_load_2d(sA + (size_t)kb * A_KB_BYTES, &tmA, &sl->a_full, kb * BK, m_tile * BM);
         a_phase ^= 1;
         const int t0 = chunk * p.chunk_tiles;
         const int t1 = (p.mode == MODE_DIAG) ? t0 + 1 : min(p.n_tiles, t0 + p.chunk_tiles);
         for (int t = t0; t < t1; ++t) {
           const int row0 = (p.mode == MODE_DIAG) ? m_tile * BM : t * BN;
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+          for (int kb = 0; kb < nkb_all; ++kb) {
             mbar_wait(&sl->empty[stage], phase ^ 1);
             mbar_expect_tx(&sl->full[stage], B_KB_BYTES);
             tma_load_2d(sB + (size_t)stage * B_KB_BYTES, &tmB, &sl->full[stage], kb * BK, row0);
@@ -300,18 +303,24 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&sl->tmem_empty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_addr = tmem_base + (uint32_t)acc * BN;
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+          for (int kb = 0; kb < nkb_all; ++kb) {
             mbar_wait(&sl->full[stage], phase);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(sA + (size_t)kb * A_KB_BYTES);
             const uint32_t b_addr = smem_u32(sB + (size_t)stage * B_KB_BYTES);
-            const int nk = (kb == p.num_kb - 1) ? p.last_kb_mmas : BK / UMMA_K;   // skip all-zero slices
+            // candidate k-block kb of part pb meets query part 0 (hi); a candidate hi block also
+            // meets the query lo block: hi.hi + lo.hi + hi.lo
+            const int pb = kb / p.num_kb, kk = kb - pb * p.num_kb;
+            const int na = (p.parts == 2 && pb == 0) ? 2 : 1;
+            const int nk = (kk == p.num_kb - 1) ? p.last_kb_mmas : BK / UMMA_K;   // skip all-zero slices
+            for (int ja = 0; ja < na; ++ja) {
+              const uint32_t a_addr = smem_u32(sA + (size_t)(ja * p.num_kb + kk) * A_KB_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              if (k < nk) {
-                const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2);
-                const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2);
-                umma_bf16(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                if (k < nk) {
+                  const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2);
+                  const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2);
+                  umma_bf16(d_addr, da, db, idesc, (kb | ja | k) != 0 ? 1u : 0u);
+                }
               }
             }
             umma_commit(&sl->empty[stage]);          // frees the smem slot when the MMAs retire
@@ -582,13 +591,13 @@ hole_rank_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // One warp per row.  Candidate operand: clip(E_j) rounded to bf16, [Re | Im | 0-pad] of K columns.
 __global__ void __launch_bounds__(256)
 hole_rank_pack_cand_kernel(const float* __restrict__ table, int stride, int H, int64_t ent_begin,
-                           int Nc, int Npad, int K, __nv_bfloat16* __restrict__ out) {
+                           int Nc, int Npad, int K, int parts, __nv_bfloat16* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (r >= Npad) return;
-  __nv_bfloat16* o = out + (size_t)r * K;
+  __nv_bfloat16* o = out + (size_t)r * K * parts;       // row = [hi part (K) | lo part (K)]
   if (r >= Nc) {
-    for (int k = lane; k < K; k += 32) o[k] = __float2bfloat16(0.f);
+    for (int k = lane; k < K * parts; k += 32) o[k] = __float2bfloat16(0.f);
     return;
   }
   const float* x = table + (size_t)(ent_begin + r) * stride;
@@ -602,7 +611,9 @@ hole_rank_pack_cand_kernel(const float* __restrict__ table, int stride, int H, i
     float v = 0.f;
     if (k < H) v = x[k] * sc;
     else if (k < 2 * H) v = x[Hp + (k - H)] * sc;
-    o[k] = __float2bfloat16(v);
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    o[k] = hi;
+    if (parts == 2) o[K + k] = __float2bfloat16(v - __bfloat162float(hi));
   }
 }
 
@@ -611,14 +622,14 @@ hole_rank_pack_cand_kernel(const float* __restrict__ table, int stride, int H, i
 __global__ void __launch_bounds__(256)
 hole_rank_pack_query_kernel(const float* __restrict__ table, int stride, int H,
                             const int32_t* __restrict__ queries, int Q, int Qpad, int side,
-                            int64_t ent_begin, int K, __nv_bfloat16* __restrict__ out,
+                            int64_t ent_begin, int K, int parts, __nv_bfloat16* __restrict__ out,
                             int32_t* __restrict__ true_idx) {
   const int lane = threadIdx.x & 31;
   const int64_t qi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (qi >= Qpad) return;
-  __nv_bfloat16* o = out + (size_t)qi * K;
+  __nv_bfloat16* o = out + (size_t)qi * K * parts;      // row = [hi part (K) | lo part (K)]
   if (qi >= Q) {
-    for (int k = lane; k < K; k += 32) o[k] = __float2bfloat16(0.f);
+    for (int k = lane; k < K * parts; k += 32) o[k] = __float2bfloat16(0.f);
     if (lane == 0) true_idx[qi] = -1;
     return;
   }
@@ -645,15 +656,20 @@ hole_rank_pack_query_kernel(const float* __restrict__ table, int stride, int H,
     s2 += __shfl_xor_sync(0xffffffffu, s2, o2);
   }
   const float c1 = fminf(__frsqrt_rn(s1), 1.0f), c2 = fminf(__frsqrt_rn(s2), 1.0f);
-  for (int k = lane; k < K; k += 32) o[k] = __float2bfloat16(0.f);
+  for (int k = lane; k < K * parts; k += 32) o[k] = __float2bfloat16(0.f);
   __syncwarp();
   for (int k = lane; k < H; k += 32) {
     const float a = x1[k] * c1, b = x1[Hp + k] * c1, c = x2[k] * c2, d = x2[Hp + k] * c2;
     float re, im;
     if (side == HOLE_SIDE_TAIL) { re = a * c - b * d; im = a * d + b * c; }   // (a,b)=h (c,d)=r
     else                        { re = a * c + b * d; im = a * d - b * c; }   // (a,b)=r (c,d)=t
-    o[k] = __float2bfloat16(re);
-    o[H + k] = __float2bfloat16(im);
+    const __nv_bfloat16 rh = __float2bfloat16(re), ih = __float2bfloat16(im);
+    o[k] = rh;
+    o[H + k] = ih;
+    if (parts == 2) {
+      o[K + k] = __float2bfloat16(re - __bfloat162float(rh));
+      o[K + H + k] = __float2bfloat16(im - __bfloat162float(ih));
+    }
   }
   if (lane == 0) true_idx[qi] = (int32_t)((int64_t)(side == HOLE_SIDE_TAIL ? t : h) - ent_begin);
 }
@@ -678,7 +694,7 @@ hole_rank_gather_true_kernel(const __nv_bfloat16* __restrict__ cand, const int32
 // for accumulation order, i.e. only exact near-ties can differ.
 __global__ void __launch_bounds__(256)
 hole_rank_filter_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ cand,
-                        int K, const int64_t* __restrict__ foff, const int32_t* __restrict__ fids,
+                        int K, int parts, const int64_t* __restrict__ foff, const int32_t* __restrict__ fids,
                         int64_t ent_begin, int Nc, const float* __restrict__ true_score,
                         const int32_t* __restrict__ true_idx, int Q, int32_t* __restrict__ filt_cnt) {
   const int lane = threadIdx.x & 31;
@@ -686,14 +702,21 @@ hole_rank_filter_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat1
   if (qi >= Q) return;
   const float thr = true_score[qi];
   const int ti = true_idx[qi];
-  const __nv_bfloat16* qrow = qp + (size_t)qi * K;
+  const __nv_bfloat16* qrow = qp + (size_t)qi * K * parts;
   int hits = 0;
   for (int64_t p = foff[qi]; p < foff[qi + 1]; ++p) {
     const int64_t j = (int64_t)fids[p] - ent_begin;
     if (j < 0 || j >= Nc) continue;            // warp-uniform
-    const __nv_bfloat16* crow = cand + (size_t)j * K;
+    const __nv_bfloat16* crow = cand + (size_t)j * K * parts;
     float s = 0.f;
-    for (int k = lane; k < K; k += 32) s = fmaf(__bfloat162float(qrow[k]), __bfloat162float(crow[k]), s);
+    for (int k = lane; k < K; k += 32) {
+      const float qh = __bfloat162float(qrow[k]), ch = __bfloat162float(crow[k]);
+      s = fmaf(qh, ch, s);
+      if (parts == 2) {
+        s = fmaf(__bfloat162float(qrow[K + k]), ch, s);
+        s = fmaf(qh, __bfloat162float(crow[K + k]), s);
+      }
+    }
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
     hits += (s < thr || (s == thr && j < ti)) ? 1 : 0;
@@ -764,8 +787,8 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
   if (side == HOLE_SIDE_BOTH) Q *= 2;    // output rows: [tail ranks of all queries | head ranks]
   HOLE_CHECK_ARG(table && queries && true_score_io && raw_before && filt_before);
   HOLE_CHECK_ARG((filter_off == nullptr) == (filter_ids == nullptr));
-  if (precision != HOLE_RANK_BF16)
-    return hole_set_error(HOLE_ERR_UNSUPPORTED, "ranking precision %d not built (only HOLE_RANK_BF16)", precision);
+  HOLE_CHECK_ARG(precision == HOLE_RANK_BF16 || precision == HOLE_RANK_BF16X3);
+  const int parts = (precision == HOLE_RANK_BF16X3) ? 2 : 1;
   HOLE_CHECK_ARG(Q < (int64_t(1) << 30) && ent_end - ent_begin < (int64_t(1) << 30));
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -780,36 +803,40 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
   const int Npad = (Nc + BN - 1) / BN * BN;
   const int qtile = use_pair ? 2 * BM : BM;
   const int Qpad = (int)((Q + qtile - 1) / qtile * qtile);
-  const int a_bytes = num_kb * A_KB_BYTES;
+  const int Kall = K * parts;                                  // operand columns in memory
+  const int a_bytes = num_kb * parts * A_KB_BYTES;
   const int b_stage_bytes = use_pair ? B_HALF_BYTES : B_KB_BYTES;
   int stages = (SMEM_LIMIT - a_bytes - 2048) / b_stage_bytes;
   stages = std::min(stages, use_pair ? MAX_STAGES : 4);
   if (stages < 2)
-    return hole_set_error(HOLE_ERR_UNSUPPORTED, "embedding_dim %d too large for the ranking kernel's smem budget", c->dim);
+    return hole_set_error(HOLE_ERR_UNSUPPORTED, "embedding_dim %d too large for the ranking kernel's smem budget at precision %d",
+                          c->dim, precision);
+  if (use_pair && parts == 2)
+    return hole_set_error(HOLE_ERR_UNSUPPORTED, "the experimental CTA-pair kernel has no split-bf16 mode");
   const int smem_bytes = a_bytes + stages * b_stage_bytes + 2048;   // + alignment slack + barriers
 
   if (c->rank == nullptr) c->rank = new hole_rank_ws();
   hole_rank_ws* w = c->rank;
-  if ((size_t)Npad * K > w->cand_cap) {
+  if ((size_t)Npad * Kall > w->cand_cap) {
     HOLE_CUDA_TRY(cudaStreamSynchronize(st));
     cudaFree(w->cand); w->cand = nullptr; w->cand_cap = 0;
-    if (cudaMalloc((void**)&w->cand, (size_t)Npad * K * 2) != cudaSuccess) {
+    if (cudaMalloc((void**)&w->cand, (size_t)Npad * Kall * 2) != cudaSuccess) {
       cudaGetLastError();
       return hole_set_error(HOLE_ERR_ALLOC, "ranking candidate operand allocation failed");
     }
-    w->cand_cap = (size_t)Npad * K;
+    w->cand_cap = (size_t)Npad * Kall;
   }
-  if ((size_t)Qpad * K > w->q_cap) {
+  if ((size_t)Qpad * Kall > w->q_cap) {
     HOLE_CUDA_TRY(cudaStreamSynchronize(st));
     cudaFree(w->qp); cudaFree(w->tq); cudaFree(w->true_idx);
     w->qp = w->tq = nullptr; w->true_idx = nullptr; w->q_cap = 0;
-    if (cudaMalloc((void**)&w->qp, (size_t)Qpad * K * 2) != cudaSuccess ||
-        cudaMalloc((void**)&w->tq, (size_t)(Qpad + BN) * K * 2) != cudaSuccess ||
+    if (cudaMalloc((void**)&w->qp, (size_t)Qpad * Kall * 2) != cudaSuccess ||
+        cudaMalloc((void**)&w->tq, (size_t)(Qpad + BN) * Kall * 2) != cudaSuccess ||
         cudaMalloc((void**)&w->true_idx, (size_t)Qpad * 4) != cudaSuccess) {
       cudaGetLastError();
       return hole_set_error(HOLE_ERR_ALLOC, "ranking query operand allocation failed");
     }
-    w->q_cap = (size_t)Qpad * K;
+    w->q_cap = (size_t)Qpad * Kall;
   }
   if (!w->attr_set) {
     HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -817,19 +844,20 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
     w->attr_set = true;
   }
 
-  w->last_npad = Npad; w->last_qpad = Qpad; w->last_K = K;
+  w->last_npad = Npad; w->last_qpad = Qpad; w->last_K = Kall;
   // operands
-  hole_rank_pack_cand_kernel<<<(unsigned)((Npad + 7) / 8), 256, 0, st>>>(table, c->row_stride, c->H, ent_begin, Nc, Npad, K, w->cand);
+  hole_rank_pack_cand_kernel<<<(unsigned)((Npad + 7) / 8), 256, 0, st>>>(table, c->row_stride, c->H, ent_begin, Nc, Npad, K, parts, w->cand);
   HOLE_LAUNCHED();
-  hole_rank_pack_query_kernel<<<(unsigned)((Qpad + 7) / 8), 256, 0, st>>>(table, c->row_stride, c->H, queries, (int)Q, Qpad, side, ent_begin, K, w->qp, w->true_idx);
+  hole_rank_pack_query_kernel<<<(unsigned)((Qpad + 7) / 8), 256, 0, st>>>(table, c->row_stride, c->H, queries, (int)Q, Qpad, side, ent_begin, K, parts, w->qp, w->true_idx);
   HOLE_LAUNCHED();
 
   CUtensorMap mapA, mapB;
-  int rc = make_map(&mapA, w->qp, Qpad, K, BM);
+  int rc = make_map(&mapA, w->qp, Qpad, Kall, BM);
   if (rc) return rc;
 
   RankParams p{};
   p.num_kb = num_kb;
+  p.parts = parts;
   p.last_kb_mmas = (c->dim - (num_kb - 1) * BK + UMMA_K - 1) / UMMA_K;
   p.stages = stages;
   p.m_tiles = Qpad / qtile;
@@ -839,10 +867,10 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
 
   if (compute_true) {
     const int rows = Qpad + BN;
-    hole_rank_gather_true_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w->cand, w->true_idx, Nc, Qpad, K, w->tq);
+    hole_rank_gather_true_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w->cand, w->true_idx, Nc, Qpad, Kall, w->tq);
     HOLE_LAUNCHED();
-    HOLE_CUDA_TRY(cudaMemsetAsync(w->tq + (size_t)Qpad * K, 0, (size_t)BN * K * 2, st));
-    rc = make_map(&mapB, w->tq, rows, K, use_pair ? BN / 2 : BN);
+    HOLE_CUDA_TRY(cudaMemsetAsync(w->tq + (size_t)Qpad * Kall, 0, (size_t)BN * Kall * 2, st));
+    rc = make_map(&mapB, w->tq, rows, Kall, use_pair ? BN / 2 : BN);
     if (rc) return rc;
     p.mode = MODE_DIAG;
     p.n_tiles = 1; p.chunk_tiles = 1; p.n_chunks = 1;
@@ -857,7 +885,7 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
     HOLE_LAUNCHED();
   }
 
-  rc = make_map(&mapB, w->cand, Npad, K, use_pair ? BN / 2 : BN);
+  rc = make_map(&mapB, w->cand, Npad, Kall, use_pair ? BN / 2 : BN);
   if (rc) return rc;
   p.mode = MODE_COUNT;
   p.n_tiles = Npad / BN;
@@ -883,7 +911,7 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
     HOLE_LAUNCHED();
   }
   if (filter_off != nullptr) {
-    hole_rank_filter_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, st>>>(w->qp, w->cand, K, filter_off, filter_ids, ent_begin, Nc, true_score_io, w->true_idx, (int)Q, filt_before);
+    hole_rank_filter_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, st>>>(w->qp, w->cand, K, parts, filter_off, filter_ids, ent_begin, Nc, true_score_io, w->true_idx, (int)Q, filt_before);
     HOLE_LAUNCHED();
   }
   return HOLE_OK;

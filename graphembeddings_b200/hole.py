@@ -24,7 +24,8 @@ import torch
 
 from . import data as D
 from . import tf_bundle
-from .engine import HOLE_SIDE_HEAD, HOLE_SIDE_TAIL, HoleEngine, inverse_time_decay
+from .engine import (HOLE_RANK_BF16, HOLE_RANK_BF16X3, HOLE_SIDE_HEAD, HOLE_SIDE_TAIL, HoleEngine,
+                     inverse_time_decay)
 
 FLAGS = None
 
@@ -284,7 +285,7 @@ def _logit(p):
 
 
 def eval_link_prediction(eng, queries, known, relation_count, entity_count, sides=("tail", "head"),
-                         threshold=None, results_path=None):
+                         threshold=None, results_path=None, precision=HOLE_RANK_BF16X3):
     """All-entity generalisation of holE.py:427-472 on the tensor cores: every test triple is
     ranked against all entity rows on each requested side, ascending by (score, id).
     Train/valid-true candidates do not advance the filtered rank (holE.py:454-463); a test
@@ -292,6 +293,8 @@ def eval_link_prediction(eng, queries, known, relation_count, entity_count, side
     threshold: the reference's confidence gate `min sigma over the candidates < infer_threshold`
     (holE.py:438), evaluated as "some candidate scores below logit(threshold)"; None disables
     it (it cannot fire for the live model).
+    precision: split-bf16 by default (ranks match the fp32 reference except within ~3e-5 of a
+    tie); HOLE_RANK_BF16 is 3x cheaper and what bench.py times.
     Returns (raw_positions, filtered_positions) lists."""
     queries = np.unique(np.asarray(queries, dtype=np.int32).reshape(-1, 3), axis=0)   # test sets dedupe
     raw_positions, filtered_positions = [], []
@@ -303,12 +306,12 @@ def eval_link_prediction(eng, queries, known, relation_count, entity_count, side
     for side_name in sides:
         side = HOLE_SIDE_TAIL if side_name == "tail" else HOLE_SIDE_HEAD
         foff, fids = D.build_filter_csr(queries, known, side_name)
-        raw, filt, ts = eng.rank(queries, side, relation_count, entity_count, foff, fids)
+        raw, filt, ts = eng.rank(queries, side, relation_count, entity_count, foff, fids, precision=precision)
         ok = np.ones(len(queries), bool)
         if threshold is not None:
             gate = torch.full((len(queries),), _logit(threshold), dtype=torch.float32, device=eng.device)
             below, _, _ = eng.rank(queries, side, relation_count, entity_count, true_score=gate,
-                                   compute_true=False)
+                                   compute_true=False, precision=precision)
             ok = below.cpu().numpy() > 0
         raw, filt, ts = raw.cpu().numpy(), filt.cpu().numpy(), ts.cpu().numpy()
         sig = 1.0 / (1.0 + np.exp(-ts.astype(np.float64)))
@@ -392,8 +395,10 @@ def infer_triples(flags=None, log=print):
                          f"{(data.entity_count, flags.embedding_dim)}")
     eng = HoleEngine(data.entity_count, flags.embedding_dim).set_embeddings(E)
     threshold = flags.infer_threshold if getattr(flags, "infer_gate", False) else None
+    precision = HOLE_RANK_BF16 if getattr(flags, "rank_precision", "bf16x3") == "bf16" else HOLE_RANK_BF16X3
     raw, filt = eval_link_prediction(eng, data.test, data.known, data.relation_count, data.entity_count,
-                                     threshold=threshold, results_path='inference_results.tsv')
+                                     threshold=threshold, results_path='inference_results.tsv',
+                                     precision=precision)
     if not raw:
         log('No test triple passed the confidence gate; no ranks recorded.')
         return None
@@ -427,6 +432,8 @@ def build_parser():
                         help='The minimum number of mentions for an entity to be a viable candidate in inference.')
     parser.add_argument('--infer_gate', action='store_true',
                         help='Apply the reference\'s `min sigma < infer_threshold` gate (off: it never fires).')
+    parser.add_argument('--rank_precision', choices=['bf16', 'bf16x3'], default='bf16x3',
+                        help='Tensor-core operand precision of --infer (bf16x3 = split-bf16, ~fp32 ranks).')
     parser.add_argument('--seed', type=int, default=0)
     parser.add_argument('--max_steps', type=int, default=None, help='Stop after this many steps (testing).')
     return parser

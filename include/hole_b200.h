@@ -54,7 +54,7 @@ typedef struct hole_ctx hole_ctx;
 
 /* Operand precision of the tensor-core ranking contraction. */
 #define HOLE_RANK_BF16   0       /* bf16 operands, fp32 accumulate                      */
-#define HOLE_RANK_BF16X3 1       /* split-bf16 (hi*hi + hi*lo + lo*hi), ~fp32 accuracy  */
+#define HOLE_RANK_BF16X3 1       /* split-bf16 (hi*hi + lo*hi + hi*lo): ranks match fp32 except within ~3e-5 of a tie; dim <= 320 */
 
 /* ABI version of this header; hole_abi_version() returns the library's. */
 #define HOLE_ABI_VERSION 1

@@ -195,7 +195,7 @@ def test_empty_queries_and_errors(eng_mod):
     with pytest.raises(eng_mod.HoleError):
         e.rank(kg.triples, 0, 3, 99999)          # range outside the table
     with pytest.raises(eng_mod.HoleError):
-        e.rank(kg.triples, 0, 3, 303, precision=eng_mod.HOLE_RANK_BF16X3)
+        e.rank(kg.triples, 0, 3, 303, precision=7)           # unknown precision
 
 
 def test_sharded_rank_single_rank_matches_engine(eng_mod):
@@ -257,3 +257,32 @@ def test_full_size_config3_sample_against_fp64_contraction(eng_mod):
     e.rank(kg.triples, 0, b, mid, true_score=ts.clone(), compute_true=False, raw_before=raw2, filt_before=f2)
     e.rank(kg.triples, 0, mid, en, true_score=ts.clone(), compute_true=False, raw_before=raw2, filt_before=f2)
     assert torch.equal(raw2, raw)
+
+
+@pytest.mark.parametrize("dim", [64, 150, 256])
+@pytest.mark.parametrize("side", [0, 1])
+def test_split_bf16_precision_matches_fp64_oracle(eng_mod, dim, side):
+    """HOLE_RANK_BF16X3 (hi.hi + lo.hi + hi.lo on the tensor cores): ranks agree with the fp64
+    oracle on the fp32 table except for candidates within 3e-5 of the threshold -- two orders of
+    magnitude tighter than plain bf16 operands."""
+    kg, e = _setup(eng_mod, 9, 3000, 500, dim, seed=50 + dim + side)
+    b, en = kg.n_relations, kg.n_rows
+    name, col = ("tail", 1) if side == 0 else ("head", 0)
+    S = O.all_scores(kg.E.astype(np.float64), kg.triples, name, np.arange(b, en), np.float64)
+    tj = kg.triples[:, col].astype(np.int64) - b
+    thr = S[np.arange(len(tj)), tj]
+    known = D.synthetic_kg(9, 3000, 20000, 4, 8, seed=96, with_embeddings=False).triples
+    foff, fids = D.build_filter_csr(kg.triples, known, name)
+    raw, filt, ts = e.rank(kg.triples, side, b, en, foff, fids, precision=eng_mod.HOLE_RANK_BF16X3)
+    raw, filt, ts = raw.cpu().numpy(), filt.cpu().numpy(), ts.cpu().numpy()
+    eps = 3e-5
+    assert np.abs(ts - thr).max() < eps
+    lo = (S < thr[:, None] - eps).sum(1)
+    hi = (S <= thr[:, None] + eps).sum(1) - 1
+    assert np.all(raw >= lo) and np.all(raw <= hi)
+    exact = (S < thr[:, None]).sum(1)
+    frac_x3 = np.mean(raw == exact)
+    raw_bf, _, _ = e.rank(kg.triples, side, b, en)
+    frac_bf = np.mean(raw_bf.cpu().numpy() == exact)
+    assert frac_x3 > 0.97 and frac_x3 > frac_bf
+    assert np.all(filt <= raw) and np.all(filt >= 0)
