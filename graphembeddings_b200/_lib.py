@@ -42,6 +42,7 @@ SIGNATURES = {
     "hole_rank_debug_operands": (_int, [_p, _p, _p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_int), _p]),
     "hole_profile_enable": (_int, [_p, _int]),
     "hole_profile_read": (_int, [_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "hole_parse_triples": (_i64, [C.c_char_p, _p, _i64]),
     "hole_crc32c": (C.c_uint32, [C.c_uint32, _p, _u64]),
     "hole_launch_count": (_i64, []),
     "hole_launch_count_reset": (None, []),

@@ -1554,3 +1554,52 @@ extern "C" uint32_t hole_crc32c(uint32_t crc, const void* data, uint64_t n) {
   while (n--) c = (c >> 8) ^ g_crc32c_table[0][(c ^ *p++) & 0xFF];
   return c ^ 0xFFFFFFFFu;
 }
+
+// ---------------------------------------------------------------------------------------
+// Fast ingestion of the triple files (host code): `head<TAB>tail<TAB>relation\n`, decimal,
+// no header (holE.py:76-81).  Replaces TextLineReader + decode_csv (holE.py:72-81) for the
+// 30 M-line files of BASELINE config 1, where a Python-level parser takes minutes.
+// Returns the number of triples (<= cap are stored), or a negative error.
+// ---------------------------------------------------------------------------------------
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+extern "C" int64_t hole_parse_triples(const char* path, int32_t* out, int64_t cap) {
+  if (path == nullptr || (out == nullptr && cap > 0)) return hole_set_error(HOLE_ERR_ARG, "hole_parse_triples: bad argument");
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return hole_set_error(HOLE_ERR_ARG, "cannot open %s", path);
+  struct stat stt;
+  if (fstat(fd, &stt) != 0) { close(fd); return hole_set_error(HOLE_ERR_ARG, "cannot stat %s", path); }
+  const size_t size = (size_t)stt.st_size;
+  if (size == 0) { close(fd); return 0; }
+  const char* p = (const char*)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) return hole_set_error(HOLE_ERR_ALLOC, "cannot map %s", path);
+  const char* end = p + size;
+  const char* q = p;
+  int64_t n = 0, line = 0;
+  int64_t rc = 0;
+  while (q < end) {
+    while (q < end && (*q == '\n' || *q == '\r')) ++q;      // blank lines
+    if (q >= end) break;
+    ++line;
+    int64_t v[3];
+    for (int f = 0; f < 3; ++f) {
+      if (q >= end || *q < '0' || *q > '9') { rc = -1; break; }
+      int64_t x = 0;
+      while (q < end && *q >= '0' && *q <= '9') { x = x * 10 + (*q - '0'); if (x > 2147483647LL) { rc = -1; break; } ++q; }
+      if (rc) break;
+      v[f] = x;
+      if (f < 2) { if (q < end && *q == '\t') ++q; else { rc = -1; break; } }
+    }
+    if (rc) break;
+    if (q < end && *q != '\n' && *q != '\r') { rc = -1; break; }
+    if (n < cap) { out[3 * n] = (int32_t)v[0]; out[3 * n + 1] = (int32_t)v[1]; out[3 * n + 2] = (int32_t)v[2]; }
+    ++n;
+  }
+  munmap((void*)p, size);
+  if (rc) return hole_set_error(HOLE_ERR_ARG, "%s: line %lld is not three tab-separated non-negative int32 values", path, (long long)line);
+  return n;
+}

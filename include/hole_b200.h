@@ -189,6 +189,11 @@ HOLE_API int hole_rank_debug_operands(hole_ctx* ctx, void* cand_out, void* query
 HOLE_API int hole_profile_enable(hole_ctx* ctx, int on);
 HOLE_API int hole_profile_read(hole_ctx* ctx, double* k1_ms, double* k3_ms, int64_t* n_steps);
 
+/* Host helper: parse a triple file (`head<TAB>tail<TAB>relation` per line, holE.py:76-81) into
+ * out [host] int32[cap,3].  Returns the number of triples in the file (call with cap = 0 to
+ * size the buffer), or a negative error code. */
+HOLE_API int64_t hole_parse_triples(const char* path, int32_t* out_host, int64_t cap);
+
 /* Host helper for the checkpoint writer: CRC32C (Castagnoli) of a HOST buffer, continuing
  * from `crc` (0 to start).  TF's tensor bundle stores it masked (holE.py:359 saver.save). */
 HOLE_API uint32_t hole_crc32c(uint32_t crc, const void* data_host, uint64_t n);

@@ -90,3 +90,24 @@ def test_lr_schedule_matches_oracle():
     from oracle import hole_oracle as O
     for step in (0, 1, 1000, 123456):
         assert inverse_time_decay(0.1, step, 32 * 943, 0.5) == O.inverse_time_decay(0.1, step, 32 * 943, 0.5)
+
+
+def test_native_triple_parser_matches_numpy(tmp_path, golden_dir):
+    from graphembeddings_b200 import build
+    build.build()
+    src = os.path.join(golden_dir, "fb15k_triples-valid_head.txt")
+    want = np.loadtxt(src, dtype=np.int64, delimiter="\t").astype(np.int32)
+    got = D.load_triples(src)
+    assert got.dtype == np.int32 and np.array_equal(got, want)
+    # no trailing newline, CRLF, blank line at the end
+    p = tmp_path / "t.txt"
+    p.write_bytes(b"1\t2\t3\r\n40\t50\t6\n\n7\t8\t9")
+    assert D.load_triples(str(p)).tolist() == [[1, 2, 3], [40, 50, 6], [7, 8, 9]]
+    bad = tmp_path / "bad.txt"
+    bad.write_text("1\t2\n")
+    with pytest.raises(ValueError):
+        D.load_triples(str(bad))
+    neg = tmp_path / "neg.txt"
+    neg.write_text("1\t-2\t3\n")
+    with pytest.raises(ValueError):
+        D.load_triples(str(neg))
