@@ -35,6 +35,8 @@ SIGNATURES = {
     "hole_train_step": (_int, [_p, _p, _p, _p, _int, _i64, _f32, _f32, _p, _p, _p]),
     "hole_train_step_ex": (_int, [_p, _p, _p, _p, _p, _int, _i64, _f32, _f32, _p, _p, _p]),
     "hole_train_step_plan": (_int, [_p, _p, _p, _i64, _p]),
+    "hole_enable_peer_access": (_int, [_p, _int]),
+    "hole_gather_rows": (_int, [_p, _p, _p, _i64, _p, _i64, _p]),
     "hole_add_rows": (_int, [_p, _p, _p, _i64, _p, _i64, _p]),
     "hole_train_steps": (_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _u64, _u64, _f32, _p, _p, _p, _p]),
     "hole_train_steps_host": (_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _u64, _u64, _f32, _p, _p, _p]),

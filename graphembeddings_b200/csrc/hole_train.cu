@@ -893,9 +893,23 @@ hole_add_rows_kernel(float* __restrict__ E, const int64_t* __restrict__ ids, con
   float* erow = E + (size_t)(ids[k] + id_offset) * stride;
   Row<V> x, d;
   row_load<GS, V, false>(x, erow, lane, nvec);
-  row_load<GS, V, true>(d, rows + (size_t)k * stride, lane, nvec);
+  row_load<GS, V, false>(d, rows + (size_t)k * stride, lane, nvec);   // may be peer memory
   row_add(x, d);
   row_store<GS, V>(x, erow, lane, nvec);
+}
+
+// dst[k] = table[ids[k] + id_offset] (multi-GPU: the owner pushes the rows a peer asked for
+// straight into that peer's step table over NVLink -- dst may be peer memory)
+template <int GS, int V>
+__global__ void __launch_bounds__(256)
+hole_gather_rows_kernel(const float* __restrict__ E, const int64_t* __restrict__ ids, float* __restrict__ dst,
+                        int64_t n, int64_t id_offset, int nvec, int stride) {
+  const int lane = threadIdx.x % GS;
+  const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
+  if (k >= n) return;
+  Row<V> x;
+  row_load<GS, V, false>(x, E + (size_t)(ids[k] + id_offset) * stride, lane, nvec);
+  row_store<GS, V>(x, dst + (size_t)k * stride, lane, nvec);
 }
 
 // deterministic per-step loss sum: one CTA per step, fixed-shape tree
@@ -1367,6 +1381,30 @@ extern "C" int hole_train_step(hole_ctx* c, float* table, const int32_t* pos, co
                                float* sigma_out, void* stream) {
   return hole_train_step_ex(c, table, nullptr, pos, neg_ent, side, B, margin, lr, loss_out, sigma_out,
                             stream);
+}
+
+extern "C" int hole_enable_peer_access(hole_ctx* c, int peer_device) {
+  HOLE_CHECK_ARG(c && peer_device >= 0);
+  if (peer_device == c->device) return HOLE_OK;
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  int can = 0;
+  HOLE_CUDA_TRY(cudaDeviceCanAccessPeer(&can, c->device, peer_device));
+  if (!can) return hole_set_error(HOLE_ERR_CUDA, "device %d cannot access peer %d", c->device, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return HOLE_OK; }
+  HOLE_CUDA_TRY(e);
+  return HOLE_OK;
+}
+
+extern "C" int hole_gather_rows(hole_ctx* c, const float* table, const int64_t* ids, int64_t id_offset,
+                                float* dst_rows, int64_t n, void* stream) {
+  HOLE_CHECK_ARG(c && n >= 0);
+  if (n == 0) return HOLE_OK;
+  HOLE_CHECK_ARG(table && ids && dst_rows);
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  HOLE_DISPATCH(c, hole_gather_rows_kernel, grid_for_groups(n, c->gs), 256, (cudaStream_t)stream, table, ids,
+                dst_rows, n, id_offset, c->nvec, c->row_stride);
+  return HOLE_OK;
 }
 
 extern "C" int hole_add_rows(hole_ctx* c, float* table, const int64_t* ids, int64_t id_offset,

@@ -152,6 +152,14 @@ class HoleEngine:
                                           _ptr(loss), None, _stream()))
         return loss
 
+    def enable_peer_access(self, peer_device):
+        check(self.lib.hole_enable_peer_access(self._ctx, int(peer_device)))
+
+    def gather_rows(self, table, ids_i64, id_offset, dst_rows):
+        """dst_rows[k] = table[ids[k] + id_offset]; dst_rows may be a peer GPU's (IPC) buffer."""
+        check(self.lib.hole_gather_rows(self._ctx, _ptr(table), _ptr(ids_i64), int(id_offset), _ptr(dst_rows),
+                                        ids_i64.shape[0], _stream()))
+
     def add_rows(self, table, ids_i64, id_offset, rows):
         """table[ids + id_offset] += rows, ids unique (the owner applies one rank's deltas)."""
         check(self.lib.hole_add_rows(self._ctx, _ptr(table), _ptr(ids_i64), int(id_offset), _ptr(rows),

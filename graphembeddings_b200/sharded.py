@@ -282,6 +282,100 @@ class RowShardedTrainer:
         return raw, filt
 
 
+class P2PRowShardedTrainer(RowShardedTrainer):
+    """Same protocol with the two bulk exchanges done by our own kernels over NVLink peer
+    memory instead of NCCL all-to-alls: every rank maps the step table W and the delta table D
+    of every other rank (CUDA IPC); the OWNER of a row pushes it straight into the requester's
+    W (`hole_gather_rows` with a peer destination) and later pulls the requester's delta row out
+    of its D and adds it to the shard in one pass (`hole_add_rows` with a peer source).  NCCL
+    only carries the row ids, the counts, the relation all-reduce and two tiny all-reduces
+    per step that act as stream-ordered barriers."""
+
+    def __init__(self, n_relations, n_entities, dim, backend, dist):
+        super().__init__(n_relations, n_entities, dim, backend, dist)
+        from torch.multiprocessing.reductions import reduce_tensor
+        me = (reduce_tensor(backend.W), reduce_tensor(backend.D), backend.device.index)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, me)
+        self.peer_W, self.peer_D = [], []
+        for k, (hw, hd, dev_k) in enumerate(everyone):
+            if k == self.my_rank:
+                self.peer_W.append(backend.W)
+                self.peer_D.append(backend.D)
+            else:
+                # Open the peer's allocation in MY device's address space (argument 6 of torch's
+                # rebuild is the device the IPC handle is opened on): the tensor then reads as
+                # local to torch while its pages live on GPU k -- kernels launched on my device
+                # reach it over NVLink.  Opened on device k instead, our kernels fault on it
+                # (tools/p2p_diag.py, variant A).
+                backend.eng.enable_peer_access(dev_k)
+                mine = backend.device.index
+                self.peer_W.append(hw[0](*(list(hw[1][:6]) + [mine] + list(hw[1][7:]))))
+                self.peer_D.append(hd[0](*(list(hd[1][:6]) + [mine] + list(hd[1][7:]))))
+        self._flag = torch.zeros(1, dtype=torch.float32, device=backend.device)
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def _barrier(self):
+        self.dist.all_reduce(self._flag)          # stream-ordered, no host synchronisation
+
+    def train_step(self, pos_local, seed, step, margin, lr):
+        dev, eng = self.shard.device, self.be.eng
+        pos = torch.as_tensor(pos_local).to(dev).long()
+        B, R, G = pos.shape[0], self.R, self.world
+        with _Section("corrupt"):
+            side, neg = self.be.corrupt(pos.to(torch.int32), seed, step, self.my_rank * B)
+            neg = neg.to(dev)
+        with _Section("unique"):
+            ents = torch.cat([pos[:, 0], pos[:, 1], neg]).to(torch.int32)
+            uniq, inv = torch.unique(ents, return_inverse=True)
+            uniq = uniq.long()
+            U = uniq.shape[0]
+        with _Section("route (counts, host sync)"):
+            bounds = R + self.rows_per * torch.arange(1, G + 1, device=dev)
+            cut = torch.searchsorted(uniq, bounds)
+            send = torch.diff(cut, prepend=torch.zeros(1, dtype=cut.dtype, device=dev))
+            meta = torch.stack([send, cut - send], dim=1).contiguous()     # (count, offset in my list) per owner
+            meta_in = torch.empty_like(meta)
+            self.dist.all_to_all_single(meta_in, meta)                     # per requester: (count, its offset)
+            host = torch.cat([meta, meta_in]).tolist()                     # one host synchronisation
+            send_counts = [int(r[0]) for r in host[:G]]
+            recv_counts = [int(r[0]) for r in host[G:]]
+            recv_offs = [int(r[1]) for r in host[G:]]
+        with _Section("a2a ids"):
+            ids_in = self._a2a(uniq, send_counts, recv_counts)
+        with _Section("plan (side stream)"):
+            pos_w = torch.stack([R + inv[:B], R + inv[B:2 * B], pos[:, 2]], dim=1).to(torch.int32)
+            neg_w = (R + inv[2 * B:]).to(torch.int32)
+            self.be.plan(pos_w, neg_w)
+        with _Section("push rows to peers"):
+            off = 0
+            for k in range(G):
+                n_k = recv_counts[k]
+                if n_k:
+                    dst = self.peer_W[k][R + recv_offs[k]: R + recv_offs[k] + n_k]
+                    eng.gather_rows(self.shard, ids_in[off:off + n_k], R - self.begin, dst)
+                off += n_k
+            self._barrier()                        # every rank's W is complete (and last step's pulls are done)
+        with _Section("local step (K1+K3, delta mode)"):
+            self.be.W[:R].copy_(self.shard[:R])
+            loss = self.be.step_delta(R + U, pos_w, neg_w, side, margin, lr)
+        with _Section("allreduce relations"):
+            d_rel = self.be.D[:R].contiguous()
+            self.dist.all_reduce(d_rel)
+            self.shard[:R] += d_rel
+            self._barrier()                        # every rank's D is complete
+        with _Section("pull deltas from peers"):
+            off = 0
+            for k in range(G):                     # rank order: deterministic
+                n_k = recv_counts[k]
+                if n_k:
+                    src = self.peer_D[k][R + recv_offs[k]: R + recv_offs[k] + n_k]
+                    eng.add_rows(self.shard, ids_in[off:off + n_k], R - self.begin, src)
+                off += n_k
+        return loss
+
+
 # --------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1)
 # --------------------------------------------------------------------------------------
@@ -296,7 +390,8 @@ def bench(args, dist, rank, world, local_rank):
     kg = D.make_config(B_.WORKLOAD, n_triples=(K + W) * Bl * world)
     off, ids = D.build_type_csr(kg.type_of)
     be = CudaBackend(kg.n_relations, kg.dim, Bl, local_rank, kg.type_of, off, ids)
-    tr = RowShardedTrainer(kg.n_relations, kg.n_entities, kg.dim, be, dist).load_embeddings(kg.E)
+    cls = RowShardedTrainer if os.environ.get("HOLE_SHARDED_NCCL") == "1" else P2PRowShardedTrainer
+    tr = cls(kg.n_relations, kg.n_entities, kg.dim, be, dist).load_embeddings(kg.E)
     # step s, rank r takes triples [(s*world + r)*Bl, +Bl)
     mine = torch.from_numpy(kg.triples).view(K + W, world, Bl, 3)[:, rank].contiguous()
     dev_tri = mine.cuda()
@@ -357,7 +452,9 @@ def bench(args, dist, rank, world, local_rank):
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{B_.WORKLOAD}: BASELINE.json configs[1] table row-sharded over {world} GPUs "
-                                   "(relations replicated), NCCL all-to-all of rows and row deltas",
+                                   "(relations replicated); rows pushed / deltas pulled by our kernels over NVLink peer "
+                                   "memory, NCCL for ids, counts and barriers" if cls is P2PRowShardedTrainer else
+                                   f"{B_.WORKLOAD}: table row-sharded over {world} GPUs, NCCL all-to-all of rows and row deltas",
                        "batch_per_gpu": Bl, "global_batch": Bl * world, "margin": B_.MARGIN, "lr0": B_.LR0,
                        "parallelism": f"rowshard{world}", "l2": "table shard larger than L2; no flush",
                        "mean_loss_last_step": losses[-1] / Bl if losses else None},

@@ -122,12 +122,19 @@ HOLE_API int hole_train_step(hole_ctx* ctx, float* table, const int32_t* pos, co
  * hole_train_step_plan: optionally builds the integer update plan for the next
  * hole_train_step(_ex) call with the same pos / neg_ent / B on a side stream, so that it
  * overlaps whatever the caller enqueues in between (e.g. the row exchange).
- * hole_add_rows: table[ids[k] + id_offset] += rows[k] for k < n, ids unique within a call. */
+ * hole_add_rows: table[ids[k] + id_offset] += rows[k] for k < n, ids unique within a call.
+ * hole_gather_rows: dst_rows[k] = table[ids[k] + id_offset].  For both, the row buffer may be
+ * PEER device memory (an IPC-mapped buffer of another rank): the owner pushes requested rows
+ * into, and pulls row deltas out of, the requester's step tables directly over NVLink. */
 HOLE_API int hole_train_step_ex(hole_ctx* ctx, float* table, float* delta_out, const int32_t* pos,
                        const int32_t* neg_ent, int side, int64_t B, float margin, float lr,
                        float* loss_out, float* sigma_out, void* stream);
 HOLE_API int hole_train_step_plan(hole_ctx* ctx, const int32_t* pos, const int32_t* neg_ent, int64_t B,
                          void* stream);
+/* Enable loads/stores from ctx's device to memory of `peer_device` (no-op if already on). */
+HOLE_API int hole_enable_peer_access(hole_ctx* ctx, int peer_device);
+HOLE_API int hole_gather_rows(hole_ctx* ctx, const float* table, const int64_t* ids, int64_t id_offset,
+                     float* dst_rows, int64_t n, void* stream);
 HOLE_API int hole_add_rows(hole_ctx* ctx, float* table, const int64_t* ids, int64_t id_offset,
                   const float* rows, int64_t n, void* stream);
 

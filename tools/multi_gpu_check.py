@@ -10,7 +10,7 @@ import torch.distributed as dist
 
 from graphembeddings_b200 import data as D
 from graphembeddings_b200.engine import HoleEngine
-from graphembeddings_b200.sharded import CudaBackend, RowShardedTrainer
+from graphembeddings_b200.sharded import CudaBackend, RowShardedTrainer, P2PRowShardedTrainer
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -19,7 +19,10 @@ Bl, steps = 2048, 4
 kg = D.synthetic_kg(9, 50000, Bl * world * steps, 5, 256, seed=77, trained_scale=True)
 off, ids = D.build_type_csr(kg.type_of)
 be = CudaBackend(kg.n_relations, kg.dim, Bl, local, kg.type_of, off, ids)
-tr = RowShardedTrainer(kg.n_relations, kg.n_entities, kg.dim, be, dist).load_embeddings(kg.E)
+cls = RowShardedTrainer if os.environ.get("HOLE_SHARDED_NCCL") == "1" else P2PRowShardedTrainer
+tr = cls(kg.n_relations, kg.n_entities, kg.dim, be, dist).load_embeddings(kg.E)
+if rank == 0:
+    print("trainer:", cls.__name__)
 for s in range(steps):
     gb = kg.triples[s * Bl * world:(s + 1) * Bl * world]
     tr.train_step(torch.from_numpy(gb[rank * Bl:(rank + 1) * Bl]), 3, s, 0.2, 0.1)

@@ -29,7 +29,11 @@ def run(tag, noplan=False):
     if rank == 0:
         print(f"{tag:32s} {dt * 1e6:9.1f} us/step  {Bl * world / dt / 1e6:8.1f} M triples/s", flush=True)
 
-run("fast path (plan on side stream)")
+run("NCCL all-to-all path")
+tr2 = S.P2PRowShardedTrainer(kg.n_relations, kg.n_entities, kg.dim, be, dist).load_embeddings(kg.E)
+tr_nccl, tr = tr, tr2
+run("P2P push/pull path")
+tr = tr_nccl
 run("fast path, plan inline", noplan=True)
 del S.CudaBackend.step_delta
 run("generic path")
