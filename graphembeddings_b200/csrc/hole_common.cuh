@@ -97,6 +97,9 @@ struct hole_ctx {
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
 
   hole_rank_ws* rank = nullptr;
+  // multi-GPU step routing (hole_shard_route): sort scratch for 3B entity keys
+  uint32_t* route_buf = nullptr;
+  int64_t route_cap = 0;
 
   // ---- measurement hooks
   bool profile = false;

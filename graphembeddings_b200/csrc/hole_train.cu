@@ -535,18 +535,23 @@ __device__ __forceinline__ void finish_row(Row<V>& d, const Row<V>& y, const flo
     }
   }
   if (uniq) {
-    if (act) {                     // inactive hinge: zero gradient, row unchanged
-      if (delta) {                 // delta mode: erow points into the (pre-zeroed) delta table
+    if (delta) {
+      // delta mode: erow points into the delta table.  Every row a step uses is written
+      // (zeros for an inactive hinge), so the caller only clears the relation block.
+      const float sc = act ? -lr : 0.f;
 #pragma unroll
-        for (int k = 0; k < 4 * V; ++k) { d.re[k] = -lr * d.re[k]; d.im[k] = -lr * d.im[k]; }
-      } else {
-        Row<V> x;
-        row_from_smem<GS, V, FULL>(x, xraw, lane, nvec);
+      for (int k = 0; k < 4 * V; ++k) {
+        d.re[k] = act ? sc * d.re[k] : 0.f;
+        d.im[k] = act ? sc * d.im[k] : 0.f;
+      }
+      row_store<GS, V, FULL>(d, erow, lane, nvec);
+    } else if (act) {              // inactive hinge: zero gradient, row unchanged
+      Row<V> x;
+      row_from_smem<GS, V, FULL>(x, xraw, lane, nvec);
 #pragma unroll
-        for (int k = 0; k < 4 * V; ++k) {
-          d.re[k] = x.re[k] - lr * d.re[k];
-          d.im[k] = x.im[k] - lr * d.im[k];
-        }
+      for (int k = 0; k < 4 * V; ++k) {
+        d.re[k] = x.re[k] - lr * d.re[k];
+        d.im[k] = x.im[k] - lr * d.im[k];
       }
       row_store<GS, V, FULL>(d, erow, lane, nvec);
     }
@@ -912,6 +917,178 @@ hole_gather_rows_kernel(const float* __restrict__ E, const int64_t* __restrict__
   row_store<GS, V>(x, dst + (size_t)k * stride, lane, nvec);
 }
 
+// ---------------------------------------------------------------------------------------
+// Multi-GPU step routing.  The table is row-sharded; a rank's step touches the
+// entity rows {h, t, corrupt entity} of its B triples.  Everything below runs on the device
+// with device-side counts, so that a sharded step never returns to the host:
+//   route : dedup the 3B ids (radix sort + one-block scan), sorted unique list `uniq`,
+//           per-owner cut points, triples re-indexed to step-table rows R + slot
+//   post  : write each owner's slice of `uniq` into THAT owner's inbox (peer memory)
+//   push  : the owner copies the requested rows into the requester's step table (peer memory)
+//   pull  : the owner reads the requester's delta rows (peer memory) and adds them to its shard
+// ---------------------------------------------------------------------------------------
+struct hole_peer_ptrs { void* p[HOLE_MAX_RANKS]; };
+
+__global__ void hole_shard_keys_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ neg,
+                                       int B, uint32_t* __restrict__ keys) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+    keys[i] = (uint32_t)pos[3 * i];
+    keys[B + i] = (uint32_t)pos[3 * i + 1];
+    keys[2 * B + i] = (uint32_t)neg[i];
+  }
+}
+
+// Dedup of the sorted keys in two passes over tiles of RT_TILE entries (coalesced):
+// count: heads per tile;  assign: slot of every entry = (heads up to and including it) - 1,
+// uniq[slot] = id, and the three entity columns of the step-table triples;
+// cuts: cuts[o] = first slot owned by rank o, cuts[world] = U.
+constexpr int RT_THREADS = 256;
+constexpr int RT_ITERS = 8;
+constexpr int RT_TILE = RT_THREADS * RT_ITERS;
+
+__global__ void __launch_bounds__(RT_THREADS)
+hole_shard_count_kernel(const uint32_t* __restrict__ sk, int M, int* __restrict__ tile_heads,
+                        const int32_t* __restrict__ pos, int B, int32_t* __restrict__ pos_w) {
+  __shared__ int wsum[RT_THREADS / 32];
+  const int tid = threadIdx.x;
+  int cnt = 0;
+#pragma unroll
+  for (int u = 0; u < RT_ITERS; ++u) {
+    const int j = blockIdx.x * RT_TILE + u * RT_THREADS + tid;
+    cnt += (j < M) && (j == 0 || sk[j] != sk[j - 1]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((tid & 31) == 0) wsum[tid >> 5] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int q = 0; q < RT_THREADS / 32; ++q) t += wsum[q];
+    tile_heads[blockIdx.x] = t;
+  }
+  for (int i = blockIdx.x * RT_THREADS + tid; i < B; i += gridDim.x * RT_THREADS)
+    pos_w[3 * i + 2] = pos[3 * i + 2];                    // relation column
+}
+
+__global__ void __launch_bounds__(RT_THREADS)
+hole_shard_assign_kernel(const uint32_t* __restrict__ sk, const uint32_t* __restrict__ sp, int M, int B,
+                         int R, const int* __restrict__ tile_heads, int* __restrict__ total,
+                         int32_t* __restrict__ uniq, int32_t* __restrict__ pos_w,
+                         int32_t* __restrict__ neg_w) {
+  __shared__ int wsum[RT_THREADS / 32];
+  __shared__ int base_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (w == 0) {                                   // heads in the tiles before mine
+    int t = 0;
+    for (int q = lane; q < (int)blockIdx.x; q += 32) t += tile_heads[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) base_s = t;
+  }
+  __syncthreads();
+  int base = base_s;
+#pragma unroll 1
+  for (int u = 0; u < RT_ITERS; ++u) {
+    const int j = blockIdx.x * RT_TILE + u * RT_THREADS + tid;
+    const bool ok = j < M;
+    const uint32_t key = ok ? sk[j] : 0u;
+    const bool head = ok && (j == 0 || key != sk[j - 1]);
+    const unsigned bal = __ballot_sync(0xffffffffu, head);
+    const int incl = __popc(bal & (0xffffffffu >> (31 - lane)));   // heads in my warp up to me
+    __syncthreads();                              // wsum of the previous iteration is consumed
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int q = 0; q < RT_THREADS / 32; ++q) {
+      const int c = wsum[q];
+      before += (q < w) ? c : 0;
+      all += c;
+    }
+    if (ok) {
+      const int slot = base + before + incl - 1;
+      if (head) uniq[slot] = (int32_t)key;
+      const int p = (int)sp[j], loc = R + slot;
+      if (p < B) pos_w[3 * p] = loc;
+      else if (p < 2 * B) pos_w[3 * (p - B) + 1] = loc;
+      else neg_w[p - 2 * B] = loc;
+    }
+    base += all;
+  }
+  if (blockIdx.x == gridDim.x - 1 && tid == 0) *total = base;
+}
+
+__global__ void hole_shard_cuts_kernel(const int32_t* __restrict__ uniq, const int* __restrict__ total,
+                                       int R, int64_t rows_per, int world, int32_t* __restrict__ cuts) {
+  const int tid = threadIdx.x;
+  if (tid > world) return;
+  const int U = *total;
+  const int64_t bound = (int64_t)R + rows_per * tid;     // first row of rank `tid`
+  int a = 0, b = U;
+  while (a < b) {
+    const int mid = (a + b) >> 1;
+    if ((int64_t)uniq[mid] < bound) a = mid + 1; else b = mid;
+  }
+  cuts[tid] = (tid == world) ? U : a;
+}
+
+__global__ void hole_shard_post_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict__ cuts,
+                                       int world, int me, int64_t cap, hole_peer_ptrs inbox,
+                                       hole_peer_ptrs meta) {
+  const int U = cuts[world];
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = gtid; j < U; j += gridDim.x * blockDim.x) {
+    int o = 0;
+    while (j >= cuts[o + 1]) ++o;
+    static_cast<int32_t*>(inbox.p[o])[(size_t)me * cap + (j - cuts[o])] = uniq[j];
+  }
+  if (gtid < world) {
+    int32_t* m = static_cast<int32_t*>(meta.p[gtid]);
+    m[2 * me] = cuts[gtid + 1] - cuts[gtid];     // how many rows I want from rank gtid
+    m[2 * me + 1] = cuts[gtid];                  // where they sit in my step table (after R)
+  }
+}
+
+// grid.y = requester k: tables.p[k][row_base + off_k + g] = shard[inbox[k][g] + id_offset]
+template <int GS, int V>
+__global__ void __launch_bounds__(256)
+hole_shard_push_kernel(const float* __restrict__ shard, int64_t id_offset, const int32_t* __restrict__ inbox,
+                       const int32_t* __restrict__ meta, int64_t cap, int64_t row_base,
+                       hole_peer_ptrs tables, int nvec, int stride) {
+  const int k = blockIdx.y, lane = threadIdx.x % GS;
+  const int n = meta[2 * k], off = meta[2 * k + 1];
+  float* dst = static_cast<float*>(tables.p[k]) + (size_t)(row_base + off) * stride;
+  const int32_t* ids = inbox + (size_t)k * cap;
+  const int gstride = (gridDim.x * blockDim.x) / GS;
+  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) / GS; g < n; g += gstride) {
+    Row<V> x;
+    row_load<GS, V, false>(x, shard + (size_t)(ids[g] + id_offset) * stride, lane, nvec);
+    row_store<GS, V>(x, dst + (size_t)g * stride, lane, nvec);
+  }
+}
+
+// one requester k per launch (launched in rank order: a row several ranks touched gets its
+// deltas in a fixed order): shard[inbox[k][g] + id_offset] += deltas_k[row_base + off_k + g]
+template <int GS, int V>
+__global__ void __launch_bounds__(256)
+hole_shard_pull_kernel(float* __restrict__ shard, int64_t id_offset, const int32_t* __restrict__ inbox,
+                       const int32_t* __restrict__ meta, int k, int64_t cap, int64_t row_base,
+                       const float* __restrict__ deltas_k, int nvec, int stride) {
+  const int lane = threadIdx.x % GS;
+  const int n = meta[2 * k], off = meta[2 * k + 1];
+  const float* src = deltas_k + (size_t)(row_base + off) * stride;
+  const int32_t* ids = inbox + (size_t)k * cap;
+  const int gstride = (gridDim.x * blockDim.x) / GS;
+  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) / GS; g < n; g += gstride) {
+    float* erow = shard + (size_t)(ids[g] + id_offset) * stride;
+    Row<V> x, d;
+    row_load<GS, V, false>(x, erow, lane, nvec);
+    row_load<GS, V, false>(d, src + (size_t)g * stride, lane, nvec);
+    row_add(x, d);
+    row_store<GS, V>(x, erow, lane, nvec);
+  }
+}
+
 // deterministic per-step loss sum: one CTA per step, fixed-shape tree
 __global__ void __launch_bounds__(256)
 hole_loss_sum_kernel(const float* __restrict__ loss, int64_t B, float* __restrict__ out) {
@@ -1082,6 +1259,7 @@ extern "C" int hole_ctx_destroy(hole_ctx* c) {
   cudaDeviceSynchronize();
   ws_free(c);
   hole_rank_ws_free(c);
+  cudaFree(c->route_buf);
   cudaFree(c->triples_stage[0]); cudaFree(c->triples_stage[1]);
   if (c->loss_sum_pinned) cudaFreeHost(c->loss_sum_pinned);
   for (int k = 0; k < 2; ++k) {
@@ -1199,7 +1377,7 @@ extern "C" int hole_score(hole_ctx* c, const float* table, const int32_t* triple
 // Stable LSD radix sort of S independent arrays of M (key, value = original index) pairs.
 // Keys start in kA (destroyed); kB, vA, vB are scratch; the last pass writes the values to
 // v_final when given.  Returns where the sorted keys / values ended up.
-static int radix_sort(hole_plan& pl, uint32_t* kA, uint32_t* kB, uint32_t* vA, uint32_t* vB,
+static int radix_sort(uint32_t* ghist, uint32_t* kA, uint32_t* kB, uint32_t* vA, uint32_t* vB,
                       uint32_t* v_final, int64_t S, int M, int passes, cudaStream_t st,
                       uint32_t** k_out, uint32_t** v_out) {
   const int P = (M + ST_TILE - 1) / ST_TILE;
@@ -1207,11 +1385,11 @@ static int radix_sort(hole_plan& pl, uint32_t* kA, uint32_t* kB, uint32_t* vA, u
   dim3 grid((unsigned)P, (unsigned)S);
   for (int pass = 0; pass < passes; ++pass) {
     if (pass == passes - 1 && v_final != nullptr) vout = v_final;
-    hole_sort_hist_kernel<<<grid, ST_THREADS, 0, st>>>(kin, pl.ghist, M, P, 8 * pass);
+    hole_sort_hist_kernel<<<grid, ST_THREADS, 0, st>>>(kin, ghist, M, P, 8 * pass);
     HOLE_LAUNCHED();
-    hole_sort_scan_kernel<<<(unsigned)S, 256, 0, st>>>(pl.ghist, P);
+    hole_sort_scan_kernel<<<(unsigned)S, 256, 0, st>>>(ghist, P);
     HOLE_LAUNCHED();
-    hole_sort_scatter_kernel<<<grid, ST_THREADS, 0, st>>>(kin, vin, kout, vout, pl.ghist, M, P, 8 * pass);
+    hole_sort_scatter_kernel<<<grid, ST_THREADS, 0, st>>>(kin, vin, kout, vout, ghist, M, P, 8 * pass);
     HOLE_LAUNCHED();
     uint32_t* nk = (kout == kB) ? kA : kB;
     uint32_t* nv = (vout == vB) ? vA : vB;
@@ -1241,7 +1419,7 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
   hole_rel_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, pl.keysA);
   HOLE_LAUNCHED();
   uint32_t *ko, *vo;
-  int rc = radix_sort(pl, pl.keysA, pl.keysB, pl.valsA, pl.valsB, reinterpret_cast<uint32_t*>(pl.perm),
+  int rc = radix_sort(pl.ghist, pl.keysA, pl.keysB, pl.valsA, pl.valsB, reinterpret_cast<uint32_t*>(pl.perm),
                       S, (int)B, c->rel_passes, ps, &ko, &vo);
   if (rc) return rc;
   // 2. corruption + the 4B row keys of every step
@@ -1250,7 +1428,7 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
                                               seed, first_step, neg_in, pl.neg, pl.keysA);
   HOLE_LAUNCHED();
   // 3. sort by row, 4. segments
-  rc = radix_sort(pl, pl.keysA, pl.keysB, pl.valsA, pl.valsB, nullptr, S, M, c->row_passes, ps,
+  rc = radix_sort(pl.ghist, pl.keysA, pl.keysB, pl.valsA, pl.valsB, nullptr, S, M, c->row_passes, ps,
                   &pl.skey, &pl.spos);
   if (rc) return rc;
   pl.heads_cap = M / 2 + 1;
@@ -1415,6 +1593,113 @@ extern "C" int hole_add_rows(hole_ctx* c, float* table, const int64_t* ids, int6
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   HOLE_DISPATCH(c, hole_add_rows_kernel, grid_for_groups(n, c->gs), 256, (cudaStream_t)stream, table, ids,
                 rows, n, id_offset, c->nvec, c->row_stride);
+  return HOLE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU step routing: host side (see the kernels above)
+// ---------------------------------------------------------------------------------------
+static int route_reserve(hole_ctx* c, int64_t M) {
+  if (M <= c->route_cap) return HOLE_OK;
+  HOLE_CUDA_TRY(cudaDeviceSynchronize());
+  cudaFree(c->route_buf);
+  c->route_buf = nullptr;
+  c->route_cap = 0;
+  const size_t tiles = (M + ST_TILE - 1) / ST_TILE;
+  if (cudaMalloc((void**)&c->route_buf, (4 * (size_t)M + 256 * tiles) * 4) != cudaSuccess) {
+    cudaGetLastError();
+    return hole_set_error(HOLE_ERR_ALLOC, "route workspace allocation failed");
+  }
+  c->route_cap = M;
+  return HOLE_OK;
+}
+
+extern "C" int hole_shard_route(hole_ctx* c, const int32_t* pos, const int32_t* neg_ent, int64_t B,
+                                int64_t n_relations, int64_t n_rows_global, int64_t rows_per_rank,
+                                int world, int32_t* uniq_out, int32_t* cuts_out, int32_t* pos_w,
+                                int32_t* neg_w, void* stream) {
+  HOLE_CHECK_ARG(c && pos && neg_ent && uniq_out && cuts_out && pos_w && neg_w);
+  HOLE_CHECK_ARG(B > 0 && 3 * B < (int64_t(1) << 31) && world >= 1 && world <= HOLE_MAX_RANKS);
+  HOLE_CHECK_ARG(n_relations >= 0 && rows_per_rank > 0 && n_rows_global > n_relations &&
+                 n_rows_global <= (int64_t(1) << 31));
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  const int M = (int)(3 * B);
+  int rc = route_reserve(c, M);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t *kA = c->route_buf, *kB = kA + M, *vA = kB + M, *vB = vA + M, *ghist = vB + M;
+  int passes = 1;
+  while (passes < 4 && (n_rows_global - 1) >> (8 * passes)) ++passes;
+  hole_shard_keys_kernel<<<(unsigned)std::min<int64_t>((B + 255) / 256, 1024), 256, 0, st>>>(pos, neg_ent, (int)B, kA);
+  HOLE_LAUNCHED();
+  uint32_t *sk, *sp;
+  rc = radix_sort(ghist, kA, kB, vA, vB, nullptr, 1, M, passes, st, &sk, &sp);
+  if (rc) return rc;
+  // the sort's tile histogram is free again: tile head counts + the total live there
+  const int tiles = (M + RT_TILE - 1) / RT_TILE;
+  int* tile_heads = reinterpret_cast<int*>(ghist);
+  int* total = tile_heads + tiles;
+  hole_shard_count_kernel<<<tiles, RT_THREADS, 0, st>>>(sk, M, tile_heads, pos, (int)B, pos_w);
+  HOLE_LAUNCHED();
+  hole_shard_assign_kernel<<<tiles, RT_THREADS, 0, st>>>(sk, sp, M, (int)B, (int)n_relations, tile_heads, total,
+                                                        uniq_out, pos_w, neg_w);
+  HOLE_LAUNCHED();
+  hole_shard_cuts_kernel<<<1, 32, 0, st>>>(uniq_out, total, (int)n_relations, rows_per_rank, world, cuts_out);
+  HOLE_LAUNCHED();
+  return HOLE_OK;
+}
+
+static int peer_ptrs(hole_peer_ptrs& out, void* const* in, int world) {
+  for (int k = 0; k < HOLE_MAX_RANKS; ++k) out.p[k] = nullptr;
+  for (int k = 0; k < world; ++k) {
+    if (in[k] == nullptr) return hole_set_error(HOLE_ERR_ARG, "peer pointer %d is null", k);
+    out.p[k] = in[k];
+  }
+  return HOLE_OK;
+}
+
+extern "C" int hole_shard_post(hole_ctx* c, const int32_t* uniq, const int32_t* cuts, int world, int me,
+                               int64_t cap, void* const* peer_inbox, void* const* peer_meta, void* stream) {
+  HOLE_CHECK_ARG(c && uniq && cuts && peer_inbox && peer_meta);
+  HOLE_CHECK_ARG(world >= 1 && world <= HOLE_MAX_RANKS && me >= 0 && me < world && cap > 0);
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  hole_peer_ptrs ib, mt;
+  int rc = peer_ptrs(ib, peer_inbox, world);
+  if (rc) return rc;
+  rc = peer_ptrs(mt, peer_meta, world);
+  if (rc) return rc;
+  hole_shard_post_kernel<<<(unsigned)std::min<int64_t>((cap + 255) / 256, c->sm_count * 4), 256, 0,
+                           (cudaStream_t)stream>>>(uniq, cuts, world, me, cap, ib, mt);
+  HOLE_LAUNCHED();
+  return HOLE_OK;
+}
+
+extern "C" int hole_shard_push(hole_ctx* c, const float* shard, int64_t id_offset, const int32_t* inbox,
+                               const int32_t* meta, int world, int64_t cap, int64_t row_base,
+                               void* const* peer_tables, void* stream) {
+  HOLE_CHECK_ARG(c && shard && inbox && meta && peer_tables);
+  HOLE_CHECK_ARG(world >= 1 && world <= HOLE_MAX_RANKS && cap > 0 && row_base >= 0);
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  hole_peer_ptrs tb;
+  int rc = peer_ptrs(tb, peer_tables, world);
+  if (rc) return rc;
+  const dim3 grid((unsigned)std::max(1, c->sm_count * 8 / world), (unsigned)world);
+  HOLE_DISPATCH(c, hole_shard_push_kernel, grid, 256, (cudaStream_t)stream, shard, id_offset, inbox, meta, cap,
+                row_base, tb, c->nvec, c->row_stride);
+  return HOLE_OK;
+}
+
+extern "C" int hole_shard_pull(hole_ctx* c, float* shard, int64_t id_offset, const int32_t* inbox,
+                               const int32_t* meta, int world, int64_t cap, int64_t row_base,
+                               void* const* peer_deltas, void* stream) {
+  HOLE_CHECK_ARG(c && shard && inbox && meta && peer_deltas);
+  HOLE_CHECK_ARG(world >= 1 && world <= HOLE_MAX_RANKS && cap > 0 && row_base >= 0);
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  for (int k = 0; k < world; ++k) {
+    HOLE_CHECK_ARG(peer_deltas[k] != nullptr);
+    HOLE_DISPATCH(c, hole_shard_pull_kernel, (unsigned)c->sm_count * 8, 256, (cudaStream_t)stream, shard, id_offset,
+                  inbox, meta, k, cap, row_base, static_cast<const float*>(peer_deltas[k]), c->nvec, c->row_stride);
+  }
   return HOLE_OK;
 }
 

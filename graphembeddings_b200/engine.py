@@ -144,13 +144,39 @@ class HoleEngine:
 
     def train_step_delta(self, pos_i32, neg_i32, side, margin, lr, delta_out):
         """One step that leaves the table untouched and writes every row's change into
-        delta_out [n_rows, row_stride] (zeroed by the caller).  pos/neg: int32 CUDA tensors."""
+        delta_out [n_rows, row_stride].  Every row the step uses is written; rows it does not
+        use (relations absent from the batch) keep their content, so the caller clears the
+        relation block.  pos/neg: int32 CUDA tensors."""
         B = pos_i32.shape[0]
         loss = torch.empty(B, dtype=torch.float32, device=self.device)
         check(self.lib.hole_train_step_ex(self._ctx, _ptr(self.table), _ptr(delta_out), _ptr(pos_i32),
                                           _ptr(neg_i32), int(side), B, float(margin), float(lr),
                                           _ptr(loss), None, _stream()))
         return loss
+
+    # ---- multi-GPU step routing (include/hole_b200.h, "multi-GPU step routing") ----
+    @staticmethod
+    def peer_array(tensors):
+        """ctypes void*[world] of the tensors' device addresses (keep the tensors alive)."""
+        return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    def shard_route(self, pos_i32, neg_i32, n_relations, n_rows_global, rows_per_rank, world,
+                    uniq, cuts, pos_w, neg_w):
+        check(self.lib.hole_shard_route(self._ctx, _ptr(pos_i32), _ptr(neg_i32), pos_i32.shape[0],
+                                        int(n_relations), int(n_rows_global), int(rows_per_rank), int(world),
+                                        _ptr(uniq), _ptr(cuts), _ptr(pos_w), _ptr(neg_w), _stream()))
+
+    def shard_post(self, uniq, cuts, world, me, cap, peer_inbox, peer_meta):
+        check(self.lib.hole_shard_post(self._ctx, _ptr(uniq), _ptr(cuts), int(world), int(me), int(cap),
+                                       peer_inbox, peer_meta, _stream()))
+
+    def shard_push(self, shard, id_offset, inbox, meta, world, cap, row_base, peer_tables):
+        check(self.lib.hole_shard_push(self._ctx, _ptr(shard), int(id_offset), _ptr(inbox), _ptr(meta),
+                                       int(world), int(cap), int(row_base), peer_tables, _stream()))
+
+    def shard_pull(self, shard, id_offset, inbox, meta, world, cap, row_base, peer_deltas):
+        check(self.lib.hole_shard_pull(self._ctx, _ptr(shard), int(id_offset), _ptr(inbox), _ptr(meta),
+                                       int(world), int(cap), int(row_base), peer_deltas, _stream()))
 
     def enable_peer_access(self, peer_device):
         check(self.lib.hole_enable_peer_access(self._ctx, int(peer_device)))

@@ -28,10 +28,12 @@ import torch
 
 
 TIMING = None      # set to a dict to collect a per-section breakdown (tools/sharded_breakdown.py)
+EVENTS = None      # set to a list to collect (name, start, end) CUDA events without synchronising
 
 
 class _Section:
-    """Synchronising section timer, active only when sharded.TIMING is a dict."""
+    """Section timer: synchronising wall-clock when sharded.TIMING is a dict, stream events
+    (no synchronisation, the GPU timeline as it runs) when sharded.EVENTS is a list."""
 
     def __init__(self, name):
         self.name = name
@@ -40,11 +42,18 @@ class _Section:
         if TIMING is not None:
             torch.cuda.synchronize()
             self.t0 = time.perf_counter()
+        elif EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
 
     def __exit__(self, *a):
         if TIMING is not None:
             torch.cuda.synchronize()
             TIMING[self.name] = TIMING.get(self.name, 0.0) + (time.perf_counter() - self.t0) * 1e3
+        elif EVENTS is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            EVENTS.append((self.name, self.e0, e1))
 
 
 def row_partition(n_entities, world):
@@ -283,36 +292,59 @@ class RowShardedTrainer:
 
 
 class P2PRowShardedTrainer(RowShardedTrainer):
-    """Same protocol with the two bulk exchanges done by our own kernels over NVLink peer
-    memory instead of NCCL all-to-alls: every rank maps the step table W and the delta table D
-    of every other rank (CUDA IPC); the OWNER of a row pushes it straight into the requester's
-    W (`hole_gather_rows` with a peer destination) and later pulls the requester's delta row out
-    of its D and adds it to the shard in one pass (`hole_add_rows` with a peer source).  NCCL
-    only carries the row ids, the counts, the relation all-reduce and two tiny all-reduces
-    per step that act as stream-ordered barriers."""
+    """The same protocol with every exchange done by our own kernels over NVLink peer memory,
+    and no host synchronisation inside a step.  Each rank maps (CUDA IPC) every other rank's
+    step table W, delta table D and request inbox.  Per step, on the compute stream:
+
+      corrupt -> route (dedup 3B ids, per-owner cuts, triples re-indexed to W rows; device counts)
+      post    : my request lists go straight into the owners' inboxes             (peer stores)
+      -- barrier --
+      push    : as an owner, copy the requested rows into the requesters' W       (peer stores)
+      -- barrier --        (the plan of the step is built on a side stream meanwhile)
+      K1 + K3 in delta mode on W -> D;  all-reduce of the replicated relation block of D
+      (that all-reduce is also the barrier "every D is complete")
+      pull    : as an owner, read the requesters' D rows and add them to my shard (peer loads),
+                requester by requester in rank order -> deterministic
+
+    NCCL carries only the tiny barriers and the relation all-reduce.  Inboxes are double
+    buffered by step parity (a fast rank may post step s+1 while a slow owner still pulls
+    step s); W and D are protected by the barriers."""
 
     def __init__(self, n_relations, n_entities, dim, backend, dist):
         super().__init__(n_relations, n_entities, dim, backend, dist)
         from torch.multiprocessing.reductions import reduce_tensor
-        me = (reduce_tensor(backend.W), reduce_tensor(backend.D), backend.device.index)
-        everyone = [None] * self.world
-        dist.all_gather_object(everyone, me)
-        self.peer_W, self.peer_D = [], []
-        for k, (hw, hd, dev_k) in enumerate(everyone):
+        dev, G = backend.device, self.world
+        self.cap = (backend.W.shape[0] - self.R)                    # 3 * max_batch rows
+        self.inbox = torch.zeros((2, G, self.cap), dtype=torch.int32, device=dev)
+        self.meta = torch.zeros((2, G, 2), dtype=torch.int32, device=dev)
+        mine = [backend.W, backend.D, self.inbox, self.meta]
+        everyone = [None] * G
+        dist.all_gather_object(everyone, ([reduce_tensor(t) for t in mine], dev.index))
+        peers = []
+        for k, (handles, dev_k) in enumerate(everyone):
             if k == self.my_rank:
-                self.peer_W.append(backend.W)
-                self.peer_D.append(backend.D)
-            else:
-                # Open the peer's allocation in MY device's address space (argument 6 of torch's
-                # rebuild is the device the IPC handle is opened on): the tensor then reads as
-                # local to torch while its pages live on GPU k -- kernels launched on my device
-                # reach it over NVLink.  Opened on device k instead, our kernels fault on it
-                # (tools/p2p_diag.py, variant A).
-                backend.eng.enable_peer_access(dev_k)
-                mine = backend.device.index
-                self.peer_W.append(hw[0](*(list(hw[1][:6]) + [mine] + list(hw[1][7:]))))
-                self.peer_D.append(hd[0](*(list(hd[1][:6]) + [mine] + list(hd[1][7:]))))
-        self._flag = torch.zeros(1, dtype=torch.float32, device=backend.device)
+                peers.append(mine)
+                continue
+            # Open the peer's allocation in MY device's address space (argument 6 of torch's
+            # rebuild is the device the IPC handle is opened on): the tensor then reads as
+            # local to torch while its pages live on GPU k -- kernels launched on my device
+            # reach it over NVLink.  Opened on device k instead, our kernels fault on it
+            # (tools/p2p_diag.py, variant A).
+            backend.eng.enable_peer_access(dev_k)
+            peers.append([fn(*(list(a[:6]) + [dev.index] + list(a[7:]))) for fn, a in handles])
+        self._peers = peers                                         # keeps the mappings alive
+        pa = backend.eng.peer_array
+        self.peer_W = pa([p[0] for p in peers])
+        self.peer_D = pa([p[1] for p in peers])
+        self.peer_inbox = [pa([p[2][b] for p in peers]) for b in range(2)]
+        self.peer_meta = [pa([p[3][b] for p in peers]) for b in range(2)]
+        B3 = self.cap
+        self.uniq = torch.zeros(B3, dtype=torch.int32, device=dev)
+        self.cuts = torch.zeros(G + 1, dtype=torch.int32, device=dev)
+        self.pos_w = torch.zeros((B3 // 3, 3), dtype=torch.int32, device=dev)
+        self.neg_w = torch.zeros(B3 // 3, dtype=torch.int32, device=dev)
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._parity = 0
         torch.cuda.synchronize()
         dist.barrier()
 
@@ -320,59 +352,36 @@ class P2PRowShardedTrainer(RowShardedTrainer):
         self.dist.all_reduce(self._flag)          # stream-ordered, no host synchronisation
 
     def train_step(self, pos_local, seed, step, margin, lr):
-        dev, eng = self.shard.device, self.be.eng
-        pos = torch.as_tensor(pos_local).to(dev).long()
+        dev, eng, be = self.shard.device, self.be.eng, self.be
+        pos = torch.as_tensor(pos_local).to(dev).to(torch.int32).contiguous()
         B, R, G = pos.shape[0], self.R, self.world
+        assert 3 * B <= self.cap
+        par = self._parity
+        self._parity ^= 1
+        inbox, meta = self.inbox[par], self.meta[par]
+        pos_w, neg_w = self.pos_w[:B], self.neg_w[:B]
         with _Section("corrupt"):
-            side, neg = self.be.corrupt(pos.to(torch.int32), seed, step, self.my_rank * B)
-            neg = neg.to(dev)
-        with _Section("unique"):
-            ents = torch.cat([pos[:, 0], pos[:, 1], neg]).to(torch.int32)
-            uniq, inv = torch.unique(ents, return_inverse=True)
-            uniq = uniq.long()
-            U = uniq.shape[0]
-        with _Section("route (counts, host sync)"):
-            bounds = R + self.rows_per * torch.arange(1, G + 1, device=dev)
-            cut = torch.searchsorted(uniq, bounds)
-            send = torch.diff(cut, prepend=torch.zeros(1, dtype=cut.dtype, device=dev))
-            meta = torch.stack([send, cut - send], dim=1).contiguous()     # (count, offset in my list) per owner
-            meta_in = torch.empty_like(meta)
-            self.dist.all_to_all_single(meta_in, meta)                     # per requester: (count, its offset)
-            host = torch.cat([meta, meta_in]).tolist()                     # one host synchronisation
-            send_counts = [int(r[0]) for r in host[:G]]
-            recv_counts = [int(r[0]) for r in host[G:]]
-            recv_offs = [int(r[1]) for r in host[G:]]
-        with _Section("a2a ids"):
-            ids_in = self._a2a(uniq, send_counts, recv_counts)
+            side, neg = eng.corrupt_batch(pos, seed, step, self.my_rank * B)
+        with _Section("route (dedup, cuts, re-index)"):
+            eng.shard_route(pos, neg, R, R + self.n_ent, self.rows_per, G, self.uniq, self.cuts, pos_w, neg_w)
         with _Section("plan (side stream)"):
-            pos_w = torch.stack([R + inv[:B], R + inv[B:2 * B], pos[:, 2]], dim=1).to(torch.int32)
-            neg_w = (R + inv[2 * B:]).to(torch.int32)
-            self.be.plan(pos_w, neg_w)
-        with _Section("push rows to peers"):
-            off = 0
-            for k in range(G):
-                n_k = recv_counts[k]
-                if n_k:
-                    dst = self.peer_W[k][R + recv_offs[k]: R + recv_offs[k] + n_k]
-                    eng.gather_rows(self.shard, ids_in[off:off + n_k], R - self.begin, dst)
-                off += n_k
-            self._barrier()                        # every rank's W is complete (and last step's pulls are done)
+            be.plan(pos_w, neg_w)                  # overlaps the exchange below
+        with _Section("post requests to owners"):
+            eng.shard_post(self.uniq, self.cuts, G, self.my_rank, self.cap, self.peer_inbox[par], self.peer_meta[par])
+            self._barrier()                        # every inbox is complete
+        with _Section("push rows to requesters"):
+            eng.shard_push(self.shard, R - self.begin, inbox, meta, G, self.cap, R, self.peer_W)
+            be.W[:R].copy_(self.shard[:R])
+            be.D[:R].zero_()
+            self._barrier()                        # every W is complete
         with _Section("local step (K1+K3, delta mode)"):
-            self.be.W[:R].copy_(self.shard[:R])
-            loss = self.be.step_delta(R + U, pos_w, neg_w, side, margin, lr)
+            loss = eng.train_step_delta(pos_w, neg_w, side, margin, lr, be.D)
         with _Section("allreduce relations"):
-            d_rel = self.be.D[:R].contiguous()
-            self.dist.all_reduce(d_rel)
+            d_rel = be.D[:R].clone()
+            self.dist.all_reduce(d_rel)            # also the barrier "every D is complete"
             self.shard[:R] += d_rel
-            self._barrier()                        # every rank's D is complete
-        with _Section("pull deltas from peers"):
-            off = 0
-            for k in range(G):                     # rank order: deterministic
-                n_k = recv_counts[k]
-                if n_k:
-                    src = self.peer_D[k][R + recv_offs[k]: R + recv_offs[k] + n_k]
-                    eng.add_rows(self.shard, ids_in[off:off + n_k], R - self.begin, src)
-                off += n_k
+        with _Section("pull deltas from requesters"):
+            eng.shard_pull(self.shard, R - self.begin, inbox, meta, G, self.cap, R, self.peer_D)
         return loss
 
 

@@ -131,6 +131,36 @@ HOLE_API int hole_train_step_ex(hole_ctx* ctx, float* table, float* delta_out, c
                        float* loss_out, float* sigma_out, void* stream);
 HOLE_API int hole_train_step_plan(hole_ctx* ctx, const int32_t* pos, const int32_t* neg_ent, int64_t B,
                          void* stream);
+/* ---- multi-GPU step routing over NVLink peer memory (no counterpart in the reference;
+ * SURVEY.md 8e).  All counts stay on the device: a sharded step never synchronises the host.
+ * Buffers marked PEER may live on another GPU (mapped with CUDA IPC after
+ * hole_enable_peer_access).  world <= HOLE_MAX_RANKS.
+ *
+ * hole_shard_route: dedup the 3B entity rows {head, tail, corrupt entity} of this rank's B
+ *   triples (global row ids).  uniq_out[0..U) ascending, cuts_out[o] = first slot owned by rank
+ *   o (rank o owns rows [n_relations + o*rows_per_rank, +rows_per_rank)), cuts_out[world] = U;
+ *   pos_w / neg_w = the triples re-indexed to step-table rows n_relations + slot (relation
+ *   column copied).  uniq_out needs 3B entries, cuts_out world+1.
+ * hole_shard_post: writes uniq[cuts[o]..cuts[o+1]) to rank o's inbox (PEER int32 [world][cap],
+ *   row `me`) and (count, cuts[o]) to rank o's meta (PEER int32 [world][2], row `me`).
+ * hole_shard_push: for every requester k, copies shard[inbox[k][g] + id_offset] to
+ *   peer_tables[k] (PEER step table) row row_base + meta[k][1] + g, g < meta[k][0].
+ * hole_shard_pull: for k = 0..world-1 in order, shard[inbox[k][g] + id_offset] +=
+ *   peer_deltas[k] (PEER delta table) row row_base + meta[k][1] + g. */
+#define HOLE_MAX_RANKS 16
+HOLE_API int hole_shard_route(hole_ctx* ctx, const int32_t* pos, const int32_t* neg_ent, int64_t B,
+                              int64_t n_relations, int64_t n_rows_global, int64_t rows_per_rank, int world,
+                              int32_t* uniq_out, int32_t* cuts_out, int32_t* pos_w, int32_t* neg_w,
+                              void* stream);
+HOLE_API int hole_shard_post(hole_ctx* ctx, const int32_t* uniq, const int32_t* cuts, int world, int me,
+                             int64_t cap, void* const* peer_inbox, void* const* peer_meta, void* stream);
+HOLE_API int hole_shard_push(hole_ctx* ctx, const float* shard, int64_t id_offset, const int32_t* inbox,
+                             const int32_t* meta, int world, int64_t cap, int64_t row_base,
+                             void* const* peer_tables, void* stream);
+HOLE_API int hole_shard_pull(hole_ctx* ctx, float* shard, int64_t id_offset, const int32_t* inbox,
+                             const int32_t* meta, int world, int64_t cap, int64_t row_base,
+                             void* const* peer_deltas, void* stream);
+
 /* Enable loads/stores from ctx's device to memory of `peer_device` (no-op if already on). */
 HOLE_API int hole_enable_peer_access(hole_ctx* ctx, int peer_device);
 HOLE_API int hole_gather_rows(hole_ctx* ctx, const float* table, const int64_t* ids, int64_t id_offset,

@@ -234,6 +234,94 @@ def test_sharded_trainer_single_rank_matches_engine(eng_mod):
     assert np.abs(want - kg.E).max() > 1e-4
 
 
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_shard_route_post_push_pull_virtual_ranks(eng_mod, world):
+    """The multi-GPU exchange primitives with `world` virtual ranks on one GPU (peer buffers
+    are local tensors): route == np.unique / searchsorted, push delivers exactly the
+    requested rows, pull adds the delta rows in rank order (bit-exact vs a float32 loop)."""
+    from graphembeddings_b200.sharded import row_partition
+    rng = np.random.default_rng(100 + world)
+    dim, R, n_ent, B = 150, 5, 1000, 257
+    e = eng_mod.HoleEngine(R + n_ent, dim)
+    stride, cap = e.row_stride, 3 * B
+    rows_per = row_partition(n_ent, world)
+    table = rng.standard_normal((R + n_ent, stride)).astype(np.float32)
+    dev = e.device
+    shards, begins = [], []
+    for o in range(world):
+        b0 = R + o * rows_per
+        b1 = min(R + n_ent, b0 + rows_per)
+        shards.append(torch.from_numpy(np.concatenate([table[:R], table[b0:b1]])).to(dev))
+        begins.append(b0)
+    inbox = [torch.zeros((world, cap), dtype=torch.int32, device=dev) for _ in range(world)]
+    meta = [torch.zeros((world, 2), dtype=torch.int32, device=dev) for _ in range(world)]
+    W = [torch.zeros((R + cap, stride), dtype=torch.float32, device=dev) for _ in range(world)]
+    Dl = [torch.from_numpy(rng.standard_normal((R + cap, stride)).astype(np.float32)).to(dev) for _ in range(world)]
+    pa = e.peer_array
+    uniqs = []
+    for k in range(world):
+        pos = np.stack([R + rng.integers(0, n_ent, B), R + rng.integers(0, n_ent, B), rng.integers(0, R, B)], 1)
+        pos[:5, 1] = pos[:5, 0]                                  # head == tail rows
+        neg = R + rng.integers(0, n_ent, B)
+        pos_t = torch.from_numpy(pos.astype(np.int32)).to(dev)
+        neg_t = torch.from_numpy(neg.astype(np.int32)).to(dev)
+        uniq = torch.full((cap,), -1, dtype=torch.int32, device=dev)
+        cuts = torch.zeros(world + 1, dtype=torch.int32, device=dev)
+        pos_w = torch.zeros((B, 3), dtype=torch.int32, device=dev)
+        neg_w = torch.zeros(B, dtype=torch.int32, device=dev)
+        e.shard_route(pos_t, neg_t, R, R + n_ent, rows_per, world, uniq, cuts, pos_w, neg_w)
+        want = np.unique(np.concatenate([pos[:, 0], pos[:, 1], neg]))
+        U = len(want)
+        cuts_h = cuts.cpu().numpy()
+        assert cuts_h[world] == U and cuts_h[0] == 0
+        uh = uniq.cpu().numpy()
+        assert np.array_equal(uh[:U], want) and (uh[U:] == -1).all()
+        bounds = R + rows_per * np.arange(world + 1)
+        assert np.array_equal(cuts_h[:world], np.searchsorted(want, bounds[:world]))
+        pw, nw = pos_w.cpu().numpy(), neg_w.cpu().numpy()
+        assert np.array_equal(want[pw[:, 0] - R], pos[:, 0]) and np.array_equal(want[pw[:, 1] - R], pos[:, 1])
+        assert np.array_equal(pw[:, 2], pos[:, 2]) and np.array_equal(want[nw - R], neg)
+        e.shard_post(uniq, cuts, world, k, cap, pa(inbox), pa(meta))
+        uniqs.append(want)
+    for o in range(world):
+        e.shard_push(shards[o], R - begins[o], inbox[o], meta[o], world, cap, R, pa(W))
+    for k in range(world):
+        got = W[k].cpu().numpy()
+        assert np.array_equal(got[R:R + len(uniqs[k])], table[uniqs[k]])
+        assert not got[R + len(uniqs[k]):].any()
+    for o in range(world):
+        e.shard_pull(shards[o], R - begins[o], inbox[o], meta[o], world, cap, R, pa(Dl))
+    expect = table.copy()
+    for k in range(world):                                       # rank order, float32 adds
+        expect[uniqs[k]] += Dl[k].cpu().numpy()[R:R + len(uniqs[k])]
+    for o in range(world):
+        n_o = shards[o].shape[0] - R
+        assert np.array_equal(shards[o].cpu().numpy()[R:], expect[begins[o]:begins[o] + n_o])
+
+
+def test_delta_mode_writes_every_used_row(eng_mod):
+    """hole_train_step_ex in delta mode must overwrite (not accumulate into) every row the
+    step uses, zeros included for inactive hinges: the sharded trainer does not clear D."""
+    kg = D.synthetic_kg(6, 3000, 600, 4, 150, seed=43, trained_scale=True)
+    e, _, _ = _engine(eng_mod, kg)
+    pos = torch.from_numpy(kg.triples[:600]).to(e.device)
+    side, neg = e.corrupt_batch(pos, 9, 0)
+    before = e.table.clone()
+    e.train_step_plan(pos, neg)
+    junk = torch.full_like(e.table, 7.0)
+    e.train_step_delta(pos, neg, side, 0.0, 0.1, junk)           # margin 0: about half the hinges inactive
+    e.train_step_plan(pos, neg)
+    clean = torch.zeros_like(e.table)
+    loss = e.train_step_delta(pos, neg, side, 0.0, 0.1, clean)
+    assert torch.equal(e.table, before)
+    used = torch.unique(torch.cat([pos[:, 0], pos[:, 1], pos[:, 2], neg.to(pos.dtype)]).long())
+    assert torch.equal(junk[used], clean[used])
+    assert (loss == 0).any() and (loss > 0).any()
+    mask = torch.ones(e.table.shape[0], dtype=torch.bool, device=e.device)
+    mask[used] = False
+    assert (junk[mask] == 7.0).all()
+
+
 def test_full_size_properties_config1(eng_mod):
     """BASELINE config 1 at full table size (1,200,014 x 256), B = 32768: determinism across
     runs, rows untouched by any step bit-identical, loss sums finite and equal between the

@@ -12,7 +12,7 @@ Bl, steps = 32768, 12
 kg = D.make_config("diffbot_d256", n_triples=Bl * world * steps)
 off, ids = D.build_type_csr(kg.type_of)
 be = S.CudaBackend(kg.n_relations, kg.dim, Bl, local, kg.type_of, off, ids)
-tr = S.RowShardedTrainer(kg.n_relations, kg.n_entities, kg.dim, be, dist).load_embeddings(kg.E)
+tr = (S.RowShardedTrainer if os.environ.get("HOLE_SHARDED_NCCL") == "1" else S.P2PRowShardedTrainer)(kg.n_relations, kg.n_entities, kg.dim, be, dist).load_embeddings(kg.E)
 tri = torch.from_numpy(kg.triples).view(steps, world, Bl, 3)[:, rank].contiguous().cuda()
 S.TIMING = {}
 for s in range(steps):
