@@ -1049,18 +1049,58 @@ __global__ void hole_shard_post_kernel(const int32_t* __restrict__ uniq, const i
   }
 }
 
+// Barrier across the ranks' compute streams through peer flags: thread k stores `epoch` into
+// flag[me] of rank k (release, system scope) and spins until flag[k] of my own array reaches
+// `epoch` (acquire).  Epochs only grow, so there is nothing to reset.  Everything the earlier
+// kernels of my stream wrote to peer memory is visible to a peer's kernels that follow its
+// barrier.  A peer that never arrives trips a 10 s timeout: *err is set and the kernel leaves.
+__global__ void hole_shard_barrier_kernel(int world, int me, int epoch, hole_peer_ptrs flags,
+                                          int* __restrict__ err) {
+  const int k = threadIdx.x;
+  if (k >= world) return;
+  __threadfence_system();
+  int* theirs = static_cast<int*>(flags.p[k]) + me;
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+  const int* mine = static_cast<const int*>(flags.p[me]) + k;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  while (true) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (v - epoch >= 0) break;
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ull) { atomicExch(err, 1); break; }
+  }
+  __threadfence_system();
+}
+
 // grid.y = requester k: tables.p[k][row_base + off_k + g] = shard[inbox[k][g] + id_offset]
 template <int GS, int V>
 __global__ void __launch_bounds__(256)
 hole_shard_push_kernel(const float* __restrict__ shard, int64_t id_offset, const int32_t* __restrict__ inbox,
                        const int32_t* __restrict__ meta, int64_t cap, int64_t row_base,
-                       hole_peer_ptrs tables, int nvec, int stride) {
+                       hole_peer_ptrs tables, float* __restrict__ my_table, float* __restrict__ my_delta,
+                       int nvec, int stride) {
   const int k = blockIdx.y, lane = threadIdx.x % GS;
+  const int gstride = (gridDim.x * blockDim.x) / GS;
+  const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) / GS;
+  if (k == 0 && my_table != nullptr) {
+    // the replicated relation block: my step table takes the current rows, my delta table zeros
+    // (delta mode writes only the relations a step uses)
+    Row<V> z;
+    row_zero(z);
+    for (int g = g0; g < (int)row_base; g += gstride) {
+      Row<V> x;
+      row_load<GS, V, false>(x, shard + (size_t)g * stride, lane, nvec);
+      row_store<GS, V>(x, my_table + (size_t)g * stride, lane, nvec);
+      row_store<GS, V>(z, my_delta + (size_t)g * stride, lane, nvec);
+    }
+  }
   const int n = meta[2 * k], off = meta[2 * k + 1];
   float* dst = static_cast<float*>(tables.p[k]) + (size_t)(row_base + off) * stride;
   const int32_t* ids = inbox + (size_t)k * cap;
-  const int gstride = (gridDim.x * blockDim.x) / GS;
-  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) / GS; g < n; g += gstride) {
+  for (int g = g0; g < n; g += gstride) {
     Row<V> x;
     row_load<GS, V, false>(x, shard + (size_t)(ids[g] + id_offset) * stride, lane, nvec);
     row_store<GS, V>(x, dst + (size_t)g * stride, lane, nvec);
@@ -1676,16 +1716,30 @@ extern "C" int hole_shard_post(hole_ctx* c, const int32_t* uniq, const int32_t* 
 
 extern "C" int hole_shard_push(hole_ctx* c, const float* shard, int64_t id_offset, const int32_t* inbox,
                                const int32_t* meta, int world, int64_t cap, int64_t row_base,
-                               void* const* peer_tables, void* stream) {
+                               void* const* peer_tables, float* my_table, float* my_delta, void* stream) {
   HOLE_CHECK_ARG(c && shard && inbox && meta && peer_tables);
   HOLE_CHECK_ARG(world >= 1 && world <= HOLE_MAX_RANKS && cap > 0 && row_base >= 0);
+  HOLE_CHECK_ARG((my_table == nullptr) == (my_delta == nullptr));
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   hole_peer_ptrs tb;
   int rc = peer_ptrs(tb, peer_tables, world);
   if (rc) return rc;
   const dim3 grid((unsigned)std::max(1, c->sm_count * 8 / world), (unsigned)world);
   HOLE_DISPATCH(c, hole_shard_push_kernel, grid, 256, (cudaStream_t)stream, shard, id_offset, inbox, meta, cap,
-                row_base, tb, c->nvec, c->row_stride);
+                row_base, tb, my_table, my_delta, c->nvec, c->row_stride);
+  return HOLE_OK;
+}
+
+extern "C" int hole_shard_barrier(hole_ctx* c, int world, int me, int32_t epoch, void* const* peer_flags,
+                                  int32_t* err_flag, void* stream) {
+  HOLE_CHECK_ARG(c && peer_flags && err_flag);
+  HOLE_CHECK_ARG(world >= 1 && world <= HOLE_MAX_RANKS && me >= 0 && me < world);
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  hole_peer_ptrs fl;
+  int rc = peer_ptrs(fl, peer_flags, world);
+  if (rc) return rc;
+  hole_shard_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(world, me, epoch, fl, err_flag);
+  HOLE_LAUNCHED();
   return HOLE_OK;
 }
 

@@ -170,9 +170,16 @@ class HoleEngine:
         check(self.lib.hole_shard_post(self._ctx, _ptr(uniq), _ptr(cuts), int(world), int(me), int(cap),
                                        peer_inbox, peer_meta, _stream()))
 
-    def shard_push(self, shard, id_offset, inbox, meta, world, cap, row_base, peer_tables):
+    def shard_push(self, shard, id_offset, inbox, meta, world, cap, row_base, peer_tables,
+                   my_table=None, my_delta=None):
         check(self.lib.hole_shard_push(self._ctx, _ptr(shard), int(id_offset), _ptr(inbox), _ptr(meta),
-                                       int(world), int(cap), int(row_base), peer_tables, _stream()))
+                                       int(world), int(cap), int(row_base), peer_tables,
+                                       None if my_table is None else _ptr(my_table),
+                                       None if my_delta is None else _ptr(my_delta), _stream()))
+
+    def shard_barrier(self, world, me, epoch, peer_flags, err_flag):
+        check(self.lib.hole_shard_barrier(self._ctx, int(world), int(me), int(epoch), peer_flags,
+                                          _ptr(err_flag), _stream()))
 
     def shard_pull(self, shard, id_offset, inbox, meta, world, cap, row_base, peer_deltas):
         check(self.lib.hole_shard_pull(self._ctx, _ptr(shard), int(id_offset), _ptr(inbox), _ptr(meta),

@@ -24,6 +24,8 @@ import os
 import time
 
 import numpy as np
+import collections
+
 import torch
 
 
@@ -171,9 +173,10 @@ class RowShardedTrainer:
         return [int(x) for x in both[0]], [int(x) for x in both[1]]
 
     # ------------------------------------------------------------------ training
-    def train_step(self, pos_local, seed, step, margin, lr):
+    def train_step(self, pos_local, seed, step, margin, lr, next_pos=None):
         """pos_local: this rank's [B,3] slice (global row ids) of the global batch of
-        world*B triples.  Returns the per-triple hinge loss of the slice."""
+        world*B triples.  Returns the per-triple hinge loss of the slice.  (next_pos is used by
+        the peer-memory trainer to work one step ahead; ignored here.)"""
         dev = self.shard.device
         pos = torch.as_tensor(pos_local).to(dev).long()
         B, R = pos.shape[0], self.R
@@ -291,24 +294,32 @@ class RowShardedTrainer:
         return raw, filt
 
 
+class _Prepared:
+    """Table-independent part of one step (corruption, routing, update plan), built ahead."""
+    __slots__ = ("key", "side", "uniq", "cuts", "pos_w", "neg_w", "done")
+
+
 class P2PRowShardedTrainer(RowShardedTrainer):
     """The same protocol with every exchange done by our own kernels over NVLink peer memory,
     and no host synchronisation inside a step.  Each rank maps (CUDA IPC) every other rank's
-    step table W, delta table D and request inbox.  Per step, on the compute stream:
+    step table W, delta table D, request inbox and barrier flags.  Per step:
 
-      corrupt -> route (dedup 3B ids, per-owner cuts, triples re-indexed to W rows; device counts)
-      post    : my request lists go straight into the owners' inboxes             (peer stores)
-      -- barrier --
-      push    : as an owner, copy the requested rows into the requesters' W       (peer stores)
-      -- barrier --        (the plan of the step is built on a side stream meanwhile)
-      K1 + K3 in delta mode on W -> D;  all-reduce of the replicated relation block of D
-      (that all-reduce is also the barrier "every D is complete")
-      pull    : as an owner, read the requesters' D rows and add them to my shard (peer loads),
-                requester by requester in rank order -> deterministic
+      side stream (table-independent, may run one step ahead -- pass `next_pos`):
+        corrupt -> route (dedup 3B ids, per-owner cuts, triples re-indexed to W rows; device
+        counts) -> update plan
+      compute stream:
+        post    : my request lists go straight into the owners' inboxes             (peer stores)
+        -- barrier --
+        push    : as an owner, copy the requested rows into the requesters' W       (peer stores)
+        -- barrier --
+        K1 + K3 in delta mode on W -> D;  all-reduce of the replicated relation block of D
+        (that all-reduce is also the barrier "every D is complete")
+        pull    : as an owner, read the requesters' D rows and add them to my shard (peer loads),
+                  requester by requester in rank order -> deterministic
 
-    NCCL carries only the tiny barriers and the relation all-reduce.  Inboxes are double
-    buffered by step parity (a fast rank may post step s+1 while a slow owner still pulls
-    step s); W and D are protected by the barriers."""
+    NCCL carries only the relation all-reduce; the barriers are a one-warp kernel on peer flags.
+    Inboxes are double buffered by step parity (a fast rank may post step s+1 while a slow
+    owner still pulls step s); W and D are protected by the barriers."""
 
     def __init__(self, n_relations, n_entities, dim, backend, dist):
         super().__init__(n_relations, n_entities, dim, backend, dist)
@@ -317,7 +328,8 @@ class P2PRowShardedTrainer(RowShardedTrainer):
         self.cap = (backend.W.shape[0] - self.R)                    # 3 * max_batch rows
         self.inbox = torch.zeros((2, G, self.cap), dtype=torch.int32, device=dev)
         self.meta = torch.zeros((2, G, 2), dtype=torch.int32, device=dev)
-        mine = [backend.W, backend.D, self.inbox, self.meta]
+        self.flags = torch.zeros(G, dtype=torch.int32, device=dev)
+        mine = [backend.W, backend.D, self.inbox, self.meta, self.flags]
         everyone = [None] * G
         dist.all_gather_object(everyone, ([reduce_tensor(t) for t in mine], dev.index))
         peers = []
@@ -338,44 +350,91 @@ class P2PRowShardedTrainer(RowShardedTrainer):
         self.peer_D = pa([p[1] for p in peers])
         self.peer_inbox = [pa([p[2][b] for p in peers]) for b in range(2)]
         self.peer_meta = [pa([p[3][b] for p in peers]) for b in range(2)]
+        self.peer_flags = pa([p[4] for p in peers])
         B3 = self.cap
-        self.uniq = torch.zeros(B3, dtype=torch.int32, device=dev)
-        self.cuts = torch.zeros(G + 1, dtype=torch.int32, device=dev)
-        self.pos_w = torch.zeros((B3 // 3, 3), dtype=torch.int32, device=dev)
-        self.neg_w = torch.zeros(B3 // 3, dtype=torch.int32, device=dev)
-        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._bufs = [dict(uniq=torch.zeros(B3, dtype=torch.int32, device=dev),
+                           cuts=torch.zeros(G + 1, dtype=torch.int32, device=dev),
+                           pos_w=torch.zeros((B3 // 3, 3), dtype=torch.int32, device=dev),
+                           neg_w=torch.zeros(B3 // 3, dtype=torch.int32, device=dev)) for _ in range(2)]
+        self._n_prepared = 0
+        self._ahead = None
+        self.prep_stream = torch.cuda.Stream(device=dev)
+        self.barrier_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._epoch = 0
         self._parity = 0
+        self.max_run_ahead = int(os.environ.get("HOLE_SHARDED_RUN_AHEAD", "0"))
+        self._inflight = collections.deque()
         torch.cuda.synchronize()
         dist.barrier()
 
     def _barrier(self):
-        self.dist.all_reduce(self._flag)          # stream-ordered, no host synchronisation
+        self._epoch += 1
+        self.be.eng.shard_barrier(self.world, self.my_rank, self._epoch, self.peer_flags, self.barrier_err)
 
-    def train_step(self, pos_local, seed, step, margin, lr):
-        dev, eng, be = self.shard.device, self.be.eng, self.be
-        pos = torch.as_tensor(pos_local).to(dev).to(torch.int32).contiguous()
-        B, R, G = pos.shape[0], self.R, self.world
+    def check_barriers(self):
+        """Raises if a peer ever failed to reach a barrier (host synchronisation)."""
+        if int(self.barrier_err.item()) != 0:
+            raise RuntimeError("a peer did not reach a step barrier within 10 s; the tables are inconsistent")
+
+    def gather_embeddings(self):
+        self.check_barriers()
+        return super().gather_embeddings()
+
+    def _prepare(self, pos_local, seed, step, after):
+        """Enqueue corrupt + route + plan of `step` on the side stream, once `after` (an event
+        of the compute stream that covers pos_local and the last use of the buffer set) is done."""
+        eng, R, G = self.be.eng, self.R, self.world
+        pos = torch.as_tensor(pos_local)
+        B = pos.shape[0]
         assert 3 * B <= self.cap
+        buf = self._bufs[self._n_prepared & 1]
+        self._n_prepared += 1
+        p = _Prepared()
+        p.key = (int(seed), int(step), B)
+        p.uniq, p.cuts, p.pos_w, p.neg_w = buf["uniq"], buf["cuts"], buf["pos_w"][:B], buf["neg_w"][:B]
+        with torch.cuda.stream(self.prep_stream):
+            self.prep_stream.wait_event(after)
+            if pos.is_cuda:
+                pos.record_stream(self.prep_stream)      # the caller may drop it right after this call
+            if pos.device != self.shard.device or pos.dtype != torch.int32 or not pos.is_contiguous():
+                pos = pos.to(self.shard.device, non_blocking=True).to(torch.int32).contiguous()
+            p.side, neg = eng.corrupt_batch(pos, seed, step, self.my_rank * B)
+            eng.shard_route(pos, neg, R, R + self.n_ent, self.rows_per, G, p.uniq, p.cuts, p.pos_w, p.neg_w)
+            p.done = self.prep_stream.record_event()
+            self.be.plan(p.pos_w, p.neg_w)           # the library's plan stream takes over from here
+        return p
+
+    def train_step(self, pos_local, seed, step, margin, lr, next_pos=None):
+        """next_pos: the slice of step + 1, if known -- its corruption, routing and plan are
+        then built on the side stream while this step's exchange and kernels run."""
+        eng, be, R, G = self.be.eng, self.be, self.R, self.world
+        main = torch.cuda.current_stream()
+        if self.max_run_ahead > 0:                 # bound how far the host runs ahead of the GPU
+            if len(self._inflight) >= self.max_run_ahead:
+                self._inflight.popleft().synchronize()
+        entry = main.record_event()
+        if self.max_run_ahead > 0:
+            self._inflight.append(entry)
+        B = int(pos_local.shape[0])
+        p, self._ahead = self._ahead, None
+        if p is None or p.key != (int(seed), int(step), B):
+            with _Section("prepare (corrupt, route, plan)"):
+                p = self._prepare(pos_local, seed, step, entry)
+        main.wait_event(p.done)
         par = self._parity
         self._parity ^= 1
         inbox, meta = self.inbox[par], self.meta[par]
-        pos_w, neg_w = self.pos_w[:B], self.neg_w[:B]
-        with _Section("corrupt"):
-            side, neg = eng.corrupt_batch(pos, seed, step, self.my_rank * B)
-        with _Section("route (dedup, cuts, re-index)"):
-            eng.shard_route(pos, neg, R, R + self.n_ent, self.rows_per, G, self.uniq, self.cuts, pos_w, neg_w)
-        with _Section("plan (side stream)"):
-            be.plan(pos_w, neg_w)                  # overlaps the exchange below
         with _Section("post requests to owners"):
-            eng.shard_post(self.uniq, self.cuts, G, self.my_rank, self.cap, self.peer_inbox[par], self.peer_meta[par])
+            eng.shard_post(p.uniq, p.cuts, G, self.my_rank, self.cap, self.peer_inbox[par], self.peer_meta[par])
             self._barrier()                        # every inbox is complete
         with _Section("push rows to requesters"):
-            eng.shard_push(self.shard, R - self.begin, inbox, meta, G, self.cap, R, self.peer_W)
-            be.W[:R].copy_(self.shard[:R])
-            be.D[:R].zero_()
+            eng.shard_push(self.shard, R - self.begin, inbox, meta, G, self.cap, R, self.peer_W, be.W, be.D)
             self._barrier()                        # every W is complete
         with _Section("local step (K1+K3, delta mode)"):
-            loss = eng.train_step_delta(pos_w, neg_w, side, margin, lr, be.D)
+            loss = eng.train_step_delta(p.pos_w, p.neg_w, p.side, margin, lr, be.D)
+        if next_pos is not None:
+            with _Section("prepare next (side stream)"):
+                self._ahead = self._prepare(next_pos, seed, step + 1, entry)
         with _Section("allreduce relations"):
             d_rel = be.D[:R].clone()
             self.dist.all_reduce(d_rel)            # also the barrier "every D is complete"
@@ -416,32 +475,59 @@ def bench(args, dist, rank, world, local_rank):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         fn()
+        host_ms[0] = (time.perf_counter() - h0) * 1e3      # host time to enqueue the region
         e1.record()
         sync_all()
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    host_ms = [0.0]
+
     # nvidia-smi's start-up (NVML initialisation) disturbs running GPU work for a few hundred
     # ms: start the clock sampler before the warm-up, not inside the timed region
     sampler = B_.ClockSampler(local_rank, period=0.25)
-    if rank == 0:
+    if rank == 0 and os.environ.get("HOLE_NO_SAMPLER") != "1":
         sampler.start()
         time.sleep(1.0)
     for s in range(W):
-        tr.train_step(dev_tri[s], 1, s, B_.MARGIN, float(lrs[s]))
+        tr.train_step(dev_tri[s], 1, s, B_.MARGIN, float(lrs[s]), next_pos=dev_tri[s + 1])
     be.eng.reset_launch_count()
-    ms = timed(lambda: [tr.train_step(dev_tri[W + s], 1, W + s, B_.MARGIN, float(lrs[W + s])) for s in range(K)])
+    stamps = []
+
+    def value_pass():
+        for s in range(K):
+            stamps.append(time.perf_counter())
+            tr.train_step(dev_tri[W + s], 1, W + s, B_.MARGIN, float(lrs[W + s]),
+                          next_pos=dev_tri[W + s + 1] if s + 1 < K else None)
+        stamps.append(time.perf_counter())
+
+    ms = timed(value_pass)
+    if os.environ.get("HOLE_BENCH_TRACE") == "1":
+        gaps = np.diff(np.asarray(stamps)) * 1e6
+        big = np.flatnonzero(gaps > 1000)
+        print(f"[trace rank {rank}] host us/step: median {np.median(gaps):.0f}, mean {gaps.mean():.0f}, "
+              f"max {gaps.max():.0f}; steps > 1 ms: {[(int(i), int(gaps[i])) for i in big[:12]]}", flush=True)
     launches = be.eng.launch_count()
+    host_enqueue_us = host_ms[0] / K * 1e3
+    if hasattr(tr, "check_barriers"):
+        tr.check_barriers()
     value = K * Bl * world / (ms * 1e-3)
 
     losses = []
+    stage = [torch.empty_like(dev_tri[0]) for _ in range(2)]
 
     def e2e_pass():
+        # two device staging slots, filled from pinned host memory one step ahead
+        stage[0].copy_(host_tri[W], non_blocking=True)
         for s in range(K):
-            t = host_tri[W + s].cuda(non_blocking=True)
-            loss = tr.train_step(t, 1, K + W + s, B_.MARGIN, float(lrs[K + W + s]))
+            nxt = None
+            if s + 1 < K:
+                nxt = stage[(s + 1) & 1]
+                nxt.copy_(host_tri[W + s + 1], non_blocking=True)
+            loss = tr.train_step(stage[s & 1], 1, K + W + s, B_.MARGIN, float(lrs[K + W + s]), next_pos=nxt)
             losses.append(float(loss.sum().item()))        # device -> host read of the step's result
 
     ms_e2e = timed(e2e_pass)
@@ -461,14 +547,15 @@ def bench(args, dist, rank, world, local_rank):
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{B_.WORKLOAD}: BASELINE.json configs[1] table row-sharded over {world} GPUs "
-                                   "(relations replicated); rows pushed / deltas pulled by our kernels over NVLink peer "
-                                   "memory, NCCL for ids, counts and barriers" if cls is P2PRowShardedTrainer else
+                                   "(relations replicated); requests posted, rows pushed and deltas pulled by our kernels "
+                                   "over NVLink peer memory; NCCL only for the relation all-reduce" if cls is P2PRowShardedTrainer else
                                    f"{B_.WORKLOAD}: table row-sharded over {world} GPUs, NCCL all-to-all of rows and row deltas",
                        "batch_per_gpu": Bl, "global_batch": Bl * world, "margin": B_.MARGIN, "lr0": B_.LR0,
                        "parallelism": f"rowshard{world}", "l2": "table shard larger than L2; no flush",
+                       "host_enqueue_us_per_step": host_enqueue_us,
                        "mean_loss_last_step": losses[-1] / Bl if losses else None},
             "e2e": {"value": e2e, "unit": "triples/s", "h2d_bytes_per_step": 12 * Bl, "d2h_bytes_per_step": 4,
-                    "call": "RowShardedTrainer.train_step (pinned host triples in, loss sum out), per rank"},
+                    "call": "P2PRowShardedTrainer.train_step (pinned host triples in, loss sum out), per rank"},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": value * alg / 1e9 / world, "peak": peak, "unit": "GB/s",
                          "frac": value * alg / 1e9 / world / peak, "traffic": None, "peak_source": src,

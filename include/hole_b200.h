@@ -144,7 +144,12 @@ HOLE_API int hole_train_step_plan(hole_ctx* ctx, const int32_t* pos, const int32
  * hole_shard_post: writes uniq[cuts[o]..cuts[o+1]) to rank o's inbox (PEER int32 [world][cap],
  *   row `me`) and (count, cuts[o]) to rank o's meta (PEER int32 [world][2], row `me`).
  * hole_shard_push: for every requester k, copies shard[inbox[k][g] + id_offset] to
- *   peer_tables[k] (PEER step table) row row_base + meta[k][1] + g, g < meta[k][0].
+ *   peer_tables[k] (PEER step table) row row_base + meta[k][1] + g, g < meta[k][0].  With
+ *   my_table / my_delta (both or neither) it also refreshes the replicated relation block:
+ *   my_table[0..row_base) = shard[0..row_base), my_delta[0..row_base) = 0.
+ * hole_shard_barrier: barrier across the ranks' streams through peer flags (PEER int32 [world]
+ *   each, zero-initialised); `epoch` must grow by one per call on every rank.  A peer that does
+ *   not arrive within 10 s sets *err_flag (device int32) instead of hanging the GPU.
  * hole_shard_pull: for k = 0..world-1 in order, shard[inbox[k][g] + id_offset] +=
  *   peer_deltas[k] (PEER delta table) row row_base + meta[k][1] + g. */
 #define HOLE_MAX_RANKS 16
@@ -156,7 +161,9 @@ HOLE_API int hole_shard_post(hole_ctx* ctx, const int32_t* uniq, const int32_t* 
                              int64_t cap, void* const* peer_inbox, void* const* peer_meta, void* stream);
 HOLE_API int hole_shard_push(hole_ctx* ctx, const float* shard, int64_t id_offset, const int32_t* inbox,
                              const int32_t* meta, int world, int64_t cap, int64_t row_base,
-                             void* const* peer_tables, void* stream);
+                             void* const* peer_tables, float* my_table, float* my_delta, void* stream);
+HOLE_API int hole_shard_barrier(hole_ctx* ctx, int world, int me, int32_t epoch, void* const* peer_flags,
+                                int32_t* err_flag, void* stream);
 HOLE_API int hole_shard_pull(hole_ctx* ctx, float* shard, int64_t id_offset, const int32_t* inbox,
                              const int32_t* meta, int world, int64_t cap, int64_t row_base,
                              void* const* peer_deltas, void* stream);

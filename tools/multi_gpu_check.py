@@ -15,7 +15,7 @@ from graphembeddings_b200.sharded import CudaBackend, RowShardedTrainer, P2PRowS
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-Bl, steps = 2048, 4
+Bl, steps = 2048, int(os.environ.get("STEPS", 4))
 kg = D.synthetic_kg(9, 50000, Bl * world * steps, 5, 256, seed=77, trained_scale=True)
 off, ids = D.build_type_csr(kg.type_of)
 be = CudaBackend(kg.n_relations, kg.dim, Bl, local, kg.type_of, off, ids)
@@ -23,9 +23,15 @@ cls = RowShardedTrainer if os.environ.get("HOLE_SHARDED_NCCL") == "1" else P2PRo
 tr = cls(kg.n_relations, kg.n_entities, kg.dim, be, dist).load_embeddings(kg.E)
 if rank == 0:
     print("trainer:", cls.__name__)
+ahead = os.environ.get("NO_AHEAD") != "1"        # work one step ahead on the side stream (host tensors in)
+
+
+def slice_of(s):
+    return torch.from_numpy(kg.triples[(s * world + rank) * Bl:(s * world + rank + 1) * Bl])
+
+
 for s in range(steps):
-    gb = kg.triples[s * Bl * world:(s + 1) * Bl * world]
-    tr.train_step(torch.from_numpy(gb[rank * Bl:(rank + 1) * Bl]), 3, s, 0.2, 0.1)
+    tr.train_step(slice_of(s), 3, s, 0.2, 0.1, next_pos=slice_of(s + 1) if (ahead and s + 1 < steps) else None)
 full = tr.gather_embeddings()
 q = torch.from_numpy(kg.triples[:1000])
 raw, filt = tr.rank(q, 0)
