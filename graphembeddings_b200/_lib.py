@@ -35,6 +35,7 @@ SIGNATURES = {
     "hole_train_step": (_int, [_p, _p, _p, _p, _int, _i64, _f32, _f32, _p, _p, _p]),
     "hole_train_step_ex": (_int, [_p, _p, _p, _p, _p, _int, _i64, _f32, _f32, _p, _p, _p]),
     "hole_train_step_plan": (_int, [_p, _p, _p, _i64, _p]),
+    "hole_train_step_logloss": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p, _p, _u64, _u64, _f32, _f32, _p, _p, _p, _p, _p]),
     "hole_shard_route": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _int, _p, _p, _p, _p, _p]),
     "hole_shard_post": (_int, [_p, _p, _p, _int, _int, _i64, _p, _p, _p]),
     "hole_shard_push": (_int, [_p, _p, _i64, _p, _p, _int, _i64, _i64, _p, _p, _p, _p]),

@@ -107,6 +107,9 @@ struct hole_ctx {
   size_t prof_used = 0;
 };
 
+// K1 / K3 `flags`: bits 0-1 = loss mode (0 hinge, 1 / 2 log-loss pass with / without the positive
+// term), bit 2 = add to the delta table instead of overwriting it
+constexpr int HOLE_K1_ACCUMULATE = 4;
 constexpr int HOLE_TREE_C = 32;      // fan-in of the deterministic gradient combine tree
 constexpr int HOLE_TREE_LEVELS = 6;  // 32^6 > any 4B
 

@@ -187,12 +187,13 @@ __global__ void hole_corrupt_kernel(const int32_t* __restrict__ triples, int64_t
 }
 
 // relation id of every triple: the key of the per-step "group by relation" sort
-__global__ void hole_rel_keys_kernel(const int32_t* __restrict__ triples, int64_t B,
+__global__ void hole_rel_keys_kernel(const int32_t* __restrict__ triples, int64_t B, int64_t tstride,
                                      uint32_t* __restrict__ relkeys) {
   const size_t base = (size_t)blockIdx.y * B;
+  const int32_t* tr = triples + (size_t)blockIdx.y * tstride;   // tstride 0: every step shares the batch
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B;
        i += (int64_t)gridDim.x * blockDim.x)
-    relkeys[base + i] = (uint32_t)triples[(base + i) * 3 + 2];
+    relkeys[base + i] = (uint32_t)tr[i * 3 + 2];
 }
 
 // For step s and position g of the relation-grouped order: i = perm[g]; draws (or takes) the
@@ -200,7 +201,7 @@ __global__ void hole_rel_keys_kernel(const int32_t* __restrict__ triples, int64_
 // with slots [relation, tail-slot, head-slot, corrupt entity].  K1 gives T consecutive
 // positions to one lane group and pre-sums the relation gradient over runs of equal relation
 // inside that range, so only the first triple of such a run carries a relation key.
-__global__ void hole_plan_keys_kernel(const int32_t* __restrict__ triples, int64_t B, int T,
+__global__ void hole_plan_keys_kernel(const int32_t* __restrict__ triples, int64_t B, int64_t tstride, int T,
                                       const int32_t* __restrict__ perm,
                                       const int32_t* __restrict__ type_of,
                                       const int64_t* __restrict__ csr_off,
@@ -210,7 +211,7 @@ __global__ void hole_plan_keys_kernel(const int32_t* __restrict__ triples, int64
   const int s = blockIdx.y;
   const uint64_t step = first_step + (uint64_t)s;
   const int side = hole_side_coin(seed, step);
-  const int32_t* tr = triples + (size_t)s * B * 3;
+  const int32_t* tr = triples + (size_t)s * tstride;
   const int32_t* pm = perm + (size_t)s * B;
   uint32_t* k = keys + (size_t)s * 4 * B;
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < B;
@@ -522,7 +523,7 @@ template <int GS, int V, bool FULL>
 __device__ __forceinline__ void finish_row(Row<V>& d, const Row<V>& y, const float4* xraw,
                                            float inv_self, bool uniq, bool act, float lr,
                                            float* erow, float* grow, int lane, int nvec,
-                                           unsigned gmask, bool delta) {
+                                           unsigned gmask, int dmode) {
   if (inv_self <= 1.0f) {          // group-uniform
     float proj = 0.f;
 #pragma unroll
@@ -535,14 +536,20 @@ __device__ __forceinline__ void finish_row(Row<V>& d, const Row<V>& y, const flo
     }
   }
   if (uniq) {
-    if (delta) {
+    if (dmode != 0) {
       // delta mode: erow points into the delta table.  Every row a step uses is written
       // (zeros for an inactive hinge), so the caller only clears the relation block.
+      // dmode 2 adds to what the delta table holds (several passes over one old table).
       const float sc = act ? -lr : 0.f;
 #pragma unroll
       for (int k = 0; k < 4 * V; ++k) {
         d.re[k] = act ? sc * d.re[k] : 0.f;
         d.im[k] = act ? sc * d.im[k] : 0.f;
+      }
+      if (dmode == 2) {
+        Row<V> o;
+        row_load<GS, V, false>(o, erow, lane, nvec);
+        row_add(d, o);
       }
       row_store<GS, V, FULL>(d, erow, lane, nvec);
     } else if (act) {              // inactive hinge: zero gradient, row unchanged
@@ -566,7 +573,7 @@ __device__ __forceinline__ void emit_row(const Row<V>& yh, const Row<V>& yt, con
                                          const Row<V>& yn, const float4* xraw, float inv_self,
                                          float gp, float gn, bool uniq, bool act, float lr,
                                          float* erow, float* grow, int lane, int nvec,
-                                         unsigned gmask, bool delta) {
+                                         unsigned gmask, int dmode) {
   Row<V> d;
   const Row<V>& ys = (ROLE == ROLE_T) ? yt : (ROLE == ROLE_H) ? yh : yn;
 #pragma unroll
@@ -595,7 +602,7 @@ __device__ __forceinline__ void emit_row(const Row<V>& yh, const Row<V>& yt, con
     d.re[k] = gre;
     d.im[k] = gim;
   }
-  finish_row<GS, V, FULL>(d, ys, xraw, inv_self, uniq, act, lr, erow, grow, lane, nvec, gmask, delta);
+  finish_row<GS, V, FULL>(d, ys, xraw, inv_self, uniq, act, lr, erow, grow, lane, nvec, gmask, dmode);
 }
 
 struct TripleIds { int i, h, t, r, n; };
@@ -619,11 +626,14 @@ hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
                           const int32_t* __restrict__ neg, const int32_t* __restrict__ perm,
                           const uint32_t* __restrict__ gslot, int B, int T, int nvec,
                           int stride, float margin, float lr, float* __restrict__ G,
-                          float* __restrict__ loss, float* __restrict__ sigma, float* __restrict__ Dtab) {
+                          float* __restrict__ loss, float* __restrict__ sigma, float* __restrict__ Dtab,
+                          int flags) {
   extern __shared__ float4 k1_smem[];
-  // delta mode (multi-GPU step tables): unique rows write -lr*dx into Dtab instead of
-  // updating E in place
+  // delta mode (multi-GPU step tables, log-loss passes): unique rows write -lr*dx into Dtab
+  // instead of updating E in place
   const bool delta = Dtab != nullptr;
+  const int dmode = delta ? ((flags & HOLE_K1_ACCUMULATE) ? 2 : 1) : 0;
+  const int mode = flags & 3;    // 0 hinge; 1 / 2 = --log_loss pass with / without the positive term
   float* const Eout = delta ? Dtab : E;
   const int lane = threadIdx.x % GS;
   const int gbase = (threadIdx.x % 32) / GS * GS;
@@ -664,7 +674,7 @@ hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
   auto flush_relation = [&]() {
     const uint32_t sl = gslot[run_i];
     finish_row<GS, V, FULL>(acc, yr, rel_smem, ir, sl == HOLE_SLOT_UNIQUE, run_act, lr,
-                      Eout + (size_t)r_cur * stride, G + (size_t)sl * stride, lane, nvec, gmask, delta);
+                      Eout + (size_t)r_cur * stride, G + (size_t)sl * stride, lane, nvec, gmask, dmode);
   };
 
   int stage = 0;
@@ -732,13 +742,27 @@ hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
       sn += __shfl_xor_sync(gmask, sn, o);
     }
     const float vp = sigmoidf_precise(sp), vn = sigmoidf_precise(sn);
-    const float pre = vp - vn + margin;
-    const bool act = pre >= 0.0f;                       // TF Maximum grad: GreaterEqual
-    const float gp = act ? vp * (1.0f - vp) : 0.0f;
-    const float gn = act ? -(vn * (1.0f - vn)) : 0.0f;
-    if (lane == 0) {
-      loss[i] = fmaxf(pre, 0.0f);
-      if (sigma != nullptr) { sigma[i] = vp; sigma[B + i] = vn; }
+    bool act;
+    float gp, gn;
+    if (mode == 0) {
+      const float pre = vp - vn + margin;
+      act = pre >= 0.0f;                                // TF Maximum grad: GreaterEqual
+      gp = act ? vp * (1.0f - vp) : 0.0f;
+      gn = act ? -(vn * (1.0f - vn)) : 0.0f;
+      if (lane == 0) {
+        loss[i] = fmaxf(pre, 0.0f);
+        if (sigma != nullptr) { sigma[i] = vp; sigma[B + i] = vn; }
+      }
+    } else {
+      // --log_loss (holE.py:194-195): loss = log(1 + exp(-label * s)), d/ds = -label * sigmoid(-label * s).
+      // `loss` takes the positives (pass 1 only), `sigma` this pass's negatives.
+      act = true;
+      gp = (mode == 1) ? vp - 1.0f : 0.0f;
+      gn = vn;
+      if (lane == 0) {
+        if (mode == 1) loss[i] = logf(1.0f + expf(-sp));
+        sigma[i] = logf(1.0f + expf(sn));
+      }
     }
     run_act = run_act || act;
     // relation gradient, summed over the run before the clip backward:
@@ -752,11 +776,11 @@ hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
       acc.im[k] += gp * (a * f - b * e) + gn * (a2 * f2 - b2 * e2);
     }
     emit_row<GS, V, ROLE_T, side, FULL>(yh, yt, yr, yn, sb + row4, it, gp, gn, sl_t == HOLE_SLOT_UNIQUE, act, lr,
-                            Eout + (size_t)c.t * stride, G + (size_t)sl_t * stride, lane, nvec, gmask, delta);
+                            Eout + (size_t)c.t * stride, G + (size_t)sl_t * stride, lane, nvec, gmask, dmode);
     emit_row<GS, V, ROLE_H, side, FULL>(yh, yt, yr, yn, sb, ih, gp, gn, sl_h == HOLE_SLOT_UNIQUE, act, lr,
-                            Eout + (size_t)c.h * stride, G + (size_t)sl_h * stride, lane, nvec, gmask, delta);
+                            Eout + (size_t)c.h * stride, G + (size_t)sl_h * stride, lane, nvec, gmask, dmode);
     emit_row<GS, V, ROLE_N, side, FULL>(yh, yt, yr, yn, sb + 2 * row4, in_, gp, gn, sl_n == HOLE_SLOT_UNIQUE, act, lr,
-                            Eout + (size_t)c.n * stride, G + (size_t)sl_n * stride, lane, nvec, gmask, delta);
+                            Eout + (size_t)c.n * stride, G + (size_t)sl_n * stride, lane, nvec, gmask, dmode);
     c = n1;
     n1 = n2;
     n2 = n3;
@@ -773,15 +797,16 @@ hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri
                           const int32_t* __restrict__ neg, const int32_t* __restrict__ perm,
                           const uint32_t* __restrict__ gslot, int side, int B, int T, int nvec,
                           int stride, float margin, float lr, float* __restrict__ G,
-                          float* __restrict__ loss, float* __restrict__ sigma, float* __restrict__ Dtab) {
+                          float* __restrict__ loss, float* __restrict__ sigma, float* __restrict__ Dtab,
+                          int flags) {
   // specialise on the corruption side and on "every lane owns valid float4s" (nvec == GS*V)
   const bool full = (nvec == GS * V);
   if (side) {
-    if (full) hole_train_fwd_bwd_body<GS, V, 1, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab);
-    else      hole_train_fwd_bwd_body<GS, V, 1, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab);
+    if (full) hole_train_fwd_bwd_body<GS, V, 1, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab, flags);
+    else      hole_train_fwd_bwd_body<GS, V, 1, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab, flags);
   } else {
-    if (full) hole_train_fwd_bwd_body<GS, V, 0, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab);
-    else      hole_train_fwd_bwd_body<GS, V, 0, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab);
+    if (full) hole_train_fwd_bwd_body<GS, V, 0, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab, flags);
+    else      hole_train_fwd_bwd_body<GS, V, 0, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab, flags);
   }
 }
 
@@ -821,7 +846,7 @@ template <int GS, int V>
 __global__ void __launch_bounds__(256)
 hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __restrict__ heads,
                   const int* __restrict__ nheads, int* __restrict__ counters, int M, int nvec,
-                  int stride, float lr, float* __restrict__ Dtab) {
+                  int stride, float lr, float* __restrict__ Dtab, int flags) {
   constexpr int C = HOLE_TREE_C;
   const int lane = threadIdx.x % GS;
   const int gbase = (threadIdx.x % 32) / GS * GS;
@@ -850,6 +875,11 @@ hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __r
         if (delta) {
 #pragma unroll
           for (int k = 0; k < 4 * V; ++k) { x.re[k] = -lr * acc.re[k]; x.im[k] = -lr * acc.im[k]; }
+          if (flags & HOLE_K1_ACCUMULATE) {
+            Row<V> o;
+            row_load<GS, V, false>(o, Dtab + (size_t)row * stride, lane, nvec);
+            row_add(x, o);
+          }
           row_store<GS, V>(x, Dtab + (size_t)row * stride, lane, nvec);
           break;
         }
@@ -1127,6 +1157,68 @@ hole_shard_pull_kernel(float* __restrict__ shard, int64_t id_offset, const int32
     row_add(x, d);
     row_store<GS, V>(x, erow, lane, nvec);
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// --log_loss step (holE.py:194-196, 206-220): helpers around the K1/K3 passes
+// ---------------------------------------------------------------------------------------
+// The L2 term  l2 * tf.nn.l2_loss(embeddings)  sits in every one of the (1+k)B loss rows
+// (holE.py:196), so its gradient is dense: E <- E * (1 - lr * (1+k) B l2).  One pass over the
+// table applies it and sums x^2 of the OLD table (block partials; hole_l2_finish adds them
+// in a fixed order and halves).
+__global__ void __launch_bounds__(256)
+hole_l2_scale_kernel(float4* __restrict__ E4, size_t n4, float scale, float* __restrict__ partial) {
+  __shared__ float sm[256];
+  float a = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = E4[i];
+    a += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    if (scale != 1.0f) {
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      E4[i] = v;
+    }
+  }
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+
+__global__ void __launch_bounds__(256)
+hole_l2_finish_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  __shared__ double sm[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += (double)partial[i];
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)(0.5 * sm[0]);
+}
+
+// E[row] += D[row]; D[row] = 0  for every distinct row of one pass (first entry of each run of
+// its sorted keys).  A row shared by several passes is applied by the first and adds zero after.
+template <int GS, int V>
+__global__ void __launch_bounds__(256)
+hole_apply_delta_kernel(float* __restrict__ E, float* __restrict__ D, const uint32_t* __restrict__ skey, int M,
+                        int nvec, int stride) {
+  const int lane = threadIdx.x % GS;
+  const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
+  if (j >= M) return;
+  const uint32_t key = skey[j];
+  if (key == HOLE_KEY_ABSENT || (j > 0 && skey[j - 1] == key)) return;
+  Row<V> x, d, z;
+  row_zero(z);
+  row_load<GS, V, false>(x, E + (size_t)key * stride, lane, nvec);
+  row_load<GS, V, false>(d, D + (size_t)key * stride, lane, nvec);
+  row_add(x, d);
+  row_store<GS, V>(x, E + (size_t)key * stride, lane, nvec);
+  row_store<GS, V>(z, D + (size_t)key * stride, lane, nvec);
 }
 
 // deterministic per-step loss sum: one CTA per step, fixed-shape tree
@@ -1451,12 +1543,14 @@ static int triples_per_group(const hole_ctx* c, int64_t B) {
 // neg_in != nullptr (single-step API): the caller supplies the corruption.
 static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, int64_t B, int64_t S,
                       const int32_t* type_of, const int64_t* csr_off, const int32_t* csr_ids,
-                      uint64_t seed, uint64_t first_step, const int32_t* neg_in, cudaStream_t ps) {
+                      uint64_t seed, uint64_t first_step, const int32_t* neg_in, cudaStream_t ps,
+                      int64_t tstride = -1) {
+  if (tstride < 0) tstride = 3 * B;
   if (pl.used) HOLE_CUDA_TRY(cudaStreamWaitEvent(ps, pl.released, 0));   // last consumer is done
   const int M = (int)(4 * B);
   dim3 grid((unsigned)std::min<int64_t>((B + 255) / 256, 4096), (unsigned)S);
   // 1. perm: triples grouped by relation (stable)
-  hole_rel_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, pl.keysA);
+  hole_rel_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, tstride, pl.keysA);
   HOLE_LAUNCHED();
   uint32_t *ko, *vo;
   int rc = radix_sort(pl.ghist, pl.keysA, pl.keysB, pl.valsA, pl.valsB, reinterpret_cast<uint32_t*>(pl.perm),
@@ -1464,7 +1558,7 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
   if (rc) return rc;
   // 2. corruption + the 4B row keys of every step
   pl.T = triples_per_group(c, B);
-  hole_plan_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, pl.T, pl.perm, type_of, csr_off, csr_ids,
+  hole_plan_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, tstride, pl.T, pl.perm, type_of, csr_off, csr_ids,
                                               seed, first_step, neg_in, pl.neg, pl.keysA);
   HOLE_LAUNCHED();
   // 3. sort by row, 4. segments
@@ -1484,7 +1578,8 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
 // K1 + K3 of one step whose plan is slot `slot` of pl.
 static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos, const int32_t* neg,
                     int side, int64_t B, float margin, float lr, float* loss_out, float* sigma_out,
-                    int64_t slot, cudaStream_t st, float* delta_out = nullptr, bool k1_follows_k3 = false) {
+                    int64_t slot, cudaStream_t st, float* delta_out = nullptr, bool k1_follows_k3 = false,
+                    int flags = 0) {
   const int M = (int)(4 * B);
   const size_t off = (size_t)slot * M;
   cudaEvent_t* pe = nullptr;
@@ -1505,17 +1600,17 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
   if (k1_follows_k3 && !c->profile) {
     HOLE_DISPATCH_PDL(c, hole_train_fwd_bwd_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
                       c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
-                c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out);
+                c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out, flags);
   } else {
     HOLE_DISPATCH_SMEM(c, hole_train_fwd_bwd_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
                        c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
-                c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out);
+                c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out, flags);
   }
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[1], st));
   const unsigned k3_grid = std::min<unsigned>(grid_for_groups(pl.heads_cap, c->gs), (unsigned)c->sm_count * 4);
   HOLE_DISPATCH_PDL(c, hole_apply_kernel, k3_grid, 256, 0, st, table, c->G,
                 pl.heads + (size_t)slot * pl.heads_cap, pl.nheads + slot, c->counters, M, c->nvec,
-                c->row_stride, lr, delta_out);
+                c->row_stride, lr, delta_out, flags);
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[2], st));
   return HOLE_OK;
 }
@@ -1599,6 +1694,64 @@ extern "C" int hole_train_step(hole_ctx* c, float* table, const int32_t* pos, co
                                float* sigma_out, void* stream) {
   return hole_train_step_ex(c, table, nullptr, pos, neg_ent, side, B, margin, lr, loss_out, sigma_out,
                             stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// --log_loss training step (holE.py:194-196, 206-220, 296): k = negative_ratio corrupt
+// batches, each with its own side coin and draws (virtual step  step * k + j).  Every term's
+// gradient is taken at the OLD table, so the k passes run K1/K3 in accumulate-delta mode on an
+// untouched table (pass 0 carries the positive term), then the dense L2 decay and the summed
+// deltas are applied.  delta_ws: table-sized, all zero on entry, all zero again on return.
+// ---------------------------------------------------------------------------------------
+extern "C" int hole_train_step_logloss(hole_ctx* c, float* table, float* delta_ws, const int32_t* triples,
+                                       int64_t B, int negative_ratio, const int32_t* type_of,
+                                       const int64_t* csr_off, const int32_t* csr_ids, uint64_t seed,
+                                       uint64_t step, float lr, float l2, float* loss_out,
+                                       float* l2_loss_out, int32_t* neg_out, int32_t* sides_out,
+                                       void* stream) {
+  HOLE_CHECK_ARG(c && B >= 0 && negative_ratio >= 1 && negative_ratio <= 64);
+  if (B == 0) return HOLE_OK;
+  HOLE_CHECK_ARG(table && delta_ws && triples && type_of && csr_off && csr_ids && loss_out);
+  HOLE_CHECK_ARG(4 * B < (int64_t(1) << 31));
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  const int k = negative_ratio;
+  int rc = hole_ws_reserve(c, B, k);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  hole_plan& pl = c->plan[0];
+  pl.prepared_B = -1;
+  pl.prepared_pos = pl.prepared_neg = nullptr;
+  const uint64_t v0 = step * (uint64_t)k;
+  rc = plan_steps(c, pl, triples, B, k, type_of, csr_off, csr_ids, seed, v0, nullptr, st, /*tstride=*/0);
+  if (rc) return rc;
+  for (int j = 0; j < k; ++j) {
+    const int side = hole_side_coin(seed, v0 + (uint64_t)j);
+    if (sides_out) sides_out[j] = side;
+    rc = run_step(c, pl, table, triples, pl.neg + (size_t)j * B, side, B, 0.0f, lr, loss_out,
+                  loss_out + (size_t)(1 + j) * B, j, st, delta_ws, false,
+                  (j == 0 ? 1 : 2) | HOLE_K1_ACCUMULATE);
+    if (rc) return rc;
+  }
+  if (neg_out)
+    HOLE_CUDA_TRY(cudaMemcpyAsync(neg_out, pl.neg, (size_t)k * B * 4, cudaMemcpyDeviceToDevice, st));
+  if (l2 != 0.0f || l2_loss_out != nullptr) {
+    const float scale = 1.0f - lr * (float)(1 + k) * (float)B * l2;
+    const size_t n4 = (size_t)c->n_rows * c->row_stride / 4;
+    const int blocks = c->sm_count * 8;
+    float* partial = c->G;                 // the gradient staging area is free between steps
+    hole_l2_scale_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<float4*>(table), n4, scale, partial);
+    HOLE_LAUNCHED();
+    float* out = l2_loss_out ? l2_loss_out : partial + blocks;
+    hole_l2_finish_kernel<<<1, 256, 0, st>>>(partial, blocks, out);
+    HOLE_LAUNCHED();
+  }
+  const int M = (int)(4 * B);
+  for (int j = 0; j < k; ++j)
+    HOLE_DISPATCH(c, hole_apply_delta_kernel, grid_for_groups(M, c->gs), 256, st, table, delta_ws,
+                  pl.skey + (size_t)j * M, M, c->nvec, c->row_stride);
+  pl.used = true;
+  HOLE_CUDA_TRY(cudaEventRecord(pl.released, st));
+  return HOLE_OK;
 }
 
 extern "C" int hole_enable_peer_access(hole_ctx* c, int peer_device) {

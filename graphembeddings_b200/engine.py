@@ -154,6 +154,26 @@ class HoleEngine:
                                           _ptr(loss), None, _stream()))
         return loss
 
+    def train_step_logloss(self, triples, seed, step, lr, l2=0.0, negative_ratio=1, want_corruption=False):
+        """The --log_loss step (holE.py:194-196, 206-220, 296).  Returns (loss [(1+k), B] device,
+        l2_loss device scalar = sum(E_old^2)/2) -- the reference's per-row loss is
+        loss + l2 * l2_loss -- and, with want_corruption, also (sides list, neg [k, B] device)."""
+        t = self._triples(triples)
+        B, k = t.shape[0], int(negative_ratio)
+        if getattr(self, "_delta_ws", None) is None or self._delta_ws.shape != self.table.shape:
+            self._delta_ws = torch.zeros_like(self.table)
+        loss = torch.empty((1 + k, B), dtype=torch.float32, device=self.device)
+        l2_loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        neg = torch.empty((k, B), dtype=torch.int32, device=self.device) if want_corruption else None
+        sides = (C.c_int32 * k)()
+        check(self.lib.hole_train_step_logloss(
+            self._ctx, _ptr(self.table), _ptr(self._delta_ws), _ptr(t), B, k, _ptr(self.type_of),
+            _ptr(self.csr_off), _ptr(self.csr_ids), int(seed), int(step), float(lr), float(l2), _ptr(loss),
+            _ptr(l2_loss), None if neg is None else _ptr(neg), sides, _stream()))
+        if want_corruption:
+            return loss, l2_loss, list(sides), neg
+        return loss, l2_loss
+
     # ---- multi-GPU step routing (include/hole_b200.h, "multi-GPU step routing") ----
     @staticmethod
     def peer_array(tensors):

@@ -10,7 +10,8 @@ score_mrr (475-490), infer_triples (530-582).  Differences, all deliberate and l
 DESIGN.md: triples come from a device-resident per-epoch permutation instead of a TF shuffle
 queue; corruption is the Philox sampler (--padded_size accepted, unused); `--infer` runs the
 all-entity filtered head+tail protocol with the unreachable `infer_threshold` gate off unless
---infer_gate is given; --log_loss / --save_embeddings are rejected (out of scope).
+--infer_gate is given; --save_embeddings is rejected (a py2-only debug dump).  --log_loss,
+--negative_ratio and --l2_regularization select the logistic branch (holE.py:194-196, 206-220).
 """
 import argparse
 import errno
@@ -147,6 +148,22 @@ def evaluate_batch(eng, triple_batch, seed, step, margin):
     return torch.clamp(vp - vn + margin, min=0.0), vp, vn
 
 
+def evaluate_batch_logloss(eng, triple_batch, seed, step, l2, negative_ratio):
+    """holE.py:206-221 without the update: rows [(1 + k), B] = log(1 + exp(-label * score)) +
+    l2 * l2_loss(embeddings) for the positives and k corrupt batches (virtual steps step*k + j,
+    as in hole_train_step_logloss).  Forward only (validation); computed from the device scores."""
+    t = torch.as_tensor(triple_batch, dtype=torch.int32).to(eng.device)
+    k = int(negative_ratio)
+    rows = [-torch.log(eng.evaluate_triples(t))]                 # log(1+exp(-s)) = -log(sigmoid(s))
+    for j in range(k):
+        side, neg = eng.corrupt_batch(t, seed, step * k + j)
+        corrupt = t.clone()
+        corrupt[:, 0 if side else 1] = neg
+        rows.append(-torch.log1p(-eng.evaluate_triples(corrupt)))  # log(1+exp(s)) = -log(1 - sigmoid(s))
+    l2_loss = 0.5 * (eng.table.double() ** 2).sum()
+    return torch.stack(rows) + float(l2) * l2_loss.float()
+
+
 def summarize(var):
     """holE.py:237-246: mean / stddev / max / min of a tensor."""
     mean = var.mean()
@@ -218,12 +235,18 @@ def run_training(data, flags=None, seed=0, max_steps=None, log=print):
                 while batch < batch_count:
                     if batch % valid_every == 0 and len(valid) > 0:
                         vb = valid[vrng.integers(0, len(valid), size=B)]
-                        vloss, vp, vn = evaluate_batch(eng, vb, seed, global_step, flags.margin)
+                        if flags.log_loss:
+                            vloss = evaluate_batch_logloss(eng, vb, seed, global_step, flags.l2_regularization,
+                                                           flags.negative_ratio)
+                            parts = (("loss", vloss),)
+                        else:
+                            vloss, vp, vn = evaluate_batch(eng, vb, seed, global_step, flags.margin)
+                            parts = (("pos", vp), ("neg", vn), ("loss", vloss))
                         vlm = float(vloss.mean())
                         lr_now = float(inverse_time_decay(flags.learning_rate, global_step, decay_steps,
                                                           flags.learning_decay_rate))
                         row = {"step": global_step, "valid_loss_mean": vlm, "learning_rate": lr_now}
-                        for nm, var in (("pos", vp), ("neg", vn), ("loss", vloss)):
+                        for nm, var in parts:
                             row.update({f"{nm}_{k}": v for k, v in summarize(var).items()})
                         slog.write("\t".join(f"{k}={v}" for k, v in row.items()) + "\n")
                         slog.flush()
@@ -239,8 +262,14 @@ def run_training(data, flags=None, seed=0, max_steps=None, log=print):
                         n = min(n, max_steps - steps_done)
                     lrs = [inverse_time_decay(flags.learning_rate, global_step + k, decay_steps,
                                               flags.learning_decay_rate) for k in range(n)]
-                    eng.train_steps(shuffled[(batch - 1) * B:(batch - 1 + n) * B], B, seed, global_step,
-                                    flags.margin, lrs)
+                    if flags.log_loss:
+                        for k in range(n):       # one library call per step (k corrupt batches inside)
+                            eng.train_step_logloss(shuffled[(batch - 1 + k) * B:(batch + k) * B], seed,
+                                                   global_step + k, lrs[k], flags.l2_regularization,
+                                                   flags.negative_ratio)
+                    else:
+                        eng.train_steps(shuffled[(batch - 1) * B:(batch - 1 + n) * B], B, seed, global_step,
+                                        flags.margin, lrs)
                     batch += n
                     global_step += n
                     steps_done += n
@@ -415,7 +444,7 @@ def build_parser():
     parser.add_argument('--batch_size', type=int, default=512, help='Batch size.')
     parser.add_argument('--num_epochs', type=int, default=1000, help='Number of training epochs.')
     parser.add_argument('--embedding_dim', type=int, default=128, help='Embedding dimension.')
-    parser.add_argument('--log_loss', action='store_true', help='(out of scope here) logistic loss.')
+    parser.add_argument('--log_loss', action='store_true', help='Use logistic loss with --negative_ratio corrupt batches (holE.py:194-196, 206-220).')
     parser.add_argument('--l2_regularization', type=float, default=0.1, help='L2 regularization weight (log loss only).')
     parser.add_argument('--negative_ratio', type=int, default=1, help='Number of negative labels sampled in log_loss.')
     parser.add_argument('--margin', type=float, default=0.2, help='Hinge loss margin.')
@@ -444,8 +473,6 @@ def main(argv=None):
     FLAGS, _ = build_parser().parse_known_args(argv)
     if FLAGS.save_embeddings:
         raise SystemExit("--save_embeddings (holE.py:501-527, a py2-only debug dump) is out of scope")
-    if FLAGS.log_loss:
-        raise SystemExit("--log_loss (holE.py:194-196, 206-220) is out of scope for this path")
     if FLAGS.infer:
         infer_triples(FLAGS)
     else:

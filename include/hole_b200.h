@@ -131,6 +131,24 @@ HOLE_API int hole_train_step_ex(hole_ctx* ctx, float* table, float* delta_out, c
                        float* loss_out, float* sigma_out, void* stream);
 HOLE_API int hole_train_step_plan(hole_ctx* ctx, const int32_t* pos, const int32_t* neg_ent, int64_t B,
                          void* stream);
+/* ---- the --log_loss branch of evaluate_batch (holE.py:194-196, 206-220) + minimize (296).
+ * loss rows: B positives with label +1, then negative_ratio corrupt batches with label -1,
+ * each its own corrupt_batch call (own head/tail coin and draws: virtual step
+ * step * negative_ratio + j of the Philox stream).  Row loss = log(1 + exp(-label * score))
+ * (+ l2 * l2_loss(embeddings), the same scalar in every row -- returned separately).
+ * Update: E -= lr * d(sum of all rows)/dE, i.e. the sparse score gradients taken at the old
+ * table plus the dense decay  E * lr * (1 + negative_ratio) * B * l2.
+ *   delta_ws     [n_rows, row_stride] device scratch, all zero on entry and on return
+ *   loss_out     [(1 + negative_ratio) * B] device: positives, then each corrupt batch
+ *   l2_loss_out  device scalar = sum(E_old^2) / 2 (tf.nn.l2_loss), or NULL
+ *   neg_out      [negative_ratio * B] device int32 replacement entities, or NULL
+ *   sides_out    [negative_ratio] HOST int32 (1 = heads replaced), or NULL */
+HOLE_API int hole_train_step_logloss(hole_ctx* ctx, float* table, float* delta_ws, const int32_t* triples,
+                                     int64_t B, int negative_ratio, const int32_t* type_of,
+                                     const int64_t* csr_off, const int32_t* csr_ids, uint64_t seed,
+                                     uint64_t step, float lr, float l2, float* loss_out, float* l2_loss_out,
+                                     int32_t* neg_out, int32_t* sides_out, void* stream);
+
 /* ---- multi-GPU step routing over NVLink peer memory (no counterpart in the reference;
  * SURVEY.md 8e).  All counts stay on the device: a sharded step never synchronises the host.
  * Buffers marked PEER may live on another GPU (mapped with CUDA IPC after

@@ -221,6 +221,40 @@ def sgd_step(E, pos, neg_ent, side, margin, lr, dtype=np.float32, order="tf"):
     return loss, vp, vn
 
 
+def logloss_step(E, pos, neg_ents, sides, lr, l2=0.0, dtype=np.float32):
+    """One --log_loss training step, in place on E (holE.py:194-196, 206-220, 296).
+
+    Loss rows: the B positives with label +1 (holE.py:210), then one corrupt batch per
+    entry of ``sides`` / ``neg_ents`` with label -1 (holE.py:213-217), concatenated
+    (holE.py:221).  Row loss = log(1 + exp(-label * score)) + l2 * l2_loss(embeddings)
+    (holE.py:194-196; tf.nn.l2_loss = sum(x^2)/2 over the WHOLE variable, the same scalar in
+    every row).  minimize() differentiates the sum of the rows: the sparse score gradients
+    (through clip_by_norm, as in the hinge branch) plus  n_rows_of_loss * l2 * E  for the
+    whole table.  Returns (loss [(1+k), B] without the L2 scalar, l2_loss scalar)."""
+    pos = np.asarray(pos)
+    dt = np.dtype(dtype).type
+    B, k = len(pos), len(sides)
+    Ew = E.astype(dtype, copy=True)
+    s_p = score(Ew, pos, dtype)
+    losses = [np.log(dt(1.0) + np.exp(-s_p))]
+    acc = np.zeros_like(Ew)
+
+    def scatter(triples, g):
+        for col, dx in zip((0, 1, 2), _side_grads(Ew, triples, g, dtype)):
+            np.add.at(acc, triples[:, col].astype(np.int64), dx)
+
+    scatter(pos, sigmoid(s_p) - dt(1.0))              # d/ds log(1+exp(-s)) = -sigmoid(-s)
+    for j in range(k):
+        neg = corrupt_triples(pos, neg_ents[j], sides[j])
+        s_n = score(Ew, neg, dtype)
+        losses.append(np.log(dt(1.0) + np.exp(s_n)))
+        scatter(neg, sigmoid(s_n))                    # d/ds log(1+exp(+s)) = sigmoid(s)
+    l2_loss = dt(0.5) * np.sum(Ew.astype(np.float64) ** 2)
+    decay = dt(lr) * dt((1 + k) * B) * dt(l2)
+    E[...] = Ew - dt(lr) * acc - decay * Ew
+    return np.stack(losses), dtype(l2_loss)
+
+
 # --------------------------------------------------------------------------------------
 # corruption (holE.py:97-140, 343-347; App. A.6)
 # --------------------------------------------------------------------------------------

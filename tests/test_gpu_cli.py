@@ -84,6 +84,32 @@ def test_train_checkpoint_resume_infer(tmp_path):
     assert np.mean(np.abs(np.array(filt) - np.array(want_f)) <= 3) > 0.9
 
 
+def test_log_loss_branch_trains_and_logs(tmp_path):
+    """--log_loss --negative_ratio 2 (holE.py:194-196, 206-220) through the driver, resumed
+    from a trained-scale checkpoint: summaries and the pocket checkpoint are written (that the loss falls is
+    tests/test_gpu_train.py::test_logloss_training_reduces_the_loss)."""
+    from graphembeddings_b200 import build, hole, tf_bundle
+    build.build()
+    kg = D.synthetic_kg(8, 1500, 9000, 4, 64, seed=4, trained_scale=True)
+    d = tmp_path / "data"; d.mkdir()
+    parts = _write_data_dir(str(d), kg, 600, 400)
+    out = str(tmp_path / "run")
+    os.makedirs(out)
+    tf_bundle.save_bundle(os.path.join(out, "model.ckpt"),
+                          {"embeddings": kg.E, "batch/Variable": np.array(0, dtype=np.int32)})
+    args = ["--data_dir", str(d), "--output_dir", out, "--batch_size", "256", "--embedding_dim", "64",
+            "--num_epochs", "4", "--log_loss", "--negative_ratio", "2", "--l2_regularization", "0",
+            "--learning_rate", "0.5", "--resume_checkpoint"]
+    hole.main(args)
+    rows = [dict(kv.split("=") for kv in line.split("\t")) for line in open(os.path.join(out, "summaries.tsv"))]
+    assert len(rows) >= 8 and all(np.isfinite(float(r["valid_loss_mean"])) for r in rows)
+    E1 = tf_bundle.load_bundle(os.path.join(out, "model.ckpt"))["embeddings"]
+    assert np.isfinite(E1).all() and np.abs(E1 - kg.E).max() > 1e-4
+    # the first validation row is the logistic loss of the restored table: positives and two
+    # corrupt batches of near-random scores -> close to log 2
+    assert abs(float(rows[0]["valid_loss_mean"]) - np.log(2.0)) < 0.05
+
+
 def test_typed_candidate_protocol_matches_heap_restatement():
     """holE.py's own inference protocol: per head, product(tails, relations) ranked jointly
     (holE.py:564-573, 427-469) -- tensor-core counts vs the oracle's heap restatement, which is

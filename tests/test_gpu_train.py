@@ -234,6 +234,68 @@ def test_sharded_trainer_single_rank_matches_engine(eng_mod):
     assert np.abs(want - kg.E).max() > 1e-4
 
 
+@pytest.mark.parametrize("dim,k,l2", [(150, 1, 0.0), (256, 3, 0.0), (64, 2, 1e-5), (600, 2, 0.0)])
+def test_logloss_step_matches_oracle(eng_mod, dim, k, l2):
+    """--log_loss branch (holE.py:194-196, 206-220): k corrupt batches drawn with virtual steps
+    step*k + j (bit-exact vs the oracle's Philox), softplus rows, sparse gradients taken at the
+    old table + dense L2 decay.  fp32 tolerances as for the hinge step."""
+    kg = D.synthetic_kg(7, 4000, 900, 5, dim, seed=50 + k, trained_scale=True, zipf_entities=True)
+    e, off, ids = _engine(eng_mod, kg)
+    seed, B, lr = 21, 300, 0.05
+    E = kg.E.copy()
+    for step in range(3):
+        pos = kg.triples[step * B:(step + 1) * B]
+        loss, l2_loss, sides, neg = e.train_step_logloss(pos, seed, step, lr, l2, k, want_corruption=True)
+        neg_h = neg.cpu().numpy()
+        for j in range(k):
+            side_o, neg_o = O.corrupt(pos, kg.type_of, off, ids, seed, step * k + j)
+            assert side_o == sides[j] and np.array_equal(neg_o, neg_h[j])
+        want_l2 = 0.5 * float((E.astype(np.float64) ** 2).sum())
+        want_loss, _ = O.logloss_step(E, pos, list(neg_h), sides, lr, l2, np.float32)
+        assert np.abs(loss.cpu().numpy() - want_loss).max() <= 2e-6
+        assert abs(float(l2_loss) - want_l2) <= 1e-5 * want_l2
+    got = e.embeddings().cpu().numpy()
+    assert np.allclose(got, E, atol=ROW_ATOL * 3, rtol=ROW_RTOL)
+    assert np.abs(E - kg.E).max() > 1e-4
+    assert not e._delta_ws.any()                 # the scratch delta table is handed back clean
+
+
+def test_logloss_gradient_is_taken_at_the_old_table(eng_mod):
+    """Heavy duplicates + k = 4: every pass must see the table as it was before the step
+    (TF computes the whole gradient, then applies it once)."""
+    kg = D.synthetic_kg(3, 40, 512, 2, 128, seed=77, trained_scale=True)
+    e, off, ids = _engine(eng_mod, kg)
+    E = kg.E.copy()
+    pos = kg.triples[:512]
+    loss, l2_loss, sides, neg = e.train_step_logloss(pos, 5, 0, 0.1, 0.0, 4, want_corruption=True)
+    O.logloss_step(E, pos, list(neg.cpu().numpy()), sides, 0.1, 0.0, np.float32)
+    got = e.embeddings().cpu().numpy()
+    assert np.allclose(got, E, atol=2e-5, rtol=1e-4)
+
+
+def test_logloss_training_reduces_the_loss(eng_mod):
+    """96 consecutive --log_loss steps (k = 2): the loss of the positives falls, and by the
+    same amount as in the oracle's loop."""
+    kg = D.synthetic_kg(8, 1500, 4096, 4, 64, seed=4, trained_scale=True)
+    e, off, ids = _engine(eng_mod, kg)
+    E = kg.E.copy()
+
+    def pos_loss(X):
+        return float(np.log1p(np.exp(-O.score(X, kg.triples, np.float64))).mean())
+
+    step = 0
+    for epoch in range(6):
+        for b in range(16):
+            pos = kg.triples[b * 256:(b + 1) * 256]
+            e.train_step_logloss(pos, 3, step, 0.5, 0.0, 2)
+            drawn = [O.corrupt(pos, kg.type_of, off, ids, 3, step * 2 + j) for j in range(2)]
+            O.logloss_step(E, pos, [d[1] for d in drawn], [d[0] for d in drawn], 0.5, 0.0, np.float32)
+            step += 1
+    got = pos_loss(e.embeddings().cpu().numpy())
+    assert got < pos_loss(kg.E) - 0.02
+    assert abs(got - pos_loss(E)) < 1e-4
+
+
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_shard_route_post_push_pull_virtual_ranks(eng_mod, world):
     """The multi-GPU exchange primitives with `world` virtual ranks on one GPU (peer buffers

@@ -154,6 +154,50 @@ def test_gradient_matches_torch_autograd(side):
     assert np.abs(Et.grad.numpy() - G).max() < 1e-12
 
 
+def _torch_logloss(E, pos, neg_list, l2):
+    """Independent torch-autograd restatement of the --log_loss branch: holE.py:161-168
+    (max_norm lookup), 191-196 (score, -label * score, log(1 + exp), + l2 * l2_loss(embeddings)),
+    206-221 (positives then negative_ratio corrupt batches, concatenated), 296 (sum)."""
+    def emb(ids):
+        x = E[ids]
+        inv = torch.rsqrt((x * x).sum(dim=1, keepdim=True))
+        y = x * torch.minimum(inv, torch.ones_like(inv))
+        H = x.shape[1] // 2
+        return torch.complex(y[:, :H], y[:, H:])
+
+    def rows(tr, label):
+        h, t, r = emb(tr[:, 0]), emb(tr[:, 1]), emb(tr[:, 2])
+        s = (h * (r * torch.conj(t))).real.sum(dim=1)
+        return torch.log(1.0 + torch.exp(-label * s)) + l2 * 0.5 * (E * E).sum()
+
+    return torch.cat([rows(pos, 1.0)] + [rows(n, -1.0) for n in neg_list]).sum()
+
+
+@pytest.mark.parametrize("k,l2", [(1, 0.0), (3, 0.0), (2, 1e-3)])
+def test_logloss_step_matches_torch_autograd(k, l2):
+    kg = _kg(seed=12, dim=20, n_triples=48)
+    E = kg.E.astype(np.float64)
+    pos = kg.triples
+    rng = np.random.default_rng(8)
+    negs = [rng.integers(kg.n_relations, kg.n_rows, size=len(pos)).astype(np.int32) for _ in range(k)]
+    sides = [int(rng.integers(0, 2)) for _ in range(k)]
+    lr = 0.05
+    Et = torch.tensor(E, requires_grad=True)
+    L = _torch_logloss(Et, torch.tensor(pos, dtype=torch.long),
+                       [torch.tensor(O.corrupt_triples(pos, n, sd), dtype=torch.long) for n, sd in zip(negs, sides)], l2)
+    L.backward()
+    want = E - lr * Et.grad.numpy()
+    got = E.copy()
+    loss, l2_loss = O.logloss_step(got, pos, negs, sides, lr, l2, np.float64)
+    assert loss.shape == (1 + k, len(pos))
+    assert np.abs(got - want).max() < 1e-12
+    assert abs(float(loss.sum() + loss.size * l2 * l2_loss) - float(L.detach())) < 1e-9 * max(1.0, abs(float(L.detach())))
+    # fp32 follows fp64
+    got32 = kg.E.astype(np.float32).copy()
+    O.logloss_step(got32, pos, negs, sides, lr, l2, np.float32)
+    assert np.abs(got32 - want).max() < 5e-6
+
+
 def test_sgd_orders_agree_and_duplicates_accumulate():
     kg = _kg(seed=12, dim=16, n_triples=200)       # 60 entities, 200 triples: many duplicates
     pos = kg.triples
