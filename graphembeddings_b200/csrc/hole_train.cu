@@ -620,7 +620,7 @@ __device__ __forceinline__ TripleIds load_ids(const int32_t* __restrict__ tri,
 constexpr int K1_STAGES = 3;   // landing buffers per lane group: the triple being computed (its
                                // unscaled rows are re-read for the in-place update) + 2 in flight
 
-template <int GS, int V, int side, bool FULL>
+template <int GS, int V, int side, bool FULL, bool LOGLOSS>
 __device__ __forceinline__ void
 hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
                           const int32_t* __restrict__ neg, const int32_t* __restrict__ perm,
@@ -633,7 +633,9 @@ hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
   // instead of updating E in place
   const bool delta = Dtab != nullptr;
   const int dmode = delta ? ((flags & HOLE_K1_ACCUMULATE) ? 2 : 1) : 0;
-  const int mode = flags & 3;    // 0 hinge; 1 / 2 = --log_loss pass with / without the positive term
+  // 0 hinge; 1 / 2 = --log_loss pass with / without the positive term (own instantiation, so
+  // that the hinge kernel is compiled exactly as if the branch did not exist)
+  const int mode = LOGLOSS ? (flags & 3) : 0;
   float* const Eout = delta ? Dtab : E;
   const int lane = threadIdx.x % GS;
   const int gbase = (threadIdx.x % 32) / GS * GS;
@@ -801,14 +803,25 @@ hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri
                           int flags) {
   // specialise on the corruption side and on "every lane owns valid float4s" (nvec == GS*V)
   const bool full = (nvec == GS * V);
-  if (side) {
-    if (full) hole_train_fwd_bwd_body<GS, V, 1, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab, flags);
-    else      hole_train_fwd_bwd_body<GS, V, 1, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab, flags);
-  } else {
-    if (full) hole_train_fwd_bwd_body<GS, V, 0, true>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab, flags);
-    else      hole_train_fwd_bwd_body<GS, V, 0, false>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab, flags);
-  }
+#define HOLE_K1_BODY(SIDE, FULL_, LL) \
+  hole_train_fwd_bwd_body<GS, V, SIDE, FULL_, LL>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab, flags)
+  if (side) { if (full) HOLE_K1_BODY(1, true, false); else HOLE_K1_BODY(1, false, false); }
+  else      { if (full) HOLE_K1_BODY(0, true, false); else HOLE_K1_BODY(0, false, false); }
 }
+
+// the --log_loss passes: a kernel of their own (generic-width body), so that the hinge kernel's
+// register allocation is not the maximum over both
+template <int GS, int V>
+__global__ void __launch_bounds__(256)
+hole_train_fwd_bwd_ll_kernel(float* __restrict__ E, const int32_t* __restrict__ tri,
+                             const int32_t* __restrict__ neg, const int32_t* __restrict__ perm,
+                             const uint32_t* __restrict__ gslot, int side, int B, int T, int nvec,
+                             int stride, float margin, float lr, float* __restrict__ G,
+                             float* __restrict__ loss, float* __restrict__ sigma, float* __restrict__ Dtab,
+                             int flags) {
+  if (side) HOLE_K1_BODY(1, false, true); else HOLE_K1_BODY(0, false, true);
+}
+#undef HOLE_K1_BODY
 
 // ---------------------------------------------------------------------------------------
 // K3: deterministic sparse SGD update for rows that occur more than once in the step.
@@ -1343,6 +1356,13 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
     else if (c->v == 1) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
     else if (c->v == 2) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
     else ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+    if (ea == cudaSuccess) {
+      if (c->gs == 8) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_ll_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+      else if (c->gs == 16) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_ll_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+      else if (c->v == 1) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_ll_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+      else if (c->v == 2) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_ll_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+      else ea = cudaFuncSetAttribute(hole_train_fwd_bwd_ll_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+    }
     if (ea != cudaSuccess) {
       const int want = c->k1_smem;
       delete c;
@@ -1597,7 +1617,11 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
   }
   // K1's prologue reads plan data before griddepcontrol.wait: only overlap it with a
   // predecessor that does not write the plan, i.e. the previous step's K3 of the same chunk
-  if (k1_follows_k3 && !c->profile) {
+  if ((flags & 3) != 0) {
+    HOLE_DISPATCH_SMEM(c, hole_train_fwd_bwd_ll_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
+                       c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
+                c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out, flags);
+  } else if (k1_follows_k3 && !c->profile) {
     HOLE_DISPATCH_PDL(c, hole_train_fwd_bwd_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
                       c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
                 c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out, flags);
