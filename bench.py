@@ -181,6 +181,9 @@ def run_reference(args):
     kg, off, ids = make_workload((K + W) * B)
     from oracle import hole_oracle as O
     from oracle import hole_ref as R
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers;
+    # the other ranks have exited, the cores are free)
+    R.set_threads(int(os.environ.get("HOLE_REF_THREADS", len(os.sched_getaffinity(0)))))
     E = np.ascontiguousarray(kg.E, np.float32)
     sc = R.TrainScratch(B, kg.dim)
     negs = [O.corrupt(kg.triples[s * B:(s + 1) * B], kg.type_of, off, ids, 1, s) for s in range(K + W)]

@@ -27,6 +27,15 @@ int hole_ref_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm asks for the cores back */
+void hole_ref_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* y = x * min(1/sqrt(sum x^2), 1); returns inv norm */
 static inline float clip_row(const float* x, float* y, int D) {
   float ss = 0.f;

@@ -29,6 +29,14 @@ def threads():
     return int(load().hole_ref_threads())
 
 
+def set_threads(n):
+    """OpenMP threads of the port (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib = load()
+    lib.hole_ref_set_threads.argtypes = [C.c_int]
+    lib.hole_ref_set_threads.restype = None
+    lib.hole_ref_set_threads(int(n))
+
+
 def score(E, triples):
     E = np.ascontiguousarray(E, np.float32)
     tr = np.ascontiguousarray(triples, np.int32)
