@@ -40,7 +40,7 @@ SIGNATURES = {
     "hole_shard_post": (_int, [_p, _p, _p, _int, _int, _i64, _p, _p, _p]),
     "hole_shard_push": (_int, [_p, _p, _i64, _p, _p, _int, _i64, _i64, _p, _p, _p, _p]),
     "hole_shard_barrier": (_int, [_p, _int, _int, _i32, _p, _p, _p]),
-    "hole_shard_pull": (_int, [_p, _p, _i64, _p, _p, _int, _i64, _i64, _p, _p]),
+    "hole_shard_pull": (_int, [_p, _p, _i64, _p, _p, _int, _i64, _i64, _p, _int, _p]),
     "hole_enable_peer_access": (_int, [_p, _int]),
     "hole_gather_rows": (_int, [_p, _p, _p, _i64, _p, _i64, _p]),
     "hole_add_rows": (_int, [_p, _p, _p, _i64, _p, _i64, _p]),

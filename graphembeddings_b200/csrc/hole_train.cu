@@ -1156,13 +1156,26 @@ template <int GS, int V>
 __global__ void __launch_bounds__(256)
 hole_shard_pull_kernel(float* __restrict__ shard, int64_t id_offset, const int32_t* __restrict__ inbox,
                        const int32_t* __restrict__ meta, int k, int64_t cap, int64_t row_base,
-                       const float* __restrict__ deltas_k, int nvec, int stride) {
+                       const float* __restrict__ deltas_k, int add_replicated, int nvec, int stride) {
   const int lane = threadIdx.x % GS;
   const int n = meta[2 * k], off = meta[2 * k + 1];
   const float* src = deltas_k + (size_t)(row_base + off) * stride;
   const int32_t* ids = inbox + (size_t)k * cap;
   const int gstride = (gridDim.x * blockDim.x) / GS;
-  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) / GS; g < n; g += gstride) {
+  const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) / GS;
+  if (add_replicated) {
+    // the replicated relation block: every rank adds every rank's deltas in rank order, so the
+    // replicas stay bit-identical without an all-reduce
+    for (int g = g0; g < (int)row_base; g += gstride) {
+      float* erow = shard + (size_t)g * stride;
+      Row<V> x, d;
+      row_load<GS, V, false>(x, erow, lane, nvec);
+      row_load<GS, V, false>(d, deltas_k + (size_t)g * stride, lane, nvec);
+      row_add(x, d);
+      row_store<GS, V>(x, erow, lane, nvec);
+    }
+  }
+  for (int g = g0; g < n; g += gstride) {
     float* erow = shard + (size_t)(ids[g] + id_offset) * stride;
     Row<V> x, d;
     row_load<GS, V, false>(x, erow, lane, nvec);
@@ -1922,14 +1935,15 @@ extern "C" int hole_shard_barrier(hole_ctx* c, int world, int me, int32_t epoch,
 
 extern "C" int hole_shard_pull(hole_ctx* c, float* shard, int64_t id_offset, const int32_t* inbox,
                                const int32_t* meta, int world, int64_t cap, int64_t row_base,
-                               void* const* peer_deltas, void* stream) {
+                               void* const* peer_deltas, int add_replicated, void* stream) {
   HOLE_CHECK_ARG(c && shard && inbox && meta && peer_deltas);
   HOLE_CHECK_ARG(world >= 1 && world <= HOLE_MAX_RANKS && cap > 0 && row_base >= 0);
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   for (int k = 0; k < world; ++k) {
     HOLE_CHECK_ARG(peer_deltas[k] != nullptr);
     HOLE_DISPATCH(c, hole_shard_pull_kernel, (unsigned)c->sm_count * 8, 256, (cudaStream_t)stream, shard, id_offset,
-                  inbox, meta, k, cap, row_base, static_cast<const float*>(peer_deltas[k]), c->nvec, c->row_stride);
+                  inbox, meta, k, cap, row_base, static_cast<const float*>(peer_deltas[k]), add_replicated, c->nvec,
+                  c->row_stride);
   }
   return HOLE_OK;
 }

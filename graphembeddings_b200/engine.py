@@ -201,9 +201,10 @@ class HoleEngine:
         check(self.lib.hole_shard_barrier(self._ctx, int(world), int(me), int(epoch), peer_flags,
                                           _ptr(err_flag), _stream()))
 
-    def shard_pull(self, shard, id_offset, inbox, meta, world, cap, row_base, peer_deltas):
+    def shard_pull(self, shard, id_offset, inbox, meta, world, cap, row_base, peer_deltas, add_replicated=False):
         check(self.lib.hole_shard_pull(self._ctx, _ptr(shard), int(id_offset), _ptr(inbox), _ptr(meta),
-                                       int(world), int(cap), int(row_base), peer_deltas, _stream()))
+                                       int(world), int(cap), int(row_base), peer_deltas, int(add_replicated),
+                                       _stream()))
 
     def enable_peer_access(self, peer_device):
         check(self.lib.hole_enable_peer_access(self._ctx, int(peer_device)))

@@ -312,12 +312,14 @@ class P2PRowShardedTrainer(RowShardedTrainer):
         -- barrier --
         push    : as an owner, copy the requested rows into the requesters' W       (peer stores)
         -- barrier --
-        K1 + K3 in delta mode on W -> D;  all-reduce of the replicated relation block of D
-        (that all-reduce is also the barrier "every D is complete")
+        K1 + K3 in delta mode on W -> D
+        -- barrier --
         pull    : as an owner, read the requesters' D rows and add them to my shard (peer loads),
-                  requester by requester in rank order -> deterministic
+                  requester by requester in rank order -> deterministic; the replicated relation
+                  block takes every rank's relation deltas the same way (replicas stay
+                  bit-identical without an all-reduce)
 
-    NCCL carries only the relation all-reduce; the barriers are a one-warp kernel on peer flags.
+    No NCCL call inside a step; the barriers are a one-warp kernel on peer flags.
     Inboxes are double buffered by step parity (a fast rank may post step s+1 while a slow
     owner still pulls step s); W and D are protected by the barriers."""
 
@@ -435,12 +437,11 @@ class P2PRowShardedTrainer(RowShardedTrainer):
         if next_pos is not None:
             with _Section("prepare next (side stream)"):
                 self._ahead = self._prepare(next_pos, seed, step + 1, entry)
-        with _Section("allreduce relations"):
-            d_rel = be.D[:R].clone()
-            self.dist.all_reduce(d_rel)            # also the barrier "every D is complete"
-            self.shard[:R] += d_rel
         with _Section("pull deltas from requesters"):
-            eng.shard_pull(self.shard, R - self.begin, inbox, meta, G, self.cap, R, self.peer_D)
+            self._barrier()                        # every D is complete
+            # entity deltas from the requesters + the relation block of every rank, in rank order
+            eng.shard_pull(self.shard, R - self.begin, inbox, meta, G, self.cap, R, self.peer_D,
+                           add_replicated=True)
         return loss
 
 
@@ -548,7 +549,7 @@ def bench(args, dist, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{B_.WORKLOAD}: BASELINE.json configs[1] table row-sharded over {world} GPUs "
                                    "(relations replicated); requests posted, rows pushed and deltas pulled by our kernels "
-                                   "over NVLink peer memory; NCCL only for the relation all-reduce" if cls is P2PRowShardedTrainer else
+                                   "over NVLink peer memory; no NCCL call inside a step" if cls is P2PRowShardedTrainer else
                                    f"{B_.WORKLOAD}: table row-sharded over {world} GPUs, NCCL all-to-all of rows and row deltas",
                        "batch_per_gpu": Bl, "global_batch": Bl * world, "margin": B_.MARGIN, "lr0": B_.LR0,
                        "parallelism": f"rowshard{world}", "l2": "table shard larger than L2; no flush",

@@ -169,7 +169,9 @@ HOLE_API int hole_train_step_logloss(hole_ctx* ctx, float* table, float* delta_w
  *   each, zero-initialised); `epoch` must grow by one per call on every rank.  A peer that does
  *   not arrive within 10 s sets *err_flag (device int32) instead of hanging the GPU.
  * hole_shard_pull: for k = 0..world-1 in order, shard[inbox[k][g] + id_offset] +=
- *   peer_deltas[k] (PEER delta table) row row_base + meta[k][1] + g. */
+ *   peer_deltas[k] (PEER delta table) row row_base + meta[k][1] + g.  With add_replicated it also
+ *   adds rows [0, row_base) of every peer_deltas[k] to shard[0, row_base) in the same rank order
+ *   (the replicated relation block: all replicas stay bit-identical, no all-reduce needed). */
 #define HOLE_MAX_RANKS 16
 HOLE_API int hole_shard_route(hole_ctx* ctx, const int32_t* pos, const int32_t* neg_ent, int64_t B,
                               int64_t n_relations, int64_t n_rows_global, int64_t rows_per_rank, int world,
@@ -184,7 +186,7 @@ HOLE_API int hole_shard_barrier(hole_ctx* ctx, int world, int me, int32_t epoch,
                                 int32_t* err_flag, void* stream);
 HOLE_API int hole_shard_pull(hole_ctx* ctx, float* shard, int64_t id_offset, const int32_t* inbox,
                              const int32_t* meta, int world, int64_t cap, int64_t row_base,
-                             void* const* peer_deltas, void* stream);
+                             void* const* peer_deltas, int add_replicated, void* stream);
 
 /* Enable loads/stores from ctx's device to memory of `peer_device` (no-op if already on). */
 HOLE_API int hole_enable_peer_access(hole_ctx* ctx, int peer_device);

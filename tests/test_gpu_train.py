@@ -352,7 +352,12 @@ def test_shard_route_post_push_pull_virtual_ranks(eng_mod, world):
         assert np.array_equal(got[R:R + len(uniqs[k])], table[uniqs[k]])
         assert not got[R + len(uniqs[k]):].any()
     for o in range(world):
-        e.shard_pull(shards[o], R - begins[o], inbox[o], meta[o], world, cap, R, pa(Dl))
+        e.shard_pull(shards[o], R - begins[o], inbox[o], meta[o], world, cap, R, pa(Dl), add_replicated=True)
+    rel = table[:R].copy()
+    for k in range(world):
+        rel += Dl[k].cpu().numpy()[:R]
+    for o in range(world):
+        assert np.array_equal(shards[o].cpu().numpy()[:R], rel)   # replicated block: same order everywhere
     expect = table.copy()
     for k in range(world):                                       # rank order, float32 adds
         expect[uniqs[k]] += Dl[k].cpu().numpy()[R:R + len(uniqs[k])]
