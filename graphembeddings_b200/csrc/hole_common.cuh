@@ -96,6 +96,7 @@ struct hole_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
 
+  int plan_toggle = 0;                 // slot the next hole_train_step_plan call uses
   hole_rank_ws* rank = nullptr;
   // multi-GPU step routing (hole_shard_route): sort scratch for 3B entity keys
   uint32_t* route_buf = nullptr;

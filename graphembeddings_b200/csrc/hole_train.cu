@@ -1383,7 +1383,11 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
     }
   }
   HOLE_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  HOLE_CUDA_TRY(cudaStreamCreateWithFlags(&c->plan_stream, cudaStreamNonBlocking));
+  {   // the plan is small integer work that the next step waits for: highest priority
+    int lo = 0, hi = 0;
+    HOLE_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    HOLE_CUDA_TRY(cudaStreamCreateWithPriority(&c->plan_stream, cudaStreamNonBlocking, hi));
+  }
   HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
   for (int k = 0; k < 2; ++k) {
     HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming));
@@ -1689,7 +1693,10 @@ extern "C" int hole_train_step_plan(hole_ctx* c, const int32_t* pos, const int32
   // the plan stream reads pos / neg_ent once the caller's stream has produced them
   HOLE_CUDA_TRY(cudaEventRecord(c->ev_entry, st));
   HOLE_CUDA_TRY(cudaStreamWaitEvent(c->plan_stream, c->ev_entry, 0));
-  hole_plan& pl = c->plan[0];
+  // alternate between the two plan slots, so that the plan of step s+1 can be built while the
+  // kernels of step s still read theirs
+  hole_plan& pl = c->plan[c->plan_toggle];
+  c->plan_toggle ^= 1;
   rc = plan_steps(c, pl, pos, B, 1, nullptr, nullptr, nullptr, 0, 0, neg_ent, c->plan_stream);
   if (rc) return rc;
   pl.prepared_pos = pos;
@@ -1709,8 +1716,14 @@ extern "C" int hole_train_step_ex(hole_ctx* c, float* table, float* delta_out, c
   int rc = hole_ws_reserve(c, B, 1);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  hole_plan& pl = c->plan[0];
-  if (pl.prepared_B == B && pl.prepared_pos == pos && pl.prepared_neg == neg_ent) {
+  int slot_ix = -1;
+  for (int q = 0; q < 2; ++q)
+    if (c->plan[q].prepared_B == B && c->plan[q].prepared_pos == pos && c->plan[q].prepared_neg == neg_ent)
+      slot_ix = q;
+  const bool planned_ahead = slot_ix >= 0;
+  if (!planned_ahead) slot_ix = (c->plan[0].prepared_B >= 0 && c->plan[1].prepared_B < 0) ? 1 : 0;
+  hole_plan& pl = c->plan[slot_ix];
+  if (planned_ahead) {
     HOLE_CUDA_TRY(cudaStreamWaitEvent(st, pl.ready, 0));     // planned ahead by hole_train_step_plan
   } else {
     // the plan's keys do not depend on the side, and the corruption is the caller's
@@ -1914,7 +1927,9 @@ extern "C" int hole_shard_push(hole_ctx* c, const float* shard, int64_t id_offse
   hole_peer_ptrs tb;
   int rc = peer_ptrs(tb, peer_tables, world);
   if (rc) return rc;
-  const dim3 grid((unsigned)std::max(1, c->sm_count * 8 / world), (unsigned)world);
+  // half occupancy on purpose: the exchange is NVLink-bound, and the side streams' small plan /
+  // routing kernels must find free SM slots while it runs
+  const dim3 grid((unsigned)std::max(1, c->sm_count * 4 / world), (unsigned)world);
   HOLE_DISPATCH(c, hole_shard_push_kernel, grid, 256, (cudaStream_t)stream, shard, id_offset, inbox, meta, cap,
                 row_base, tb, my_table, my_delta, c->nvec, c->row_stride);
   return HOLE_OK;
@@ -1941,7 +1956,7 @@ extern "C" int hole_shard_pull(hole_ctx* c, float* shard, int64_t id_offset, con
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   for (int k = 0; k < world; ++k) {
     HOLE_CHECK_ARG(peer_deltas[k] != nullptr);
-    HOLE_DISPATCH(c, hole_shard_pull_kernel, (unsigned)c->sm_count * 8, 256, (cudaStream_t)stream, shard, id_offset,
+    HOLE_DISPATCH(c, hole_shard_pull_kernel, (unsigned)c->sm_count * 4, 256, (cudaStream_t)stream, shard, id_offset,
                   inbox, meta, k, cap, row_base, static_cast<const float*>(peer_deltas[k]), add_replicated, c->nvec,
                   c->row_stride);
   }

@@ -360,7 +360,7 @@ class P2PRowShardedTrainer(RowShardedTrainer):
                            neg_w=torch.zeros(B3 // 3, dtype=torch.int32, device=dev)) for _ in range(2)]
         self._n_prepared = 0
         self._ahead = None
-        self.prep_stream = torch.cuda.Stream(device=dev)
+        self.prep_stream = torch.cuda.Stream(device=dev, priority=-1)      # small kernels the next step waits for
         self.barrier_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self._epoch = 0
         self._parity = 0

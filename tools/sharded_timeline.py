@@ -36,6 +36,8 @@ for s in range(warm):
     tr.train_step(tri[s], 1, s, 0.2, LR(s), next_pos=tri[s + 1] if "warmahead" in VAR else None)
 torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
 S.EVENTS = [] if os.environ.get('NO_EVENTS') != '1' else None
+if os.environ.get('PROFILE') == '1':
+    be.eng.profile(True)
 marks = []
 prof = None
 if os.environ.get("CPROFILE") == "1" and rank == 0:
@@ -56,6 +58,9 @@ if prof is not None:
     print(buf.getvalue())
 torch.cuda.synchronize()
 n = steps - warm
+if os.environ.get('PROFILE') == '1' and rank == 0:
+    k1, k3, ns = be.eng.profile_read()
+    print(f"  library events: K1 {k1 / ns * 1e3:.1f} us, K3 {k3 / ns * 1e3:.1f} us per step ({ns} steps)")
 tot = marks[0].elapsed_time(marks[-1]) / n * 1e3
 acc = {}
 for name, a, b in (S.EVENTS or []):
