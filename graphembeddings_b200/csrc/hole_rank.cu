@@ -290,6 +290,7 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const int a_lo_off = p.num_kb * A_KB_BYTES;   // query lo part sits after the hi part
       int stage = 0; uint32_t phase = 0, a_phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -303,26 +304,38 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&sl->tmem_empty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_addr = tmem_base + (uint32_t)acc * BN;
+          int kk = 0;                                // kb modulo num_kb: k-block inside its operand part
           for (int kb = 0; kb < nkb_all; ++kb) {
             mbar_wait(&sl->full[stage], phase);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(sB + (size_t)stage * B_KB_BYTES);
-            // candidate k-block kb of part pb meets query part 0 (hi); a candidate hi block also
-            // meets the query lo block: hi.hi + lo.hi + hi.lo
-            const int pb = kb / p.num_kb, kk = kb - pb * p.num_kb;
-            const int na = (p.parts == 2 && pb == 0) ? 2 : 1;
+            // The issuing thread is on the critical path (the k-block's MMAs must be queued before
+            // the previous block's retire), so both loops below are kept free of divisions and
+            // nested runtime loops: measured 59 -> 52 ms on 100 k x 1.2 M against a generic loop.
+            const uint32_t a_addr = smem_u32(sA + (size_t)kk * A_KB_BYTES);
             const int nk = (kk == p.num_kb - 1) ? p.last_kb_mmas : BK / UMMA_K;   // skip all-zero slices
-            for (int ja = 0; ja < na; ++ja) {
-              const uint32_t a_addr = smem_u32(sA + (size_t)(ja * p.num_kb + kk) * A_KB_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (k < nk) {
+                const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2);
+                const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2);
+                umma_bf16(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            if (p.parts == 2 && kb < p.num_kb) {
+              // split-bf16: a candidate hi block also meets the query lo block (hi.hi + lo.hi + hi.lo;
+              // the candidate lo blocks, kb >= num_kb, meet the query hi block only)
+              const uint32_t a_lo = a_addr + (uint32_t)a_lo_off;
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
                 if (k < nk) {
-                  const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2);
+                  const uint64_t da = umma_desc_sw128(a_lo + k * UMMA_K * 2);
                   const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2);
-                  umma_bf16(d_addr, da, db, idesc, (kb | ja | k) != 0 ? 1u : 0u);
+                  umma_bf16(d_addr, da, db, idesc, 1u);
                 }
               }
             }
+            if (++kk == p.num_kb) kk = 0;
             umma_commit(&sl->empty[stage]);          // frees the smem slot when the MMAs retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
