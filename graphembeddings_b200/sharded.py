@@ -21,6 +21,7 @@ with gloo; the CUDA backend calls libhole_b200 through HoleEngine.
 """
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -294,6 +295,22 @@ class RowShardedTrainer:
         return raw, filt
 
 
+class PeerMemoryUnavailable(RuntimeError):
+    """The GPUs of this job cannot map each other's memory (no P2P / CUDA IPC)."""
+
+
+def make_trainer(n_relations, n_entities, dim, backend, dist, log=None):
+    """P2PRowShardedTrainer when every rank can map every other rank's buffers, else (all ranks
+    together) the NCCL all-to-all RowShardedTrainer.  HOLE_SHARDED_NCCL=1 forces the latter."""
+    if os.environ.get("HOLE_SHARDED_NCCL") != "1" and hasattr(backend, "eng"):
+        try:
+            return P2PRowShardedTrainer(n_relations, n_entities, dim, backend, dist)
+        except PeerMemoryUnavailable as e:
+            if log:
+                log(f"peer memory unavailable, using NCCL all-to-alls: {e}")
+    return RowShardedTrainer(n_relations, n_entities, dim, backend, dist)
+
+
 class _Prepared:
     """Table-independent part of one step (corruption, routing, update plan), built ahead."""
     __slots__ = ("key", "side", "uniq", "cuts", "pos_w", "neg_w", "done")
@@ -334,7 +351,7 @@ class P2PRowShardedTrainer(RowShardedTrainer):
         mine = [backend.W, backend.D, self.inbox, self.meta, self.flags]
         everyone = [None] * G
         dist.all_gather_object(everyone, ([reduce_tensor(t) for t in mine], dev.index))
-        peers = []
+        peers, failure = [], None
         for k, (handles, dev_k) in enumerate(everyone):
             if k == self.my_rank:
                 peers.append(mine)
@@ -344,8 +361,21 @@ class P2PRowShardedTrainer(RowShardedTrainer):
             # local to torch while its pages live on GPU k -- kernels launched on my device
             # reach it over NVLink.  Opened on device k instead, our kernels fault on it
             # (tools/p2p_diag.py, variant A).
-            backend.eng.enable_peer_access(dev_k)
-            peers.append([fn(*(list(a[:6]) + [dev.index] + list(a[7:]))) for fn, a in handles])
+            try:
+                backend.eng.enable_peer_access(dev_k)
+                peers.append([fn(*(list(a[:6]) + [dev.index] + list(a[7:]))) for fn, a in handles])
+            except Exception as e:                       # no P2P / IPC between these two GPUs
+                failure = f"rank {self.my_rank} cannot map rank {k}'s buffers: {e}"
+                break
+        # every rank must reach the same verdict, or the first barrier kernel would spin
+        verdicts = [None] * G
+        dist.all_gather_object(verdicts, failure)
+        bad = [v for v in verdicts if v]
+        if bad:
+            raise PeerMemoryUnavailable("; ".join(bad))
+        self._finish_init(backend, dist, peers, dev, G)
+
+    def _finish_init(self, backend, dist, peers, dev, G):
         self._peers = peers                                         # keeps the mappings alive
         pa = backend.eng.peer_array
         self.peer_W = pa([p[0] for p in peers])
@@ -459,8 +489,9 @@ def bench(args, dist, rank, world, local_rank):
     kg = D.make_config(B_.WORKLOAD, n_triples=(K + W) * Bl * world)
     off, ids = D.build_type_csr(kg.type_of)
     be = CudaBackend(kg.n_relations, kg.dim, Bl, local_rank, kg.type_of, off, ids)
-    cls = RowShardedTrainer if os.environ.get("HOLE_SHARDED_NCCL") == "1" else P2PRowShardedTrainer
-    tr = cls(kg.n_relations, kg.n_entities, kg.dim, be, dist).load_embeddings(kg.E)
+    tr = make_trainer(kg.n_relations, kg.n_entities, kg.dim, be, dist,
+                      log=lambda m: print(m, file=sys.stderr) if rank == 0 else None).load_embeddings(kg.E)
+    cls = type(tr)
     # step s, rank r takes triples [(s*world + r)*Bl, +Bl)
     mine = torch.from_numpy(kg.triples).view(K + W, world, Bl, 3)[:, rank].contiguous()
     dev_tri = mine.cuda()

@@ -19,10 +19,10 @@ Bl, steps = 2048, int(os.environ.get("STEPS", 4))
 kg = D.synthetic_kg(9, 50000, Bl * world * steps, 5, 256, seed=77, trained_scale=True)
 off, ids = D.build_type_csr(kg.type_of)
 be = CudaBackend(kg.n_relations, kg.dim, Bl, local, kg.type_of, off, ids)
-cls = RowShardedTrainer if os.environ.get("HOLE_SHARDED_NCCL") == "1" else P2PRowShardedTrainer
-tr = cls(kg.n_relations, kg.n_entities, kg.dim, be, dist).load_embeddings(kg.E)
+from graphembeddings_b200.sharded import make_trainer
+tr = make_trainer(kg.n_relations, kg.n_entities, kg.dim, be, dist, log=print).load_embeddings(kg.E)
 if rank == 0:
-    print("trainer:", cls.__name__)
+    print("trainer:", type(tr).__name__)
 ahead = os.environ.get("NO_AHEAD") != "1"        # work one step ahead on the side stream (host tensors in)
 
 
