@@ -233,13 +233,16 @@ struct SmemLayout {
 };
 
 // ------------------------------------------------------------------------------------ kernel
+// PARTS = 1 plain bf16, 2 split-bf16 (compile-time, so that the bf16 instantiation's single-thread
+// producer / issue loops carry none of the split mode's bookkeeping)
+template <int PARTS>
 __global__ void __launch_bounds__(RANK_THREADS, 1)
 hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const RankParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms repeat every 1024 bytes: align the operand area explicitly
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int nkb_all = p.num_kb * p.parts;                   // k-blocks of a whole operand row
+  const int nkb_all = p.num_kb * PARTS;                     // k-blocks of a whole operand row
   uint8_t* sA = smem;                                       // nkb_all x 16 KB
   uint8_t* sB = smem + (size_t)nkb_all * A_KB_BYTES;        // stages x 32 KB
   SmemLayout* sl = reinterpret_cast<SmemLayout*>(sB + (size_t)p.stages * B_KB_BYTES);
@@ -322,7 +325,7 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_bf16(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
               }
             }
-            if (p.parts == 2 && kb < p.num_kb) {
+            if (PARTS == 2 && kb < p.num_kb) {
               // split-bf16: a candidate hi block also meets the query lo block (hi.hi + lo.hi + hi.lo;
               // the candidate lo blocks, kb >= num_kb, meet the query hi block only)
               const uint32_t a_lo = a_addr + (uint32_t)a_lo_off;
@@ -335,7 +338,7 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
               }
             }
-            if (++kk == p.num_kb) kk = 0;
+            if (PARTS == 2) { if (++kk == p.num_kb) kk = 0; } else { kk = kb + 1; }
             umma_commit(&sl->empty[stage]);          // frees the smem slot when the MMAs retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -852,7 +855,8 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
     w->q_cap = (size_t)Qpad * Kall;
   }
   if (!w->attr_set) {
-    HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_rank_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_rank_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_rank_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     w->attr_set = true;
   }
@@ -893,7 +897,8 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
       hole_rank_pair_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
     } else {
       const int grid = std::min(p.m_tiles, c->sm_count);
-      hole_rank_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+      if (parts == 2) hole_rank_kernel<2><<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+      else hole_rank_kernel<1><<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
     }
     HOLE_LAUNCHED();
   }
@@ -919,7 +924,8 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
       hole_rank_pair_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
     } else {
       const int grid = std::min(n_items, c->sm_count);
-      hole_rank_kernel<<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+      if (parts == 2) hole_rank_kernel<2><<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
+      else hole_rank_kernel<1><<<grid, RANK_THREADS, smem_bytes, st>>>(mapA, mapB, p);
     }
     HOLE_LAUNCHED();
   }
