@@ -1096,18 +1096,22 @@ __global__ void hole_shard_post_kernel(const int32_t* __restrict__ uniq, const i
 // flag[me] of rank k (release, system scope) and spins until flag[k] of my own array reaches
 // `epoch` (acquire).  Epochs only grow, so there is nothing to reset.  Everything the earlier
 // kernels of my stream wrote to peer memory is visible to a peer's kernels that follow its
-// barrier.  A peer that never arrives trips a 10 s timeout: *err is set and the kernel leaves.
+// barrier.  A peer that never arrives trips a 10 s timeout: *err is set and the kernel leaves;
+// every later barrier of this rank then returns at once (the host raises in check_barriers).
 __global__ void hole_shard_barrier_kernel(int world, int me, int epoch, hole_peer_ptrs flags,
                                           int* __restrict__ err) {
   const int k = threadIdx.x;
   if (k >= world) return;
+  // once a barrier has timed out the run is lost: later barriers still signal (so that healthy
+  // peers do not wait for us) but never wait again -- the job drains in seconds, not hours
+  const bool dead = *reinterpret_cast<volatile int*>(err) != 0;
   __threadfence_system();
   int* theirs = static_cast<int*>(flags.p[k]) + me;
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
   const int* mine = static_cast<const int*>(flags.p[me]) + k;
   unsigned long long t0;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-  while (true) {
+  while (!dead) {
     int v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
     if (v - epoch >= 0) break;
