@@ -154,10 +154,13 @@ class HoleEngine:
                                           _ptr(loss), None, _stream()))
         return loss
 
-    def train_step_logloss(self, triples, seed, step, lr, l2=0.0, negative_ratio=1, want_corruption=False):
+    def train_step_logloss(self, triples, seed, step, lr, l2=0.0, negative_ratio=1, want_corruption=False,
+                           want_l2_loss=None):
         """The --log_loss step (holE.py:194-196, 206-220, 296).  Returns (loss [(1+k), B] device,
         l2_loss device scalar = sum(E_old^2)/2) -- the reference's per-row loss is
-        loss + l2 * l2_loss -- and, with want_corruption, also (sides list, neg [k, B] device)."""
+        loss + l2 * l2_loss -- and, with want_corruption, also (sides list, neg [k, B] device).
+        The scalar costs a pass over the whole table: by default it is only computed when
+        l2 != 0 (it is zero otherwise); want_l2_loss=True forces it."""
         t = self._triples(triples)
         B, k = t.shape[0], int(negative_ratio)
         if getattr(self, "_delta_ws", None) is None or self._delta_ws.shape != self.table.shape:
@@ -169,7 +172,8 @@ class HoleEngine:
         check(self.lib.hole_train_step_logloss(
             self._ctx, _ptr(self.table), _ptr(self._delta_ws), _ptr(t), B, k, _ptr(self.type_of),
             _ptr(self.csr_off), _ptr(self.csr_ids), int(seed), int(step), float(lr), float(l2), _ptr(loss),
-            _ptr(l2_loss), None if neg is None else _ptr(neg), sides, _stream()))
+            _ptr(l2_loss) if (want_l2_loss or (want_l2_loss is None and l2 != 0.0)) else None,
+            None if neg is None else _ptr(neg), sides, _stream()))
         if want_corruption:
             return loss, l2_loss, list(sides), neg
         return loss, l2_loss

@@ -245,7 +245,8 @@ def test_logloss_step_matches_oracle(eng_mod, dim, k, l2):
     E = kg.E.copy()
     for step in range(3):
         pos = kg.triples[step * B:(step + 1) * B]
-        loss, l2_loss, sides, neg = e.train_step_logloss(pos, seed, step, lr, l2, k, want_corruption=True)
+        loss, l2_loss, sides, neg = e.train_step_logloss(pos, seed, step, lr, l2, k, want_corruption=True,
+                                                         want_l2_loss=True)
         neg_h = neg.cpu().numpy()
         for j in range(k):
             side_o, neg_o = O.corrupt(pos, kg.type_of, off, ids, seed, step * k + j)
