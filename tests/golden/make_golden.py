@@ -170,7 +170,31 @@ def gen_train_step_golden():
     print("train_step_oracle.npz written")
 
 
+def gen_logloss_step_golden():
+    """--log_loss step of the oracle (holE.py:194-196, 206-220): k = 2 corrupt batches drawn with
+    virtual steps step*k + j, l2 = 1e-3, fp32 and fp64."""
+    from oracle import hole_oracle as O
+    from graphembeddings_b200 import data as D
+    kg = D.synthetic_kg(n_relations=7, n_entities=300, n_triples=64, n_types=5, dim=20,
+                        seed=13, trained_scale=True)
+    pos = kg.triples[:64]
+    off, ids = O.build_type_csr(kg.type_of)
+    k, seed, step, lr, l2 = 2, 5, 3, 0.05, 1e-3
+    drawn = [O.corrupt(pos, kg.type_of, off, ids, seed=seed, step=step * k + j) for j in range(k)]
+    sides = [d[0] for d in drawn]
+    negs = [d[1] for d in drawn]
+    E32 = kg.E.copy()
+    loss32, l2_32 = O.logloss_step(E32, pos, negs, sides, lr, l2, np.float32)
+    E64 = kg.E.astype(np.float64)
+    loss64, l2_64 = O.logloss_step(E64, pos, negs, sides, lr, l2, np.float64)
+    np.savez_compressed(os.path.join(HERE, "logloss_step_oracle.npz"), E0=kg.E, pos=pos, type_of=kg.type_of,
+                        k=k, seed=seed, step=step, lr=lr, l2=l2, sides=np.array(sides), negs=np.array(negs),
+                        loss32=loss32, l2_32=l2_32, E32=E32, loss64=loss64, l2_64=l2_64, E64=E64)
+    print("logloss_step_oracle.npz written")
+
+
 if __name__ == "__main__":
     gen_ranking_golden()
     gen_fb15k_fixtures()
     gen_train_step_golden()
+    gen_logloss_step_golden()

@@ -165,6 +165,21 @@ def test_golden_fixture_step(eng_mod, golden_dir):
         assert np.abs(got - z[f"E64_{step}"]).max() <= ROW_ATOL + ROW_RTOL
 
 
+def test_logloss_golden_fixture_step(eng_mod, golden_dir):
+    """The committed fixture of the oracle's --log_loss step (tests/golden/make_golden.py):
+    corruption bit-exact, loss rows and updated table within the fp32 tolerances."""
+    z = np.load(os.path.join(golden_dir, "logloss_step_oracle.npz"))
+    E0, pos, type_of = z["E0"], z["pos"], z["type_of"]
+    off, ids = D.build_type_csr(type_of)
+    e = eng_mod.HoleEngine(E0.shape[0], E0.shape[1]).set_embeddings(E0).set_types(type_of, off, ids)
+    loss, l2_loss, sides, neg = e.train_step_logloss(pos, int(z["seed"]), int(z["step"]), float(z["lr"]),
+                                                     float(z["l2"]), int(z["k"]), want_corruption=True)
+    assert sides == [int(x) for x in z["sides"]] and np.array_equal(neg.cpu().numpy(), z["negs"])
+    assert np.abs(loss.cpu().numpy() - z["loss64"]).max() <= 2e-6
+    assert abs(float(l2_loss) - float(z["l2_64"])) <= 1e-5 * float(z["l2_64"])
+    assert np.abs(e.embeddings().cpu().numpy() - z["E64"]).max() <= ROW_ATOL + ROW_RTOL
+
+
 @pytest.mark.parametrize("dim,B", [(150, 512), (256, 1000)])
 def test_multi_step_matches_oracle_loop(eng_mod, dim, B):
     """hole_train_steps (device-side loop incl. Philox corruption) vs the oracle loop."""

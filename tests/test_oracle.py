@@ -230,6 +230,23 @@ def test_train_step_golden_fixture(golden_dir):
         np.testing.assert_allclose(E, z[f"E64_{step}"], rtol=0, atol=2e-6)
 
 
+def test_logloss_step_golden_fixture(golden_dir):
+    z = np.load(os.path.join(golden_dir, "logloss_step_oracle.npz"))
+    off, ids = O.build_type_csr(z["type_of"])
+    k, seed, step = int(z["k"]), int(z["seed"]), int(z["step"])
+    for j in range(k):
+        side, neg = O.corrupt(z["pos"], z["type_of"], off, ids, seed=seed, step=step * k + j)
+        assert side == int(z["sides"][j]) and np.array_equal(neg, z["negs"][j])
+    E = z["E0"].copy()
+    loss, l2_loss = O.logloss_step(E, z["pos"], list(z["negs"]), [int(x) for x in z["sides"]],
+                                   float(z["lr"]), float(z["l2"]), np.float32)
+    np.testing.assert_allclose(loss, z["loss32"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(E, z["E32"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(E, z["E64"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(loss, z["loss64"], rtol=0, atol=1e-6)
+    assert abs(float(l2_loss) - float(z["l2_64"])) <= 1e-6 * float(z["l2_64"])
+
+
 # ---------------------------------------------------------------- corruption
 
 
