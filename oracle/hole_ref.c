@@ -153,6 +153,69 @@ double hole_ref_train_step(float* E, int64_t N, int D, const int32_t* pos, const
   return total;
 }
 
+/* One --log_loss training step in place (holE.py:194-196, 206-220, 296).
+ * Loss rows: B positives (label +1), then k corrupt batches (label -1); batch j replaces the
+ * head (sides[j] = 1) or the tail of every positive by neg_ent[j*B + i].  Row loss =
+ * log(1 + exp(-label * s)); the L2 scalar  l2_loss = sum(E^2)/2  (tf.nn.l2_loss over the whole
+ * variable) is returned through *l2_loss_out and is NOT added to loss_out.  Update:
+ * E -= lr * (sum of the sparse score gradients taken at the old table + (1+k) B l2 E).
+ * G: scratch (1+k)*3*B*D floats, idx: (1+k)*3*B ints.  loss_out: [(1+k)*B]. */
+void hole_ref_logloss_step(float* E, int64_t N, int D, const int32_t* pos, const int32_t* neg_ent,
+                           const int32_t* sides, int k, int64_t B, float lr, float l2, float* loss_out,
+                           double* l2_loss_out, float* G, int32_t* idx) {
+  const int H = D / 2;
+  const int64_t terms = (int64_t)(1 + k) * B;
+  double l2sum = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : l2sum)
+  for (int64_t p = 0; p < N * (int64_t)D; ++p) l2sum += (double)E[p] * (double)E[p];
+  if (l2_loss_out) *l2_loss_out = 0.5 * l2sum;
+#pragma omp parallel
+  {
+    float* y = (float*)malloc(sizeof(float) * 3 * D);
+#pragma omp for schedule(static)
+    for (int64_t q = 0; q < terms; ++q) {
+      const int64_t j = q / B, i = q % B;           /* j = 0: positives; j >= 1: corrupt batch j-1 */
+      int h = pos[3 * i], t = pos[3 * i + 1], r = pos[3 * i + 2];
+      float label = 1.f;
+      if (j > 0) {
+        const int n = neg_ent[(j - 1) * B + i];
+        if (sides[j - 1]) h = n; else t = n;
+        label = -1.f;
+      }
+      clip_row(E + (size_t)h * D, y, D); clip_row(E + (size_t)t * D, y + D, D);
+      clip_row(E + (size_t)r * D, y + 2 * D, D);
+      const float sc = score_rows(y, y + D, y + 2 * D, H);
+      loss_out[q] = logf(1.0f + expf(-label * sc));
+      const float g = -label * sigmoidf_(-label * sc);     /* d/ds log(1 + exp(-label s)) */
+      side_grads(E, D, h, t, r, g, y, G + (size_t)(3 * q) * D, G + (size_t)(3 * q + 1) * D,
+                 G + (size_t)(3 * q + 2) * D);
+      idx[3 * q] = h; idx[3 * q + 1] = t; idx[3 * q + 2] = r;
+    }
+    free(y);
+  }
+  /* dense decay first (it reads the old table), then the sparse sum in term order */
+  const float decay = lr * (float)terms * l2;
+  if (decay != 0.f) {
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < N * (int64_t)D; ++p) E[p] -= decay * E[p];
+  }
+#pragma omp parallel
+  {
+#ifdef _OPENMP
+    const int nt = omp_get_num_threads(), me = omp_get_thread_num();
+#else
+    const int nt = 1, me = 0;
+#endif
+    for (int64_t p = 0; p < 3 * terms; ++p) {
+      const int row = idx[p];
+      if (row % nt != me) continue;
+      float* e = E + (size_t)row * D;
+      const float* g = G + (size_t)p * D;
+      for (int c = 0; c < D; ++c) e[c] -= g[c] * lr;
+    }
+  }
+}
+
 /* Rank counts: for each query, # candidates j in [cb, ce) with (s_j, j) < (s_true, true).
  * Yc = pre-clipped candidate rows [ce-cb, D]; qv = query vectors [Q, D] (App. A.4).
  * filter CSR may be NULL. */

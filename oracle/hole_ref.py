@@ -65,6 +65,26 @@ def train_step(E, pos, neg_ent, side, margin, lr, scratch=None):
     return float(tot), sc.loss
 
 
+def logloss_step(E, pos, neg_ents, sides, lr, l2=0.0):
+    """C port of hole_oracle.logloss_step, in place on E (float32 C-contiguous).
+    Returns (loss [(1+k), B], l2_loss)."""
+    assert E.dtype == np.float32 and E.flags.c_contiguous
+    pos = np.ascontiguousarray(pos, np.int32)
+    neg = np.ascontiguousarray(np.stack([np.asarray(n) for n in neg_ents]), np.int32)
+    sd = np.ascontiguousarray(sides, np.int32)
+    k, B, D = len(sd), len(pos), E.shape[1]
+    loss = np.empty(((1 + k), B), np.float32)
+    G = np.empty(((1 + k) * 3 * B, D), np.float32)
+    idx = np.empty((1 + k) * 3 * B, np.int32)
+    l2_loss = C.c_double(0.0)
+    lib = load()
+    lib.hole_ref_logloss_step.restype = None
+    lib.hole_ref_logloss_step(_p(E), C.c_int64(E.shape[0]), C.c_int(D), _p(pos), _p(neg), _p(sd), C.c_int(k),
+                              C.c_int64(B), C.c_float(lr), C.c_float(l2), _p(loss), C.byref(l2_loss), _p(G),
+                              _p(idx))
+    return loss, l2_loss.value
+
+
 def clip_rows(E):
     E = np.ascontiguousarray(E, np.float32)
     Y = np.empty_like(E)

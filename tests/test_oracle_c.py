@@ -28,6 +28,23 @@ def test_train_step_matches_numpy_oracle_both_sides():
         assert np.abs(E - kg.E).max() > 1e-4
 
 
+def test_logloss_step_matches_numpy_oracle():
+    """Second, independent implementation of the --log_loss step (holE.py:194-196, 206-220)."""
+    kg = D.synthetic_kg(6, 300, 1500, 4, 64, seed=6, trained_scale=True, zipf_entities=True)
+    off, ids = O.build_type_csr(kg.type_of)
+    for k, l2 in ((1, 0.0), (3, 1e-5)):
+        drawn = [O.corrupt(kg.triples, kg.type_of, off, ids, 9, 4 * k + j) for j in range(k)]
+        sides, negs = [d[0] for d in drawn], [d[1] for d in drawn]
+        E = kg.E.copy()
+        loss, l2_loss = R.logloss_step(E, kg.triples, negs, sides, 0.05, l2)
+        E64 = kg.E.astype(np.float64)
+        loss64, l2_64 = O.logloss_step(E64, kg.triples, negs, sides, 0.05, l2, np.float64)
+        assert np.abs(loss - loss64).max() < 2e-6
+        assert abs(l2_loss - float(l2_64)) < 1e-6 * float(l2_64)
+        assert np.abs(E - E64).max() < 2e-5
+        assert np.abs(E - kg.E).max() > 1e-4
+
+
 def test_rank_matches_numpy_oracle():
     kg = D.synthetic_kg(5, 600, 80, 3, 32, seed=5, trained_scale=True)
     cand = np.arange(kg.n_relations, kg.n_rows)
