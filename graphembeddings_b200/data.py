@@ -144,16 +144,18 @@ def build_filter_csr(queries, known_triples, side):
     qkey = qq * big + queries[:, 2]
     order = np.lexsort((kv, kkey))
     kkey, kv = kkey[order], kv[order]
+    if len(kkey):                                   # drop repeated (key, value) pairs once, globally
+        keep = np.ones(len(kkey), dtype=bool)
+        keep[1:] = (kkey[1:] != kkey[:-1]) | (kv[1:] != kv[:-1])
+        kkey, kv = kkey[keep], kv[keep]
     lo = np.searchsorted(kkey, qkey, side="left")
     hi = np.searchsorted(kkey, qkey, side="right")
+    cnt = hi - lo
     off = np.zeros(len(queries) + 1, dtype=np.int64)
-    chunks = []
-    for q in range(len(queries)):
-        ids = np.unique(kv[lo[q]:hi[q]])
-        chunks.append(ids)
-        off[q + 1] = off[q] + len(ids)
-    ids = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.int64)
-    return off, ids.astype(np.int32)
+    np.cumsum(cnt, out=off[1:])
+    # ids = concatenation of kv[lo[q]:hi[q]] over q, without a Python loop
+    take = np.arange(off[-1], dtype=np.int64) - np.repeat(off[:-1] - lo, cnt)
+    return off, kv[take].astype(np.int32)
 
 
 # --------------------------------------------------------------------------------------
