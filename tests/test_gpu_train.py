@@ -165,6 +165,50 @@ def test_golden_fixture_step(eng_mod, golden_dir):
         assert np.abs(got - z[f"E64_{step}"]).max() <= ROW_ATOL + ROW_RTOL
 
 
+@pytest.mark.parametrize("nm,steps,margin", [("A", 3, 0.2), ("B", 2, 0.2), ("D", 2, 0.01)])
+def test_reference_source_fixture_hinge_steps(eng_mod, golden_dir, nm, steps, margin):
+    """tests/golden/tfshim_step.npz: the REFERENCE's own evaluate_batch + minimize (holE.py:205-234,
+    291-296) executed on the TensorFlow shim (tests/golden/make_tfshim_golden.py).  Identical
+    triples, identical corruption ids (checked bit-exact against the device sampler), chained
+    steps: sigma / loss <= 1e-6 / 2e-6, rows <= 2e-6 + 1e-5|x| per step vs the fp64 reference run,
+    and within 4e-6 of the reference's own fp32 run."""
+    z = np.load(os.path.join(golden_dir, "tfshim_step.npz"))
+    E0, pos, type_of = z[nm + "_E0"], z[nm + "_pos"], z[nm + "_type_of"]
+    off, ids = D.build_type_csr(type_of)
+    e = eng_mod.HoleEngine(E0.shape[0], E0.shape[1]).set_embeddings(E0).set_types(type_of, off, ids)
+    seed = {"A": 5, "B": 6, "D": 8}[nm]
+    for s in range(steps):
+        side, neg = e.corrupt_batch(pos, seed, s)
+        assert side == int(z[f"{nm}_f64_side{s}"]) and np.array_equal(neg.cpu().numpy(), z[f"{nm}_f64_neg{s}"])
+        loss, vp, vn = e.train_step(pos, neg, side, margin, float(z[f"{nm}_f32_lr{s}"]), return_sigma=True)
+        assert np.abs(vp.cpu().numpy() - z[f"{nm}_f64_vp{s}"]).max() <= SIGMA_ATOL
+        assert np.abs(vn.cpu().numpy() - z[f"{nm}_f64_vn{s}"]).max() <= SIGMA_ATOL
+        assert np.abs(loss.cpu().numpy() - z[f"{nm}_f64_loss{s}"]).max() <= 2 * SIGMA_ATOL
+        got = e.embeddings().cpu().numpy()
+        want = z[f"{nm}_f64_E{s}"]
+        assert (np.abs(got - want) <= (s + 1) * (ROW_ATOL + ROW_RTOL * np.abs(want))).all()
+        assert np.abs(got - z[f"{nm}_f32_E{s}"]).max() <= (s + 1) * 4e-6
+
+
+def test_reference_source_fixture_logloss_steps(eng_mod, golden_dir):
+    """Same fixture, --log_loss branch (holE.py:194-196, 206-220): k = 2, l2 = 1e-3, two chained steps."""
+    z = np.load(os.path.join(golden_dir, "tfshim_step.npz"))
+    E0, pos, type_of = z["C_E0"], z["C_pos"], z["C_type_of"]
+    off, ids = D.build_type_csr(type_of)
+    e = eng_mod.HoleEngine(E0.shape[0], E0.shape[1]).set_embeddings(E0).set_types(type_of, off, ids)
+    for s in range(2):
+        loss, l2_loss, sides, neg = e.train_step_logloss(pos, 7, s, float(z[f"C_f32_lr{s}"]), 1e-3, 2,
+                                                         want_corruption=True)
+        assert sides == [int(x) for x in z[f"C_f64_sides{s}"]]
+        assert np.array_equal(neg.cpu().numpy(), z[f"C_f64_negs{s}"])
+        l2_ref = float(z[f"C_f64_l2loss{s}"])
+        assert abs(float(l2_loss) - l2_ref) <= 1e-5 * l2_ref
+        want = z[f"C_f64_loss{s}"] - 1e-3 * l2_ref          # the reference adds the scalar to every row
+        assert np.abs(loss.cpu().numpy() - want).max() <= 2e-6
+        got = e.embeddings().cpu().numpy()
+        assert (np.abs(got - z[f"C_f64_E{s}"]) <= (s + 1) * (ROW_ATOL + ROW_RTOL * np.abs(z[f"C_f64_E{s}"]))).all()
+
+
 def test_logloss_golden_fixture_step(eng_mod, golden_dir):
     """The committed fixture of the oracle's --log_loss step (tests/golden/make_golden.py):
     corruption bit-exact, loss rows and updated table within the fp32 tolerances."""
