@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("HOLE_B200_LIB", os.path.join(_HERE, "libhole_b200.so"
 
 HOLE_SIDE_TAIL, HOLE_SIDE_HEAD, HOLE_SIDE_BOTH = 0, 1, 2
 HOLE_RANK_BF16, HOLE_RANK_BF16X3 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class HoleError(RuntimeError):
@@ -38,9 +38,15 @@ SIGNATURES = {
     "hole_train_step_logloss": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p, _p, _u64, _u64, _f32, _f32, _p, _p, _p, _p, _p]),
     "hole_shard_route": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _int, _p, _p, _p, _p, _p]),
     "hole_shard_post": (_int, [_p, _p, _p, _int, _int, _i64, _p, _p, _p]),
-    "hole_shard_push": (_int, [_p, _p, _i64, _p, _p, _int, _i64, _i64, _p, _p, _p, _p]),
-    "hole_shard_barrier": (_int, [_p, _int, _int, _i32, _p, _p, _p]),
-    "hole_shard_pull": (_int, [_p, _p, _i64, _p, _p, _int, _i64, _i64, _p, _int, _p]),
+    "hole_shard_init": (_int, [_p, _int, _int, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, C.c_double,
+                                _p, _p, _p]),
+    "hole_shard_prepare": (_int, [_p, _p, _i64, _u64, _u64, _p]),
+    "hole_shard_step": (_int, [_p, _p, _i64, _u64, _u64, _f32, _f32, _p, _p]),
+    "hole_shard_step_compute": (_int, [_p, _p, _i64, _u64, _u64, _f32, _f32, _p, _p]),
+    "hole_shard_step_apply": (_int, [_p, _p]),
+    "hole_shard_steps": (_int, [_p, _p, _i64, _i64, _u64, _u64, _f32, _p, _p, _p]),
+    "hole_shard_steps_host": (_int, [_p, _p, _i64, _i64, _u64, _u64, _f32, _p, _p, _p]),
+    "hole_shard_poll": (_int, [_p, C.POINTER(_int), _p]),
     "hole_enable_peer_access": (_int, [_p, _int]),
     "hole_gather_rows": (_int, [_p, _p, _p, _i64, _p, _i64, _p]),
     "hole_add_rows": (_int, [_p, _p, _p, _i64, _p, _i64, _p]),

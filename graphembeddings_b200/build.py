@@ -32,6 +32,18 @@ def _fingerprint():
     return h.hexdigest()
 
 
+def build_variant(out, extra_flags, verbose=False):
+    """A/B experiments: the same sources with extra nvcc flags into another .so (selected at run
+    time with HOLE_B200_LIB=<out>).  Not used by the product."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-shared", "-o", out, *srcs]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+    return out
+
+
 def build(force=False, verbose=False):
     fp = _fingerprint()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):

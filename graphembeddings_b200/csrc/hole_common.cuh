@@ -39,7 +39,8 @@ int hole_set_error(int code, const char* fmt, ...);
 // ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
-struct hole_rank_ws;   // hole_rank.cu
+struct hole_rank_ws;       // hole_rank.cu
+struct hole_shard_state;   // hole_shard.cuh
 
 // Update plan of a chunk of S steps (integer-only; built ahead of the steps that use it).
 struct hole_plan {
@@ -76,7 +77,15 @@ struct hole_ctx {
   int gs = 0, v = 0;   // lanes per row and float4s per lane per half (kernel variant)
   int sm_count = 0;
   int key_bits = 0;    // bits needed for a row id
-  int k1_smem = 0;     // dynamic shared memory of K1 (row landing buffers)
+  int k1_smem = 0;     // dynamic shared memory of the first-generation K1 body (--log_loss passes)
+  bool k1_ready = false;   // kernel attributes set (lazily, on the first training call)
+  int k1_gen = 2;      // 2 = hole_k1_kernel (bulk-copy pipeline); 1 = first-generation kernel (A/B)
+  int k1_block = 256;  // threads per K1 block
+  int k1v2_smem = 0;   // dynamic shared memory of hole_k1_kernel at k1_block threads
+  int k1_groups = 0;   // lane groups resident on the whole GPU (sizes T, the triples per group)
+  int ramp_first = 0;  // hole_train_steps: steps in the first planned chunk, then x ramp_factor; 0 = no ramp
+  int ramp_factor = 4; //   (HOLE_PLAN_RAMP=first,factor; measured slower than no ramp, profiles/r02_train_ab.txt:
+                       //   a plan's latency is ~120 us of dependent launches whatever its size)
   int row_passes = 1;  // 8-bit radix passes for row keys
   int rel_passes = 1;  // ... for relation ids (hole_ctx_set_relations)
 
@@ -98,6 +107,7 @@ struct hole_ctx {
 
   int plan_toggle = 0;                 // slot the next hole_train_step_plan call uses
   hole_rank_ws* rank = nullptr;
+  hole_shard_state* shard_state = nullptr;   // row-sharded step (hole_shard_init)
   // multi-GPU step routing (hole_shard_route): sort scratch for 3B entity keys
   uint32_t* route_buf = nullptr;
   int64_t route_cap = 0;
@@ -113,6 +123,9 @@ struct hole_ctx {
 constexpr int HOLE_K1_ACCUMULATE = 4;
 constexpr int HOLE_TREE_C = 32;      // fan-in of the deterministic gradient combine tree
 constexpr int HOLE_TREE_LEVELS = 6;  // 32^6 > any 4B
+
+// device addresses of one buffer on every rank (peer memory mapped with CUDA IPC)
+struct hole_peer_ptrs { void* p[HOLE_MAX_RANKS]; };
 
 int hole_ws_reserve(hole_ctx* ctx, int64_t B, int64_t S);
 void hole_rank_ws_free(hole_ctx* ctx);

@@ -115,7 +115,11 @@ __device__ __forceinline__ void row_clip(Row<V>& x, float inv) {
   for (int k = 0; k < 4 * V; ++k) { x.re[k] *= sc; x.im[k] *= sc; }
 }
 
+#ifdef HOLE_FAST_SIGMOID   // A/B only: ex2.approx + approximate division (|d sigma| ~ 1e-7)
+__device__ __forceinline__ float sigmoidf_precise(float s) { return __fdividef(1.0f, 1.0f + __expf(-s)); }
+#else
 __device__ __forceinline__ float sigmoidf_precise(float s) { return 1.0f / (1.0f + expf(-s)); }
+#endif
 
 // dx = clipped ? (dy - y (y.dy)) * inv : dy      (App. A.3)
 template <int V>
@@ -855,11 +859,19 @@ __device__ __forceinline__ void sum_rows(Row<V>& acc, const float* __restrict__ 
   }
 }
 
+// row-sharded step (hole_shard_step): a row's change goes to my slice of its owner's staging buffer
+struct hole_k3_shard {
+  const int32_t* cuts;      // [world+1] first request-list slot per owner
+  int R, me, world;         // world == 0: not sharded
+  long long cap;
+  hole_peer_ptrs stage;     // PEER: rank o's delta staging [world][cap][stride]
+};
+
 template <int GS, int V>
 __global__ void __launch_bounds__(256)
 hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __restrict__ heads,
                   const int* __restrict__ nheads, int* __restrict__ counters, int M, int nvec,
-                  int stride, float lr, float* __restrict__ Dtab, int flags) {
+                  int stride, float lr, float* __restrict__ Dtab, int flags, const hole_k3_shard sh) {
   constexpr int C = HOLE_TREE_C;
   const int lane = threadIdx.x % GS;
   const int gbase = (threadIdx.x % 32) / GS * GS;
@@ -888,12 +900,20 @@ hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __r
         if (delta) {
 #pragma unroll
           for (int k = 0; k < 4 * V; ++k) { x.re[k] = -lr * acc.re[k]; x.im[k] = -lr * acc.im[k]; }
+          float* drow = Dtab + (size_t)row * stride;
+          if (sh.world > 0 && row >= sh.R) {     // entity row of a sharded step: the owner's staging buffer
+            const int slot = row - sh.R;
+            int o = 0;
+            while (slot >= sh.cuts[o + 1]) ++o;
+            drow = static_cast<float*>(sh.stage.p[o]) +
+                   ((size_t)sh.me * (size_t)sh.cap + (size_t)(slot - sh.cuts[o])) * stride;
+          }
           if (flags & HOLE_K1_ACCUMULATE) {
             Row<V> o;
-            row_load<GS, V, false>(o, Dtab + (size_t)row * stride, lane, nvec);
+            row_load<GS, V, false>(o, drow, lane, nvec);
             row_add(x, o);
           }
-          row_store<GS, V>(x, Dtab + (size_t)row * stride, lane, nvec);
+          row_store<GS, V>(x, drow, lane, nvec);
           break;
         }
         if (!single) row_load<GS, V, false>(x, erow, lane, nvec);
@@ -928,6 +948,7 @@ hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __r
 }
 
 // ---------------------------------------------------------------------------------------
+#include "hole_k1.cuh"
 
 // table[ids[k]] += rows[k] for UNIQUE ids (multi-GPU: the owner applies one source rank's
 // row deltas; ranks are applied one after the other, so the sum order is fixed)
@@ -970,8 +991,6 @@ hole_gather_rows_kernel(const float* __restrict__ E, const int64_t* __restrict__
 //   push  : the owner copies the requested rows into the requester's step table (peer memory)
 //   pull  : the owner reads the requester's delta rows (peer memory) and adds them to its shard
 // ---------------------------------------------------------------------------------------
-struct hole_peer_ptrs { void* p[HOLE_MAX_RANKS]; };
-
 __global__ void hole_shard_keys_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ neg,
                                        int B, uint32_t* __restrict__ keys) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
@@ -1089,103 +1108,6 @@ __global__ void hole_shard_post_kernel(const int32_t* __restrict__ uniq, const i
     int32_t* m = static_cast<int32_t*>(meta.p[gtid]);
     m[2 * me] = cuts[gtid + 1] - cuts[gtid];     // how many rows I want from rank gtid
     m[2 * me + 1] = cuts[gtid];                  // where they sit in my step table (after R)
-  }
-}
-
-// Barrier across the ranks' compute streams through peer flags: thread k stores `epoch` into
-// flag[me] of rank k (release, system scope) and spins until flag[k] of my own array reaches
-// `epoch` (acquire).  Epochs only grow, so there is nothing to reset.  Everything the earlier
-// kernels of my stream wrote to peer memory is visible to a peer's kernels that follow its
-// barrier.  A peer that never arrives trips a 10 s timeout: *err is set and the kernel leaves;
-// every later barrier of this rank then returns at once (the host raises in check_barriers).
-__global__ void hole_shard_barrier_kernel(int world, int me, int epoch, hole_peer_ptrs flags,
-                                          int* __restrict__ err) {
-  const int k = threadIdx.x;
-  if (k >= world) return;
-  // once a barrier has timed out the run is lost: later barriers still signal (so that healthy
-  // peers do not wait for us) but never wait again -- the job drains in seconds, not hours
-  const bool dead = *reinterpret_cast<volatile int*>(err) != 0;
-  __threadfence_system();
-  int* theirs = static_cast<int*>(flags.p[k]) + me;
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
-  const int* mine = static_cast<const int*>(flags.p[me]) + k;
-  unsigned long long t0;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-  while (!dead) {
-    int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-    if (v - epoch >= 0) break;
-    unsigned long long t1;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 10000000000ull) { atomicExch(err, 1); break; }
-  }
-  __threadfence_system();
-}
-
-// grid.y = requester k: tables.p[k][row_base + off_k + g] = shard[inbox[k][g] + id_offset]
-template <int GS, int V>
-__global__ void __launch_bounds__(256)
-hole_shard_push_kernel(const float* __restrict__ shard, int64_t id_offset, const int32_t* __restrict__ inbox,
-                       const int32_t* __restrict__ meta, int64_t cap, int64_t row_base,
-                       hole_peer_ptrs tables, float* __restrict__ my_table, float* __restrict__ my_delta,
-                       int nvec, int stride) {
-  const int k = blockIdx.y, lane = threadIdx.x % GS;
-  const int gstride = (gridDim.x * blockDim.x) / GS;
-  const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) / GS;
-  if (k == 0 && my_table != nullptr) {
-    // the replicated relation block: my step table takes the current rows, my delta table zeros
-    // (delta mode writes only the relations a step uses)
-    Row<V> z;
-    row_zero(z);
-    for (int g = g0; g < (int)row_base; g += gstride) {
-      Row<V> x;
-      row_load<GS, V, false>(x, shard + (size_t)g * stride, lane, nvec);
-      row_store<GS, V>(x, my_table + (size_t)g * stride, lane, nvec);
-      row_store<GS, V>(z, my_delta + (size_t)g * stride, lane, nvec);
-    }
-  }
-  const int n = meta[2 * k], off = meta[2 * k + 1];
-  float* dst = static_cast<float*>(tables.p[k]) + (size_t)(row_base + off) * stride;
-  const int32_t* ids = inbox + (size_t)k * cap;
-  for (int g = g0; g < n; g += gstride) {
-    Row<V> x;
-    row_load<GS, V, false>(x, shard + (size_t)(ids[g] + id_offset) * stride, lane, nvec);
-    row_store<GS, V>(x, dst + (size_t)g * stride, lane, nvec);
-  }
-}
-
-// one requester k per launch (launched in rank order: a row several ranks touched gets its
-// deltas in a fixed order): shard[inbox[k][g] + id_offset] += deltas_k[row_base + off_k + g]
-template <int GS, int V>
-__global__ void __launch_bounds__(256)
-hole_shard_pull_kernel(float* __restrict__ shard, int64_t id_offset, const int32_t* __restrict__ inbox,
-                       const int32_t* __restrict__ meta, int k, int64_t cap, int64_t row_base,
-                       const float* __restrict__ deltas_k, int add_replicated, int nvec, int stride) {
-  const int lane = threadIdx.x % GS;
-  const int n = meta[2 * k], off = meta[2 * k + 1];
-  const float* src = deltas_k + (size_t)(row_base + off) * stride;
-  const int32_t* ids = inbox + (size_t)k * cap;
-  const int gstride = (gridDim.x * blockDim.x) / GS;
-  const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) / GS;
-  if (add_replicated) {
-    // the replicated relation block: every rank adds every rank's deltas in rank order, so the
-    // replicas stay bit-identical without an all-reduce
-    for (int g = g0; g < (int)row_base; g += gstride) {
-      float* erow = shard + (size_t)g * stride;
-      Row<V> x, d;
-      row_load<GS, V, false>(x, erow, lane, nvec);
-      row_load<GS, V, false>(d, deltas_k + (size_t)g * stride, lane, nvec);
-      row_add(x, d);
-      row_store<GS, V>(x, erow, lane, nvec);
-    }
-  }
-  for (int g = g0; g < n; g += gstride) {
-    float* erow = shard + (size_t)(ids[g] + id_offset) * stride;
-    Row<V> x, d;
-    row_load<GS, V, false>(x, erow, lane, nvec);
-    row_load<GS, V, false>(d, src + (size_t)g * stride, lane, nvec);
-    row_add(x, d);
-    row_store<GS, V>(x, erow, lane, nvec);
   }
 }
 
@@ -1324,6 +1246,23 @@ extern "C" int hole_row_stride(int dim) {
   return 2 * (((dim / 2) + 3) / 4 * 4);
 }
 
+static int ctx_create_streams(hole_ctx* c) {
+  HOLE_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  {   // the plan is small integer work that the next step waits for: highest priority
+    int lo = 0, hi = 0;
+    HOLE_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    // (for the chunked single-GPU path the priority makes no measurable difference)
+    HOLE_CUDA_TRY(cudaStreamCreateWithPriority(&c->plan_stream, cudaStreamNonBlocking, hi));
+  }
+  HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
+  for (int k = 0; k < 2; ++k) {
+    HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming));
+    HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->plan[k].ready, cudaEventDisableTiming));
+    HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->plan[k].released, cudaEventDisableTiming));
+  }
+  return HOLE_OK;
+}
+
 extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int dim) {
   HOLE_CHECK_ARG(out != nullptr);
   *out = nullptr;
@@ -1364,40 +1303,21 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
   c->row_passes = 1;
   while (((int64_t(1) << (8 * c->row_passes)) - 1) < n_rows) ++c->row_passes;
   c->rel_passes = c->row_passes;
-  // K1 landing buffers: K1_STAGES triples x 3 entity rows + 1 relation row per lane group
+  // K1 landing buffers (first-generation body): K1_STAGES triples x 3 entity rows + 1 relation row per
+  // lane group.  Kernel attributes are set lazily by k1_prepare(): scoring / ranking contexts never
+  // need them.
   c->k1_smem = (256 / c->gs) * (K1_STAGES * 3 + 1) * c->row_stride * (int)sizeof(float);
-  {
-    cudaError_t ea = cudaSuccess;
-    if (c->gs == 8) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
-    else if (c->gs == 16) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
-    else if (c->v == 1) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
-    else if (c->v == 2) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
-    else ea = cudaFuncSetAttribute(hole_train_fwd_bwd_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
-    if (ea == cudaSuccess) {
-      if (c->gs == 8) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_ll_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
-      else if (c->gs == 16) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_ll_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
-      else if (c->v == 1) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_ll_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
-      else if (c->v == 2) ea = cudaFuncSetAttribute(hole_train_fwd_bwd_ll_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
-      else ea = cudaFuncSetAttribute(hole_train_fwd_bwd_ll_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
-    }
-    if (ea != cudaSuccess) {
-      const int want = c->k1_smem;
-      delete c;
-      return hole_set_error(HOLE_ERR_CUDA, "cudaFuncSetAttribute(K1 smem %d) -> %s", want, cudaGetErrorString(ea));
-    }
+  if (const char* e = getenv("HOLE_K1")) c->k1_gen = (e[0] == '1' || !strcmp(e, "v1")) ? 1 : 2;
+  if (const char* e = getenv("HOLE_K1_BLOCK")) c->k1_block = atoi(e);
+  if (c->k1_block != 128 && c->k1_block != 192 && c->k1_block != 256) c->k1_block = 256;
+  if (const char* e = getenv("HOLE_PLAN_RAMP")) {     // "first,factor"; "0" disables the ramp
+    int a = 0, b = 4;
+    if (sscanf(e, "%d,%d", &a, &b) >= 1) { c->ramp_first = a; c->ramp_factor = b < 2 ? 2 : b; }
   }
-  HOLE_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  {   // the plan is small integer work that the next step waits for: highest priority
-    int lo = 0, hi = 0;
-    HOLE_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    // (for the chunked single-GPU path the priority makes no measurable difference)
-    HOLE_CUDA_TRY(cudaStreamCreateWithPriority(&c->plan_stream, cudaStreamNonBlocking, hi));
-  }
-  HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
-  for (int k = 0; k < 2; ++k) {
-    HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming));
-    HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->plan[k].ready, cudaEventDisableTiming));
-    HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->plan[k].released, cudaEventDisableTiming));
+  int rc = ctx_create_streams(c);
+  if (rc != HOLE_OK) {
+    hole_ctx_destroy(c);
+    return rc;
   }
   *out = c;
   return HOLE_OK;
@@ -1427,10 +1347,13 @@ extern "C" int hole_ctx_set_relations(hole_ctx* c, int64_t n_relations) {
   return HOLE_OK;
 }
 
+static void shard_free(hole_ctx* c);
+
 extern "C" int hole_ctx_destroy(hole_ctx* c) {
   if (c == nullptr) return HOLE_OK;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  shard_free(c);
   ws_free(c);
   hole_rank_ws_free(c);
   cudaFree(c->route_buf);
@@ -1449,8 +1372,14 @@ extern "C" int hole_ctx_destroy(hole_ctx* c) {
   return HOLE_OK;
 }
 
+static int k1_prepare(hole_ctx* c);
+
 // Workspace for chunks of S steps of batch B.  Reallocation synchronises the device.
 int hole_ws_reserve(hole_ctx* c, int64_t B, int64_t S) {
+  if (!c->k1_ready) {
+    int rc = k1_prepare(c);
+    if (rc) return rc;
+  }
   if (B <= c->cap_B && S <= c->cap_S) return HOLE_OK;
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   HOLE_CUDA_TRY(cudaDeviceSynchronize());
@@ -1574,9 +1503,82 @@ static int radix_sort(uint32_t* ghist, uint32_t* kA, uint32_t* kB, uint32_t* vA,
   return HOLE_OK;
 }
 
+typedef void (*hole_k1_fn)(const hole_k1_args, const hole_k1_shard);
+template <int DM>
+static hole_k1_fn k1_fn(const hole_ctx* c) {
+  if (c->gs == 8) return hole_k1_kernel<8, 1, DM>;
+  if (c->gs == 16) return hole_k1_kernel<16, 1, DM>;
+  if (c->v == 1) return hole_k1_kernel<32, 1, DM>;
+  if (c->v == 2) return hole_k1_kernel<32, 2, DM>;
+  return hole_k1_kernel<32, 3, DM>;
+}
+static hole_k1_fn k1_fn_dm(const hole_ctx* c, int dm) {
+  return dm == 0 ? k1_fn<0>(c) : dm == 1 ? k1_fn<1>(c) : k1_fn<2>(c);
+}
+
+// Kernel attributes of the training kernels, set on the first training call of a context
+// (scoring / ranking contexts never pay for, or fail on, K1's shared-memory request).
+static int k1_prepare(hole_ctx* c) {
+  if (c->k1_ready) return HOLE_OK;
+  const int limit = 227 * 1024;
+  // second generation: K1V2_STAGES x 3 landing rows + K1V2_STAGES mbarriers per lane group
+  int block = c->k1_block;
+  auto smem_of = [&](int blk) { return (blk / c->gs) * K1V2_STAGES * (3 * c->row_stride * (int)sizeof(float) + 8); };
+  while (block > 32 && smem_of(block) > limit) block -= 32;
+  if (smem_of(block) > limit || block < c->gs)
+    return hole_set_error(HOLE_ERR_UNSUPPORTED, "embedding_dim %d: a K1 lane group needs %d bytes of shared memory",
+                          c->dim, smem_of(c->gs));
+  c->k1_block = block;
+  c->k1v2_smem = smem_of(block);
+  int nb = 1;
+  for (int dm = 0; dm < 3; ++dm) {
+    HOLE_CUDA_TRY(cudaFuncSetAttribute(k1_fn_dm(c, dm), cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1v2_smem));
+  }
+  HOLE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1_fn<0>(c), c->k1_block, c->k1v2_smem));
+  c->k1_groups = c->sm_count * std::max(nb, 1) * (c->k1_block / c->gs);
+  if (c->k1_smem <= limit) {       // first-generation body (--log_loss passes; HOLE_K1=v1)
+    cudaError_t ea = cudaSuccess;
+#define HOLE_K1_ATTR(KERNEL)                                                                                   \
+    if (c->gs == 8) ea = cudaFuncSetAttribute(KERNEL<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);          \
+    else if (c->gs == 16) ea = cudaFuncSetAttribute(KERNEL<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);   \
+    else if (c->v == 1) ea = cudaFuncSetAttribute(KERNEL<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);     \
+    else if (c->v == 2) ea = cudaFuncSetAttribute(KERNEL<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);     \
+    else ea = cudaFuncSetAttribute(KERNEL<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
+    HOLE_K1_ATTR(hole_train_fwd_bwd_kernel)
+    HOLE_CUDA_TRY(ea);
+    HOLE_K1_ATTR(hole_train_fwd_bwd_ll_kernel)
+    HOLE_CUDA_TRY(ea);
+#undef HOLE_K1_ATTR
+  } else if (c->k1_gen == 1) {
+    c->k1_gen = 2;
+  }
+  if (c->k1_gen == 1) c->k1_groups = c->sm_count * 2 * (256 / c->gs);   // two resident 256-thread blocks per SM
+  c->k1_ready = true;
+  return HOLE_OK;
+}
+
+static int k1_launch(hole_ctx* c, int dm, const hole_k1_args& a, const hole_k1_shard& sh, cudaStream_t st,
+                     bool pdl) {
+  const int per_block = c->k1_block / c->gs;
+  const int64_t groups = ((int64_t)a.B + a.T - 1) / a.T;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)std::max<int64_t>(1, (groups + per_block - 1) / per_block));
+  cfg.blockDim = dim3((unsigned)c->k1_block);
+  cfg.dynamicSmemBytes = (size_t)c->k1v2_smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  HOLE_CUDA_TRY(cudaLaunchKernelEx(&cfg, k1_fn_dm(c, dm), a, sh));
+  HOLE_LAUNCHED();
+  return HOLE_OK;
+}
+
 // triples per lane group in K1 (and the run length the plan folds relation keys over)
 static int triples_per_group(const hole_ctx* c, int64_t B) {
-  const int64_t wmax = (int64_t)c->sm_count * 2 * (256 / c->gs);   // groups of two resident blocks per SM
+  const int64_t wmax = c->k1_groups > 0 ? c->k1_groups : (int64_t)c->sm_count * 2 * (256 / c->gs);
   return (int)std::max<int64_t>(1, (B + wmax - 1) / wmax);
 }
 
@@ -1618,10 +1620,13 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
 }
 
 // K1 + K3 of one step whose plan is slot `slot` of pl.
+// shard != nullptr (hole_shard_step): pos / neg are the step's triples as request-list rows (what the
+// plan was built on), shard_tri / shard_neg the same triples as global row ids (what K1 gathers).
 static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos, const int32_t* neg,
                     int side, int64_t B, float margin, float lr, float* loss_out, float* sigma_out,
                     int64_t slot, cudaStream_t st, float* delta_out = nullptr, bool k1_follows_k3 = false,
-                    int flags = 0) {
+                    int flags = 0, const hole_k1_shard* shard = nullptr, const int32_t* shard_tri = nullptr,
+                    const int32_t* shard_neg = nullptr) {
   const int M = (int)(4 * B);
   const size_t off = (size_t)slot * M;
   cudaEvent_t* pe = nullptr;
@@ -1639,7 +1644,22 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
   }
   // K1's prologue reads plan data before griddepcontrol.wait: only overlap it with a
   // predecessor that does not write the plan, i.e. the previous step's K3 of the same chunk
-  if ((flags & 3) != 0) {
+  hole_k3_shard k3s = {};
+  if (shard != nullptr) {
+    k3s.cuts = shard->cuts; k3s.R = shard->R; k3s.me = shard->me; k3s.world = shard->world;
+    k3s.cap = shard->cap; k3s.stage = shard->stage;
+  }
+  if ((flags & 3) == 0 && c->k1_gen == 2) {
+    hole_k1_args ka = {};
+    ka.E = table; ka.tri = shard ? shard_tri : pos; ka.neg = shard ? shard_neg : neg;
+    ka.perm = pl.perm + (size_t)slot * B; ka.gslot = pl.gslot + off;
+    ka.side = side; ka.B = (int)B; ka.T = pl.T; ka.nvec = c->nvec; ka.stride = c->row_stride;
+    ka.margin = margin; ka.lr = lr; ka.G = c->G; ka.loss = loss_out; ka.sigma = sigma_out; ka.Dtab = delta_out;
+    static const hole_k1_shard no_shard = {};
+    const int dm = shard ? 2 : (delta_out ? 1 : 0);
+    int rc = k1_launch(c, dm, ka, shard ? *shard : no_shard, st, k1_follows_k3 && !c->profile);
+    if (rc) return rc;
+  } else if ((flags & 3) != 0) {
     HOLE_DISPATCH_SMEM(c, hole_train_fwd_bwd_ll_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
                        c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
                 c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out, flags);
@@ -1656,7 +1676,7 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
   const unsigned k3_grid = std::min<unsigned>(grid_for_groups(pl.heads_cap, c->gs), (unsigned)c->sm_count * 4);
   HOLE_DISPATCH_PDL(c, hole_apply_kernel, k3_grid, 256, 0, st, table, c->G,
                 pl.heads + (size_t)slot * pl.heads_cap, pl.nheads + slot, c->counters, M, c->nvec,
-                c->row_stride, lr, delta_out, flags);
+                c->row_stride, lr, delta_out, flags, k3s);
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[2], st));
   return HOLE_OK;
 }
@@ -1862,10 +1882,10 @@ static int route_reserve(hole_ctx* c, int64_t M) {
   return HOLE_OK;
 }
 
-extern "C" int hole_shard_route(hole_ctx* c, const int32_t* pos, const int32_t* neg_ent, int64_t B,
-                                int64_t n_relations, int64_t n_rows_global, int64_t rows_per_rank,
-                                int world, int32_t* uniq_out, int32_t* cuts_out, int32_t* pos_w,
-                                int32_t* neg_w, void* stream) {
+static int shard_route(hole_ctx* c, const int32_t* pos, const int32_t* neg_ent, int64_t B,
+                       int64_t n_relations, int64_t n_rows_global, int64_t rows_per_rank,
+                       int world, int32_t* uniq_out, int32_t* cuts_out, int32_t* pos_w,
+                       int32_t* neg_w, void* stream) {
   HOLE_CHECK_ARG(c && pos && neg_ent && uniq_out && cuts_out && pos_w && neg_w);
   HOLE_CHECK_ARG(B > 0 && 3 * B < (int64_t(1) << 31) && world >= 1 && world <= HOLE_MAX_RANKS);
   HOLE_CHECK_ARG(n_relations >= 0 && rows_per_rank > 0 && n_rows_global > n_relations &&
@@ -1897,6 +1917,14 @@ extern "C" int hole_shard_route(hole_ctx* c, const int32_t* pos, const int32_t* 
   return HOLE_OK;
 }
 
+extern "C" int hole_shard_route(hole_ctx* c, const int32_t* pos, const int32_t* neg_ent, int64_t B,
+                                int64_t n_relations, int64_t n_rows_global, int64_t rows_per_rank,
+                                int world, int32_t* uniq_out, int32_t* cuts_out, int32_t* pos_w,
+                                int32_t* neg_w, void* stream) {
+  return shard_route(c, pos, neg_ent, B, n_relations, n_rows_global, rows_per_rank, world, uniq_out, cuts_out,
+                     pos_w, neg_w, stream);
+}
+
 static int peer_ptrs(hole_peer_ptrs& out, void* const* in, int world) {
   for (int k = 0; k < HOLE_MAX_RANKS; ++k) out.p[k] = nullptr;
   for (int k = 0; k < world; ++k) {
@@ -1922,57 +1950,27 @@ extern "C" int hole_shard_post(hole_ctx* c, const int32_t* uniq, const int32_t* 
   return HOLE_OK;
 }
 
-extern "C" int hole_shard_push(hole_ctx* c, const float* shard, int64_t id_offset, const int32_t* inbox,
-                               const int32_t* meta, int world, int64_t cap, int64_t row_base,
-                               void* const* peer_tables, float* my_table, float* my_delta, void* stream) {
-  HOLE_CHECK_ARG(c && shard && inbox && meta && peer_tables);
-  HOLE_CHECK_ARG(world >= 1 && world <= HOLE_MAX_RANKS && cap > 0 && row_base >= 0);
-  HOLE_CHECK_ARG((my_table == nullptr) == (my_delta == nullptr));
-  HOLE_CUDA_TRY(cudaSetDevice(c->device));
-  hole_peer_ptrs tb;
-  int rc = peer_ptrs(tb, peer_tables, world);
-  if (rc) return rc;
-  // half occupancy on purpose: the exchange is NVLink-bound, and the side streams' small plan /
-  // routing kernels must find free SM slots while it runs
-  const dim3 grid((unsigned)std::max(1, c->sm_count * 4 / world), (unsigned)world);
-  HOLE_DISPATCH(c, hole_shard_push_kernel, grid, 256, (cudaStream_t)stream, shard, id_offset, inbox, meta, cap,
-                row_base, tb, my_table, my_delta, c->nvec, c->row_stride);
-  return HOLE_OK;
-}
-
-extern "C" int hole_shard_barrier(hole_ctx* c, int world, int me, int32_t epoch, void* const* peer_flags,
-                                  int32_t* err_flag, void* stream) {
-  HOLE_CHECK_ARG(c && peer_flags && err_flag);
-  HOLE_CHECK_ARG(world >= 1 && world <= HOLE_MAX_RANKS && me >= 0 && me < world);
-  HOLE_CUDA_TRY(cudaSetDevice(c->device));
-  hole_peer_ptrs fl;
-  int rc = peer_ptrs(fl, peer_flags, world);
-  if (rc) return rc;
-  hole_shard_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(world, me, epoch, fl, err_flag);
-  HOLE_LAUNCHED();
-  return HOLE_OK;
-}
-
-extern "C" int hole_shard_pull(hole_ctx* c, float* shard, int64_t id_offset, const int32_t* inbox,
-                               const int32_t* meta, int world, int64_t cap, int64_t row_base,
-                               void* const* peer_deltas, int add_replicated, void* stream) {
-  HOLE_CHECK_ARG(c && shard && inbox && meta && peer_deltas);
-  HOLE_CHECK_ARG(world >= 1 && world <= HOLE_MAX_RANKS && cap > 0 && row_base >= 0);
-  HOLE_CUDA_TRY(cudaSetDevice(c->device));
-  for (int k = 0; k < world; ++k) {
-    HOLE_CHECK_ARG(peer_deltas[k] != nullptr);
-    HOLE_DISPATCH(c, hole_shard_pull_kernel, (unsigned)c->sm_count * 4, 256, (cudaStream_t)stream, shard, id_offset,
-                  inbox, meta, k, cap, row_base, static_cast<const float*>(peer_deltas[k]), add_replicated, c->nvec,
-                  c->row_stride);
-  }
-  return HOLE_OK;
-}
-
 // steps planned per chunk: enough blocks for the plan kernels to fill the GPU, bounded memory
 // (a function of B only, so that the workspace is sized once per batch size)
 static int64_t plan_chunk(int64_t B) {
   const int64_t M = 4 * B;
   return std::max<int64_t>(32, std::min<int64_t>(256, (int64_t(1) << 23) / M));
+}
+
+// Chunk sizes of an n_steps call.  The first chunk's plan cannot overlap anything (nothing is
+// training yet), so it is kept short -- ramp_first steps -- and the chunks grow by ramp_factor up to
+// plan_chunk(B): every later plan is hidden behind the previous chunk's steps.
+static std::vector<int64_t> chunk_sizes(const hole_ctx* c, int64_t B, int64_t n_steps) {
+  const int64_t S = plan_chunk(B);
+  std::vector<int64_t> v;
+  int64_t cur = c->ramp_first > 0 ? std::min<int64_t>(S, c->ramp_first) : S;
+  for (int64_t left = n_steps; left > 0;) {
+    const int64_t n = std::min(cur, left);
+    v.push_back(n);
+    left -= n;
+    cur = std::min<int64_t>(S, cur * std::max(2, c->ramp_factor));
+  }
+  return v;
 }
 
 // the S steps of one planned chunk on the compute stream
@@ -2012,14 +2010,16 @@ extern "C" int hole_train_steps(hole_ctx* c, float* table, const int32_t* triple
   // the plan stream may only read the caller's triples once the caller's stream got here
   HOLE_CUDA_TRY(cudaEventRecord(c->ev_entry, st));
   HOLE_CUDA_TRY(cudaStreamWaitEvent(c->plan_stream, c->ev_entry, 0));
-  const int64_t nchunks = (n_steps + S - 1) / S;
-  rc = plan_steps(c, c->plan[0], triples, B, std::min(S, n_steps), type_of, csr_off, csr_ids, seed,
+  const std::vector<int64_t> sizes = chunk_sizes(c, B, n_steps);
+  const int64_t nchunks = (int64_t)sizes.size();
+  rc = plan_steps(c, c->plan[0], triples, B, sizes[0], type_of, csr_off, csr_ids, seed,
                   first_step, nullptr, c->plan_stream);
   if (rc) return rc;
-  for (int64_t ci = 0; ci < nchunks; ++ci) {
-    const int64_t k0 = ci * S, s = std::min(S, n_steps - k0);
+  int64_t k0 = 0;
+  for (int64_t ci = 0; ci < nchunks; k0 += sizes[ci], ++ci) {
+    const int64_t s = sizes[ci];
     if (ci + 1 < nchunks) {   // plan the next chunk while this one trains
-      const int64_t k1 = k0 + S, s1 = std::min(S, n_steps - k1);
+      const int64_t k1 = k0 + s, s1 = sizes[ci + 1];
       rc = plan_steps(c, c->plan[(ci + 1) & 1], triples + (size_t)k1 * B * 3, B, s1, type_of, csr_off,
                       csr_ids, seed, first_step + (uint64_t)k1, nullptr, c->plan_stream);
       if (rc) return rc;
@@ -2069,12 +2069,15 @@ extern "C" int hole_train_steps_host(hole_ctx* c, float* table, const int32_t* t
   cudaStream_t st = (cudaStream_t)stream;
   HOLE_CUDA_TRY(cudaEventRecord(c->ev_entry, st));
   HOLE_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0));
-  const int64_t nchunks = (n_steps + S - 1) / S;
+  const std::vector<int64_t> sizes = chunk_sizes(c, B, n_steps);
+  const int64_t nchunks = (int64_t)sizes.size();
+  std::vector<int64_t> starts(nchunks, 0);
+  for (int64_t ci = 1; ci < nchunks; ++ci) starts[ci] = starts[ci - 1] + sizes[ci - 1];
   // chunk ci: H2D copy into staging buffer ci&1 (copy stream) -> plan (plan stream) -> steps
   // (caller's stream).  Staging buffer b is free again when plan[b].released fires.
   auto stage_and_plan = [&](int64_t ci) -> int {
     const int b = (int)(ci & 1);
-    const int64_t k0 = ci * S, s = std::min(S, n_steps - k0);
+    const int64_t k0 = starts[ci], s = sizes[ci];
     if (c->plan[b].used) HOLE_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->plan[b].released, 0));
     HOLE_CUDA_TRY(cudaMemcpyAsync(c->triples_stage[b], triples_host + (size_t)k0 * B * 3,
                                   (size_t)s * B * 3 * 4, cudaMemcpyHostToDevice, c->copy_stream));
@@ -2087,7 +2090,7 @@ extern "C" int hole_train_steps_host(hole_ctx* c, float* table, const int32_t* t
   if (rc) return rc;
   for (int64_t ci = 0; ci < nchunks; ++ci) {
     const int b = (int)(ci & 1);
-    const int64_t k0 = ci * S, s = std::min(S, n_steps - k0);
+    const int64_t k0 = starts[ci], s = sizes[ci];
     if (ci + 1 < nchunks) {
       rc = stage_and_plan(ci + 1);
       if (rc) return rc;
@@ -2103,6 +2106,8 @@ extern "C" int hole_train_steps_host(hole_ctx* c, float* table, const int32_t* t
   for (int64_t k = 0; k < n_steps; ++k) loss_sum_host[k] = c->loss_sum_pinned[k];
   return HOLE_OK;
 }
+
+#include "hole_shard.cuh"
 
 // ---------------------------------------------------------------------------------------
 // CRC32C (Castagnoli) for the TF tensor-bundle checkpoint writer (host code; holE.py:359

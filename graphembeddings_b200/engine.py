@@ -194,21 +194,64 @@ class HoleEngine:
         check(self.lib.hole_shard_post(self._ctx, _ptr(uniq), _ptr(cuts), int(world), int(me), int(cap),
                                        peer_inbox, peer_meta, _stream()))
 
-    def shard_push(self, shard, id_offset, inbox, meta, world, cap, row_base, peer_tables,
-                   my_table=None, my_delta=None):
-        check(self.lib.hole_shard_push(self._ctx, _ptr(shard), int(id_offset), _ptr(inbox), _ptr(meta),
-                                       int(world), int(cap), int(row_base), peer_tables,
-                                       None if my_table is None else _ptr(my_table),
-                                       None if my_delta is None else _ptr(my_delta), _stream()))
+    def shard_init(self, world, me, n_relations, n_entities, rows_per_rank, max_batch, shard, peer_shard,
+                   peer_stage, peer_relstage, peer_inbox, peer_meta, peer_flags, err_flag, timeout_s=0.0):
+        """hole_shard_init: bind this context to a row-sharded table (peer_* = ctypes void*[world] of the
+        IPC-mapped buffers, see include/hole_b200.h).  The type tables must have been set."""
+        self._shard_keep = (shard, err_flag)
+        check(self.lib.hole_shard_init(self._ctx, int(world), int(me), int(n_relations), int(n_entities),
+                                       int(rows_per_rank), int(max_batch), _ptr(shard), peer_shard, peer_stage,
+                                       peer_relstage, peer_inbox, peer_meta, peer_flags, _ptr(err_flag),
+                                       float(timeout_s), _ptr(self.type_of), _ptr(self.csr_off), _ptr(self.csr_ids)))
 
-    def shard_barrier(self, world, me, epoch, peer_flags, err_flag):
-        check(self.lib.hole_shard_barrier(self._ctx, int(world), int(me), int(epoch), peer_flags,
-                                          _ptr(err_flag), _stream()))
+    def shard_prepare(self, pos_i32, seed, step):
+        check(self.lib.hole_shard_prepare(self._ctx, _ptr(pos_i32), pos_i32.shape[0], int(seed), int(step), _stream()))
 
-    def shard_pull(self, shard, id_offset, inbox, meta, world, cap, row_base, peer_deltas, add_replicated=False):
-        check(self.lib.hole_shard_pull(self._ctx, _ptr(shard), int(id_offset), _ptr(inbox), _ptr(meta),
-                                       int(world), int(cap), int(row_base), peer_deltas, int(add_replicated),
-                                       _stream()))
+    def shard_step(self, pos_i32, seed, step, margin, lr, loss_out=None, phase=None):
+        """One row-sharded step on this rank's slice (int32 CUDA [B,3], global row ids).  phase:
+        None = whole step, "compute" / "apply" = its halves (virtual-rank tests)."""
+        if phase == "apply":
+            check(self.lib.hole_shard_step_apply(self._ctx, _stream()))
+            return None
+        B = pos_i32.shape[0]
+        if loss_out is None:
+            loss_out = torch.empty(B, dtype=torch.float32, device=self.device)
+        fn = self.lib.hole_shard_step if phase is None else self.lib.hole_shard_step_compute
+        check(fn(self._ctx, _ptr(pos_i32), B, int(seed), int(step), float(margin), float(lr), _ptr(loss_out), _stream()))
+        return loss_out
+
+    def shard_steps(self, triples_i32, batch_size, seed, first_step, margin, lrs):
+        """n_steps consecutive sharded steps on device-resident slices [n_steps*B, 3]; returns the
+        per-step loss sums of this rank's slices (device float32)."""
+        n_steps = triples_i32.shape[0] // batch_size
+        lrs = np.ascontiguousarray(np.asarray(lrs, dtype=np.float32))
+        assert len(lrs) >= n_steps
+        sums = torch.empty(n_steps, dtype=torch.float32, device=self.device)
+        check(self.lib.hole_shard_steps(self._ctx, _ptr(triples_i32), batch_size, n_steps, int(seed), int(first_step),
+                                        float(margin), lrs.ctypes.data_as(C.c_void_p), _ptr(sums), _stream()))
+        return sums
+
+    def shard_steps_host(self, triples_host, batch_size, seed, first_step, margin, lrs):
+        """Same from a HOST int32 [n,3] tensor (pinned) / array; copies inside; returns numpy loss sums."""
+        if isinstance(triples_host, torch.Tensor):
+            assert triples_host.device.type == "cpu" and triples_host.dtype == torch.int32 and triples_host.is_contiguous()
+            n, ptr = triples_host.shape[0], C.c_void_p(triples_host.data_ptr())
+        else:
+            triples_host = np.ascontiguousarray(triples_host, dtype=np.int32)
+            n, ptr = triples_host.shape[0], triples_host.ctypes.data_as(C.c_void_p)
+        n_steps = n // batch_size
+        lrs = np.ascontiguousarray(np.asarray(lrs, dtype=np.float32))
+        out = np.empty(n_steps, dtype=np.float32)
+        check(self.lib.hole_shard_steps_host(self._ctx, ptr, batch_size, n_steps, int(seed), int(first_step),
+                                             float(margin), lrs.ctypes.data_as(C.c_void_p),
+                                             out.ctypes.data_as(C.c_void_p), _stream()))
+        return out
+
+    def shard_poll(self):
+        """True if a peer failed to arrive at a step barrier (synchronises the stream)."""
+        v = C.c_int(0)
+        check(self.lib.hole_shard_poll(self._ctx, C.byref(v), _stream()))
+        return v.value != 0
 
     def enable_peer_access(self, peer_device):
         check(self.lib.hole_enable_peer_access(self._ctx, int(peer_device)))

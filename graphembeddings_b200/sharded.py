@@ -1,23 +1,23 @@
 """Multi-GPU HolE: entity table row-sharded over the ranks of one node.
 
-One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch; gloo in the CPU tests).
+One process per GPU (torch.distributed for rendezvous; gloo in the CPU tests).
 
-Training step (batch-synchronous, same result as one GPU on the concatenated batch up to
-fp32 summation order):
-  1. every rank corrupts its slice of the global batch (Philox keyed on the GLOBAL triple
-     index, so the draw does not depend on the number of ranks);
-  2. all-to-all of the unique entity ids a rank needs -> all-to-all of those rows from their
-     owners (relation rows are replicated);
-  3. the rank assembles a step table W = [relations | fetched rows], remaps its triples into
-     W and runs the single-GPU step kernels on it in place;
-  4. W_after - W_before is the rank's contribution: relation deltas are all-reduced and
-     applied to every replica, entity deltas travel back by all-to-all and the owner adds
-     them in rank order (deterministic).
-Ranking: candidates are sharded by row block; the true candidate's score comes from its
-owner (all-reduce of a zero-initialised vector), the int32 counts are all-reduced.
+Training is batch-synchronous and gives the same result as one GPU on the concatenated batch up to
+fp32 summation order: every rank corrupts its slice of the global batch (Philox keyed on the
+GLOBAL triple index, so the draw does not depend on the number of ranks), the rows a rank's
+triples touch come from their owners, the rank runs the step kernels on them, and every row's
+change travels back to its owner, who adds the changes in rank order (deterministic).  Relation
+rows are replicated and take every rank's change in the same rank order.
 
-The local compute is pluggable (`LocalBackend`) so that the routing can be tested on CPU
-with gloo; the CUDA backend calls libhole_b200 through HoleEngine.
+Two trainers implement this:
+  * P2PRowShardedTrainer (GPUs with peer access; the default) -- one library call per step
+    (hole_shard_step): the training kernel gathers rows straight from the owners' shards over
+    NVLink and stores the row deltas into the owners' staging buffers; no NCCL, no host
+    synchronisation inside a step (include/hole_b200.h, csrc/hole_shard.cuh);
+  * RowShardedTrainer -- generic all-to-all version (NCCL or gloo) with a pluggable local
+    backend, which is what the CPU tests drive against the oracle.
+Ranking: candidates are sharded by row block; the true candidate's score comes from its owner
+(all-reduce of a zero-initialised vector), the int32 counts are all-reduced.
 """
 import json
 import os
@@ -25,7 +25,6 @@ import sys
 import time
 
 import numpy as np
-import collections
 
 import torch
 
@@ -75,11 +74,25 @@ class CudaBackend:
         self.width = self.eng.row_stride
         self.dim = dim
         self.device = self.eng.device
-        self.W = torch.zeros((n_relations + 3 * max_batch, self.width), dtype=torch.float32, device=self.device)
-        self.D = torch.zeros_like(self.W)          # row deltas of one step (delta-mode kernels)
-        self.eng.table = self.W
+        self.max_batch = int(max_batch)
+        self._W = self._D = None
         if type_of is not None:
             self.eng.set_types(type_of, csr_off, csr_ids)
+
+    @property
+    def W(self):
+        """Step table [relations | fetched rows] of the generic trainer (allocated on first use)."""
+        if self._W is None:
+            self._W = torch.zeros((self.R + 3 * self.max_batch, self.width), dtype=torch.float32, device=self.device)
+            self.eng.table = self._W
+        return self._W
+
+    @property
+    def D(self):
+        """Row deltas of one step (delta-mode kernels) of the generic trainer."""
+        if self._D is None:
+            self._D = torch.zeros_like(self.W)
+        return self._D
 
     def pad_rows(self, E):
         """checkpoint layout [n, dim] -> device layout [n, width]"""
@@ -99,6 +112,7 @@ class CudaBackend:
         return side, neg.long()
 
     def step(self, n_rows, pos, neg, side, margin, lr):
+        self.W                                   # the engine's table is the step table
         return self.eng.train_step(pos.to(torch.int32), neg.to(torch.int32), side, margin, lr)
 
     # fast path: plan on a side stream, deltas written by the kernels, owner-side row adds
@@ -106,6 +120,7 @@ class CudaBackend:
         self.eng.train_step_plan(pos_i32, neg_i32)
 
     def step_delta(self, n_rows, pos_i32, neg_i32, side, margin, lr):
+        self.W
         self.D[:n_rows].zero_()
         return self.eng.train_step_delta(pos_i32, neg_i32, side, margin, lr, self.D)
 
@@ -254,8 +269,8 @@ class RowShardedTrainer:
         send_counts, recv_counts = self._route(uniq)
         ids_in = self._a2a(uniq, send_counts, recv_counts)
         rows_in = self._a2a(self.shard.index_select(0, ids_in - self.begin + R), recv_counts, send_counts)
-        n_mine = self.shard.shape[0] - R
-        table = torch.cat([self.shard, rows_in], dim=0)                 # [R | my block | fetched]
+        n_mine = self.end - self.begin                                  # (the last shard may carry padding rows)
+        table = torch.cat([self.shard[:R + n_mine], rows_in], dim=0)    # [R | my block | fetched]
         tr = q[:, true_col]
         # true candidate: local index if mine, else below / above my candidate range
         tr_loc = torch.where(tr < self.begin, torch.zeros_like(tr) - 1 + R,       # < ent_begin
@@ -311,168 +326,143 @@ def make_trainer(n_relations, n_entities, dim, backend, dist, log=None):
     return RowShardedTrainer(n_relations, n_entities, dim, backend, dist)
 
 
-class _Prepared:
-    """Table-independent part of one step (corruption, routing, update plan), built ahead."""
-    __slots__ = ("key", "side", "uniq", "cuts", "pos_w", "neg_w", "done")
-
-
 class P2PRowShardedTrainer(RowShardedTrainer):
-    """The same protocol with every exchange done by our own kernels over NVLink peer memory,
-    and no host synchronisation inside a step.  Each rank maps (CUDA IPC) every other rank's
-    step table W, delta table D, request inbox and barrier flags.  Per step:
+    """Row-sharded training with the exchange fused into the training kernel over NVLink peer
+    memory: one library call per step (hole_shard_step, csrc/hole_shard.cuh).  Every rank maps
+    (CUDA IPC) every other rank's shard, delta staging, relation staging, request inbox and flags.
 
-      side stream (table-independent, may run one step ahead -- pass `next_pos`):
-        corrupt -> route (dedup 3B ids, per-owner cuts, triples re-indexed to W rows; device
-        counts) -> update plan
-      compute stream:
-        post    : my request lists go straight into the owners' inboxes             (peer stores)
-        -- barrier --
-        push    : as an owner, copy the requested rows into the requesters' W       (peer stores)
-        -- barrier --
-        K1 + K3 in delta mode on W -> D
-        -- barrier --
-        pull    : as an owner, read the requesters' D rows and add them to my shard (peer loads),
-                  requester by requester in rank order -> deterministic; the replicated relation
-                  block takes every rank's relation deltas the same way (replicas stay
-                  bit-identical without an all-reduce)
+      side stream, one step ahead (pass `next_pos`):  Philox corruption -> request routing -> update plan
+      compute stream:  post request lists -> K1 gathers rows from the owners' shards and stores row
+                       deltas into the owners' staging buffers -> K3 -> relation deltas + "delivered"
+                       flag -> owner adds the staged deltas in rank order + "current" flag
 
-    No NCCL call inside a step; the barriers are a one-warp kernel on peer flags.
-    Inboxes are double buffered by step parity (a fast rank may post step s+1 while a slow
-    owner still pulls step s); W and D are protected by the barriers."""
+    No NCCL call and no host synchronisation inside a step."""
 
-    def __init__(self, n_relations, n_entities, dim, backend, dist):
+    def __init__(self, n_relations, n_entities, dim, backend, dist, timeout_s=0.0, check_every=256):
         super().__init__(n_relations, n_entities, dim, backend, dist)
         from torch.multiprocessing.reductions import reduce_tensor
-        dev, G = backend.device, self.world
-        self.cap = (backend.W.shape[0] - self.R)                    # 3 * max_batch rows
+        dev, G, R = backend.device, self.world, self.R
+        eng = backend.eng
+        if eng.type_of is None:
+            raise ValueError("the backend needs the type tables (type_of, csr_off, csr_ids) for the corruption")
+        self.max_batch = backend.max_batch
+        self.cap = 3 * self.max_batch
+        width = backend.width
+        self.shard = torch.zeros((R + self.rows_per, width), dtype=torch.float32, device=dev)
+        self.stage = torch.zeros((G, self.cap, width), dtype=torch.float32, device=dev)
+        self.relstage = torch.zeros((G, max(R, 1), width), dtype=torch.float32, device=dev)
         self.inbox = torch.zeros((2, G, self.cap), dtype=torch.int32, device=dev)
         self.meta = torch.zeros((2, G, 2), dtype=torch.int32, device=dev)
-        self.flags = torch.zeros(G, dtype=torch.int32, device=dev)
-        mine = [backend.W, backend.D, self.inbox, self.meta, self.flags]
-        everyone = [None] * G
-        dist.all_gather_object(everyone, ([reduce_tensor(t) for t in mine], dev.index))
-        peers, failure = [], None
-        for k, (handles, dev_k) in enumerate(everyone):
-            if k == self.my_rank:
-                peers.append(mine)
-                continue
-            # Open the peer's allocation in MY device's address space (argument 6 of torch's
-            # rebuild is the device the IPC handle is opened on): the tensor then reads as
-            # local to torch while its pages live on GPU k -- kernels launched on my device
-            # reach it over NVLink.  Opened on device k instead, our kernels fault on it
-            # (tools/p2p_diag.py, variant A).
-            try:
-                backend.eng.enable_peer_access(dev_k)
-                peers.append([fn(*(list(a[:6]) + [dev.index] + list(a[7:]))) for fn, a in handles])
-            except Exception as e:                       # no P2P / IPC between these two GPUs
-                failure = f"rank {self.my_rank} cannot map rank {k}'s buffers: {e}"
-                break
-        # every rank must reach the same verdict, or the first barrier kernel would spin
-        verdicts = [None] * G
-        dist.all_gather_object(verdicts, failure)
-        bad = [v for v in verdicts if v]
-        if bad:
-            raise PeerMemoryUnavailable("; ".join(bad))
-        self._finish_init(backend, dist, peers, dev, G)
-
-    def _finish_init(self, backend, dist, peers, dev, G):
-        self._peers = peers                                         # keeps the mappings alive
-        pa = backend.eng.peer_array
-        self.peer_W = pa([p[0] for p in peers])
-        self.peer_D = pa([p[1] for p in peers])
-        self.peer_inbox = [pa([p[2][b] for p in peers]) for b in range(2)]
-        self.peer_meta = [pa([p[3][b] for p in peers]) for b in range(2)]
-        self.peer_flags = pa([p[4] for p in peers])
-        B3 = self.cap
-        self._bufs = [dict(uniq=torch.zeros(B3, dtype=torch.int32, device=dev),
-                           cuts=torch.zeros(G + 1, dtype=torch.int32, device=dev),
-                           pos_w=torch.zeros((B3 // 3, 3), dtype=torch.int32, device=dev),
-                           neg_w=torch.zeros(B3 // 3, dtype=torch.int32, device=dev)) for _ in range(2)]
-        self._n_prepared = 0
-        self._ahead = None
-        self.prep_stream = torch.cuda.Stream(device=dev, priority=-1)      # small kernels the next step waits for
+        self.flags = torch.zeros((2, G), dtype=torch.int32, device=dev)
         self.barrier_err = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._epoch = 0
-        self._parity = 0
-        self.max_run_ahead = int(os.environ.get("HOLE_SHARDED_RUN_AHEAD", "0"))
-        self._inflight = collections.deque()
-        torch.cuda.synchronize()
-        dist.barrier()
+        mine = [self.shard, self.stage, self.relstage, self.inbox, self.meta, self.flags]
+        if G == 1:
+            peers = [mine]
+        else:
+            everyone = [None] * G
+            dist.all_gather_object(everyone, ([reduce_tensor(t) for t in mine], dev.index))
+            peers, failure = [], None
+            for k, (handles, dev_k) in enumerate(everyone):
+                if k == self.my_rank:
+                    peers.append(mine)
+                    continue
+                # Open the peer's allocation in MY device's address space (argument 6 of torch's
+                # rebuild is the device the IPC handle is opened on): the tensor then reads as
+                # local to torch while its pages live on GPU k -- kernels launched on my device
+                # reach it over NVLink.
+                try:
+                    eng.enable_peer_access(dev_k)
+                    peers.append([fn(*(list(a[:6]) + [dev.index] + list(a[7:]))) for fn, a in handles])
+                except Exception as e:                       # no P2P / IPC between these two GPUs
+                    failure = f"rank {self.my_rank} cannot map rank {k}'s buffers: {e}"
+                    break
+            # every rank must reach the same verdict, or the first flag wait would spin
+            verdicts = [None] * G
+            dist.all_gather_object(verdicts, failure)
+            bad = [v for v in verdicts if v]
+            if bad:
+                raise PeerMemoryUnavailable("; ".join(bad))
+        self._bind(peers, timeout_s)
+        self.check_every = int(check_every)
+        self._since_check = 0
+        if G > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
 
-    def _barrier(self):
-        self._epoch += 1
-        self.be.eng.shard_barrier(self.world, self.my_rank, self._epoch, self.peer_flags, self.barrier_err)
+    def _bind(self, peers, timeout_s=0.0):
+        self._peers = peers                                         # keeps the mappings alive
+        pa = self.be.eng.peer_array
+        self.be.eng.shard_init(self.world, self.my_rank, self.R, self.n_ent, self.rows_per, self.max_batch,
+                               self.shard, *[pa([p[i] for p in peers]) for i in range(6)], self.barrier_err,
+                               timeout_s)
+
+    def load_embeddings(self, E):
+        E = torch.as_tensor(E)
+        mine = torch.cat([E[: self.R], E[self.begin:self.end]], dim=0)
+        self.shard.zero_()
+        self.shard[: mine.shape[0]].copy_(self.be.pad_rows(mine))
+        return self
+
+    def load_shard(self, rows):
+        """rows: device [R + n_mine, row_stride] already in the padded layout (bench: generated on the GPU)."""
+        self.shard.zero_()
+        self.shard[: rows.shape[0]].copy_(rows)
+        return self
 
     def check_barriers(self):
-        """Raises if a peer ever failed to reach a barrier (host synchronisation)."""
-        if int(self.barrier_err.item()) != 0:
-            raise RuntimeError("a peer did not reach a step barrier within 10 s; the tables are inconsistent")
+        """Raises if a peer ever failed to reach a step barrier (host synchronisation)."""
+        self._since_check = 0
+        if self.be.eng.shard_poll():
+            raise RuntimeError("a peer did not reach a step barrier in time; the sharded tables are inconsistent")
 
     def gather_embeddings(self):
         self.check_barriers()
         return super().gather_embeddings()
 
-    def _prepare(self, pos_local, seed, step, after):
-        """Enqueue corrupt + route + plan of `step` on the side stream, once `after` (an event
-        of the compute stream that covers pos_local and the last use of the buffer set) is done."""
-        eng, R, G = self.be.eng, self.R, self.world
-        pos = torch.as_tensor(pos_local)
-        B = pos.shape[0]
-        assert 3 * B <= self.cap
-        buf = self._bufs[self._n_prepared & 1]
-        self._n_prepared += 1
-        p = _Prepared()
-        p.key = (int(seed), int(step), B)
-        p.uniq, p.cuts, p.pos_w, p.neg_w = buf["uniq"], buf["cuts"], buf["pos_w"][:B], buf["neg_w"][:B]
-        with torch.cuda.stream(self.prep_stream):
-            self.prep_stream.wait_event(after)
-            if pos.is_cuda:
-                pos.record_stream(self.prep_stream)      # the caller may drop it right after this call
-            if pos.device != self.shard.device or pos.dtype != torch.int32 or not pos.is_contiguous():
-                pos = pos.to(self.shard.device, non_blocking=True).to(torch.int32).contiguous()
-            p.side, neg = eng.corrupt_batch(pos, seed, step, self.my_rank * B)
-            eng.shard_route(pos, neg, R, R + self.n_ent, self.rows_per, G, p.uniq, p.cuts, p.pos_w, p.neg_w)
-            p.done = self.prep_stream.record_event()
-            self.be.plan(p.pos_w, p.neg_w)           # the library's plan stream takes over from here
-        return p
+    def rank(self, *a, **kw):
+        self.check_barriers()
+        return super().rank(*a, **kw)
+
+    def _as_slice(self, pos):
+        pos = torch.as_tensor(pos)
+        if pos.device != self.shard.device or pos.dtype != torch.int32 or not pos.is_contiguous():
+            pos = pos.to(self.shard.device, non_blocking=True).to(torch.int32).contiguous()
+        return pos
 
     def train_step(self, pos_local, seed, step, margin, lr, next_pos=None):
-        """next_pos: the slice of step + 1, if known -- its corruption, routing and plan are
-        then built on the side stream while this step's exchange and kernels run."""
-        eng, be, R, G = self.be.eng, self.be, self.R, self.world
-        main = torch.cuda.current_stream()
-        if self.max_run_ahead > 0:                 # bound how far the host runs ahead of the GPU
-            if len(self._inflight) >= self.max_run_ahead:
-                self._inflight.popleft().synchronize()
-        entry = main.record_event()
-        if self.max_run_ahead > 0:
-            self._inflight.append(entry)
-        B = int(pos_local.shape[0])
-        p, self._ahead = self._ahead, None
-        if p is None or p.key != (int(seed), int(step), B):
-            with _Section("prepare (corrupt, route, plan)"):
-                p = self._prepare(pos_local, seed, step, entry)
-        main.wait_event(p.done)
-        par = self._parity
-        self._parity ^= 1
-        inbox, meta = self.inbox[par], self.meta[par]
-        with _Section("post requests to owners"):
-            eng.shard_post(p.uniq, p.cuts, G, self.my_rank, self.cap, self.peer_inbox[par], self.peer_meta[par])
-            self._barrier()                        # every inbox is complete
-        with _Section("push rows to requesters"):
-            eng.shard_push(self.shard, R - self.begin, inbox, meta, G, self.cap, R, self.peer_W, be.W, be.D)
-            self._barrier()                        # every W is complete
-        with _Section("local step (K1+K3, delta mode)"):
-            loss = eng.train_step_delta(p.pos_w, p.neg_w, p.side, margin, lr, be.D)
-        if next_pos is not None:
-            with _Section("prepare next (side stream)"):
-                self._ahead = self._prepare(next_pos, seed, step + 1, entry)
-        with _Section("pull deltas from requesters"):
-            self._barrier()                        # every D is complete
-            # entity deltas from the requesters + the relation block of every rank, in rank order
-            eng.shard_pull(self.shard, R - self.begin, inbox, meta, G, self.cap, R, self.peer_D,
-                           add_replicated=True)
+        """pos_local: this rank's [B,3] slice of the global batch (device int32 tensors are used as they
+        are and must stay alive until the step has run).  next_pos: the slice of step + 1, if known --
+        its corruption, routing and plan are then built on the side stream while this step runs."""
+        eng = self.be.eng
+        pos = self._as_slice(pos_local)
+        keep = [pos]
+        if getattr(self, "_prepared_key", None) != (pos.data_ptr(), pos.shape[0], int(seed), int(step)):
+            eng.shard_prepare(pos, seed, step)              # nothing was built ahead for this step
+        self._prepared_key = None
+        if next_pos is not None:                            # enqueue before the step, so that it overlaps it
+            nxt = self._as_slice(next_pos)
+            keep.append(nxt)
+            eng.shard_prepare(nxt, seed, step + 1)
+            self._prepared_key = (nxt.data_ptr(), nxt.shape[0], int(seed), int(step) + 1)
+        loss = eng.shard_step(pos, seed, step, margin, lr)
+        self._keep = keep                                   # the side stream may still read them
+        self._since_check += 1
+        if self.check_every and self._since_check >= self.check_every:
+            self.check_barriers()
         return loss
+
+    def train_steps(self, triples_i32, batch_size, seed, first_step, margin, lrs):
+        """n_steps consecutive steps on device-resident slices [n_steps*B, 3] without returning to the
+        host (hole_shard_steps).  Returns this rank's per-step loss sums (device)."""
+        sums = self.be.eng.shard_steps(triples_i32, batch_size, seed, first_step, margin, lrs)
+        self._since_check += triples_i32.shape[0] // batch_size
+        return sums
+
+    def train_steps_host(self, triples_host, batch_size, seed, first_step, margin, lrs):
+        """Same from pinned host triples; returns numpy loss sums (blocks)."""
+        out = self.be.eng.shard_steps_host(triples_host, batch_size, seed, first_step, margin, lrs)
+        self.check_barriers()
+        return out
 
 
 # --------------------------------------------------------------------------------------

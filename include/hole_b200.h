@@ -57,7 +57,7 @@ typedef struct hole_ctx hole_ctx;
 #define HOLE_RANK_BF16X3 1       /* split-bf16 (hi*hi + lo*hi + hi*lo): ranks match fp32 except within ~3e-5 of a tie; dim <= 320 */
 
 /* ABI version of this header; hole_abi_version() returns the library's. */
-#define HOLE_ABI_VERSION 1
+#define HOLE_ABI_VERSION 2
 HOLE_API int hole_abi_version(void);
 
 /* Thread-local message of the last failing call on this thread ("" if none). */
@@ -124,8 +124,8 @@ HOLE_API int hole_train_step(hole_ctx* ctx, float* table, const int32_t* pos, co
  * overlaps whatever the caller enqueues in between (e.g. the row exchange).
  * hole_add_rows: table[ids[k] + id_offset] += rows[k] for k < n, ids unique within a call.
  * hole_gather_rows: dst_rows[k] = table[ids[k] + id_offset].  For both, the row buffer may be
- * PEER device memory (an IPC-mapped buffer of another rank): the owner pushes requested rows
- * into, and pulls row deltas out of, the requester's step tables directly over NVLink. */
+ * PEER device memory (an IPC-mapped buffer of another rank).  These serve the generic
+ * (NCCL / gloo all-to-all) sharded trainer; the NVLink path is hole_shard_step below. */
 HOLE_API int hole_train_step_ex(hole_ctx* ctx, float* table, float* delta_out, const int32_t* pos,
                        const int32_t* neg_ent, int side, int64_t B, float margin, float lr,
                        float* loss_out, float* sigma_out, void* stream);
@@ -149,44 +149,73 @@ HOLE_API int hole_train_step_logloss(hole_ctx* ctx, float* table, float* delta_w
                                      uint64_t step, float lr, float l2, float* loss_out, float* l2_loss_out,
                                      int32_t* neg_out, int32_t* sides_out, void* stream);
 
-/* ---- multi-GPU step routing over NVLink peer memory (no counterpart in the reference;
- * SURVEY.md 8e).  All counts stay on the device: a sharded step never synchronises the host.
- * Buffers marked PEER may live on another GPU (mapped with CUDA IPC after
- * hole_enable_peer_access).  world <= HOLE_MAX_RANKS.
+/* ---- row-sharded training over NVLink peer memory (no counterpart in the reference, which is
+ * single-device).  One process per GPU.  Rank o owns entity rows
+ * [n_relations + o*rows_per_rank, +rows_per_rank); the relation rows are replicated:
+ *   shard     float32 [n_relations + rows_per_rank, row_stride]  = [relations | my block]
+ * Buffers marked PEER live on every rank and are mapped on all of them (CUDA IPC after
+ * hole_enable_peer_access); the arrays below hold rank k's buffer at index k (index `me` = mine):
+ *   peer_shard     PEER  the shards (rows are GATHERED from them by the training kernel)
+ *   peer_stage     PEER  float32 [world][3*max_batch][row_stride]  row deltas, slice k written by rank k
+ *   peer_relstage  PEER  float32 [world][n_relations][row_stride]  relation deltas, slice k by rank k
+ *   peer_inbox     PEER  int32 [2][world][3*max_batch]             request lists (double buffered)
+ *   peer_meta      PEER  int32 [2][world][2]                       (count, offset) of each list
+ *   peer_flags     PEER  int32 [2][world], zero-initialised        epochs: [0] shard current, [1] deltas delivered
+ *   err_flag       device int32, zero: set when a peer does not arrive within timeout_s (<= 0: 600 s)
+ * type_of / csr_off / csr_ids: the type tables of hole_corrupt (kept by reference).
  *
+ * hole_shard_step: one batch-synchronous step of the GLOBAL batch = concatenation over ranks of the
+ *   ranks' `pos` slices (B triples each, global row ids, device): Philox corruption keyed on the
+ *   global triple index me*B + i (so the result does not depend on `world`), rows gathered from their
+ *   owners' shards over NVLink inside the training kernel, which also stores every row's delta into
+ *   its owner's staging buffer; owners then add the staged deltas in rank order (deterministic; the
+ *   relation replicas stay bit-identical).  No host synchronisation, no NCCL.  Every rank must call
+ *   it with the same (B, seed, step) sequence.  loss_out float32[B] (hinge of my slice).
+ * hole_shard_prepare: optional; builds the table-independent part (corruption, request routing,
+ *   update plan) of a later hole_shard_step call with the same (pos, B, seed, step) on a side stream,
+ *   so that it overlaps the step before it.
+ * hole_shard_step_compute / _apply: the two halves of hole_shard_step (test hook: with several
+ *   virtual ranks on one GPU, run compute on every rank, then apply on every rank).
+ * hole_shard_steps / hole_shard_steps_host: n_steps consecutive steps from device / host triples
+ *   [n_steps*B, 3] (this rank's slices), one step prepared ahead; lr [host] float32[n_steps];
+ *   loss sums of my slices to loss_sum_out (device) / loss_sum_host (blocks until they are there).
+ * hole_shard_poll: synchronises `stream` and reports whether a flag wait has timed out; the tables
+ *   are then inconsistent and the caller must stop. */
+#define HOLE_MAX_RANKS 16
+HOLE_API int hole_shard_init(hole_ctx* ctx, int world, int me, int64_t n_relations, int64_t n_entities,
+                             int64_t rows_per_rank, int64_t max_batch, float* shard,
+                             void* const* peer_shard, void* const* peer_stage, void* const* peer_relstage,
+                             void* const* peer_inbox, void* const* peer_meta, void* const* peer_flags,
+                             int32_t* err_flag, double timeout_s, const int32_t* type_of,
+                             const int64_t* csr_off, const int32_t* csr_ids);
+HOLE_API int hole_shard_prepare(hole_ctx* ctx, const int32_t* pos, int64_t B, uint64_t seed, uint64_t step,
+                                void* stream);
+HOLE_API int hole_shard_step(hole_ctx* ctx, const int32_t* pos, int64_t B, uint64_t seed, uint64_t step,
+                             float margin, float lr, float* loss_out, void* stream);
+HOLE_API int hole_shard_step_compute(hole_ctx* ctx, const int32_t* pos, int64_t B, uint64_t seed, uint64_t step,
+                                     float margin, float lr, float* loss_out, void* stream);
+HOLE_API int hole_shard_step_apply(hole_ctx* ctx, void* stream);
+HOLE_API int hole_shard_steps(hole_ctx* ctx, const int32_t* triples, int64_t B, int64_t n_steps, uint64_t seed,
+                              uint64_t first_step, float margin, const float* lr, float* loss_sum_out,
+                              void* stream);
+HOLE_API int hole_shard_steps_host(hole_ctx* ctx, const int32_t* triples_host, int64_t B, int64_t n_steps,
+                                   uint64_t seed, uint64_t first_step, float margin, const float* lr,
+                                   float* loss_sum_host, void* stream);
+HOLE_API int hole_shard_poll(hole_ctx* ctx, int* timed_out, void* stream);
+
+/* Building blocks of the step, exported for tests.
  * hole_shard_route: dedup the 3B entity rows {head, tail, corrupt entity} of this rank's B
  *   triples (global row ids).  uniq_out[0..U) ascending, cuts_out[o] = first slot owned by rank
- *   o (rank o owns rows [n_relations + o*rows_per_rank, +rows_per_rank)), cuts_out[world] = U;
- *   pos_w / neg_w = the triples re-indexed to step-table rows n_relations + slot (relation
- *   column copied).  uniq_out needs 3B entries, cuts_out world+1.
+ *   o, cuts_out[world] = U; pos_w / neg_w = the triples re-indexed to request-list rows
+ *   n_relations + slot (relation column copied).  uniq_out needs 3B entries, cuts_out world+1.
  * hole_shard_post: writes uniq[cuts[o]..cuts[o+1]) to rank o's inbox (PEER int32 [world][cap],
- *   row `me`) and (count, cuts[o]) to rank o's meta (PEER int32 [world][2], row `me`).
- * hole_shard_push: for every requester k, copies shard[inbox[k][g] + id_offset] to
- *   peer_tables[k] (PEER step table) row row_base + meta[k][1] + g, g < meta[k][0].  With
- *   my_table / my_delta (both or neither) it also refreshes the replicated relation block:
- *   my_table[0..row_base) = shard[0..row_base), my_delta[0..row_base) = 0.
- * hole_shard_barrier: barrier across the ranks' streams through peer flags (PEER int32 [world]
- *   each, zero-initialised); `epoch` must grow by one per call on every rank.  A peer that does
- *   not arrive within 10 s sets *err_flag (device int32) instead of hanging the GPU.
- * hole_shard_pull: for k = 0..world-1 in order, shard[inbox[k][g] + id_offset] +=
- *   peer_deltas[k] (PEER delta table) row row_base + meta[k][1] + g.  With add_replicated it also
- *   adds rows [0, row_base) of every peer_deltas[k] to shard[0, row_base) in the same rank order
- *   (the replicated relation block: all replicas stay bit-identical, no all-reduce needed). */
-#define HOLE_MAX_RANKS 16
+ *   row `me`) and (count, cuts[o]) to rank o's meta (PEER int32 [world][2], row `me`). */
 HOLE_API int hole_shard_route(hole_ctx* ctx, const int32_t* pos, const int32_t* neg_ent, int64_t B,
                               int64_t n_relations, int64_t n_rows_global, int64_t rows_per_rank, int world,
                               int32_t* uniq_out, int32_t* cuts_out, int32_t* pos_w, int32_t* neg_w,
                               void* stream);
 HOLE_API int hole_shard_post(hole_ctx* ctx, const int32_t* uniq, const int32_t* cuts, int world, int me,
                              int64_t cap, void* const* peer_inbox, void* const* peer_meta, void* stream);
-HOLE_API int hole_shard_push(hole_ctx* ctx, const float* shard, int64_t id_offset, const int32_t* inbox,
-                             const int32_t* meta, int world, int64_t cap, int64_t row_base,
-                             void* const* peer_tables, float* my_table, float* my_delta, void* stream);
-HOLE_API int hole_shard_barrier(hole_ctx* ctx, int world, int me, int32_t epoch, void* const* peer_flags,
-                                int32_t* err_flag, void* stream);
-HOLE_API int hole_shard_pull(hole_ctx* ctx, float* shard, int64_t id_offset, const int32_t* inbox,
-                             const int32_t* meta, int world, int64_t cap, int64_t row_base,
-                             void* const* peer_deltas, int add_replicated, void* stream);
 
 /* Enable loads/stores from ctx's device to memory of `peer_device` (no-op if already on). */
 HOLE_API int hole_enable_peer_access(hole_ctx* ctx, int peer_device);

@@ -357,30 +357,19 @@ def test_logloss_training_reduces_the_loss(eng_mod):
 
 
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_shard_route_post_push_pull_virtual_ranks(eng_mod, world):
-    """The multi-GPU exchange primitives with `world` virtual ranks on one GPU (peer buffers
-    are local tensors): route == np.unique / searchsorted, push delivers exactly the
-    requested rows, pull adds the delta rows in rank order (bit-exact vs a float32 loop)."""
+def test_shard_route_and_post_virtual_ranks(eng_mod, world):
+    """Request routing of the sharded step with `world` virtual ranks on one GPU (peer buffers are
+    local tensors): route == np.unique / searchsorted, post delivers every owner's slice."""
     from graphembeddings_b200.sharded import row_partition
     rng = np.random.default_rng(100 + world)
     dim, R, n_ent, B = 150, 5, 1000, 257
     e = eng_mod.HoleEngine(R + n_ent, dim)
-    stride, cap = e.row_stride, 3 * B
+    cap = 3 * B
     rows_per = row_partition(n_ent, world)
-    table = rng.standard_normal((R + n_ent, stride)).astype(np.float32)
     dev = e.device
-    shards, begins = [], []
-    for o in range(world):
-        b0 = R + o * rows_per
-        b1 = min(R + n_ent, b0 + rows_per)
-        shards.append(torch.from_numpy(np.concatenate([table[:R], table[b0:b1]])).to(dev))
-        begins.append(b0)
-    inbox = [torch.zeros((world, cap), dtype=torch.int32, device=dev) for _ in range(world)]
+    inbox = [torch.full((world, cap), -7, dtype=torch.int32, device=dev) for _ in range(world)]
     meta = [torch.zeros((world, 2), dtype=torch.int32, device=dev) for _ in range(world)]
-    W = [torch.zeros((R + cap, stride), dtype=torch.float32, device=dev) for _ in range(world)]
-    Dl = [torch.from_numpy(rng.standard_normal((R + cap, stride)).astype(np.float32)).to(dev) for _ in range(world)]
     pa = e.peer_array
-    uniqs = []
     for k in range(world):
         pos = np.stack([R + rng.integers(0, n_ent, B), R + rng.integers(0, n_ent, B), rng.integers(0, R, B)], 1)
         pos[:5, 1] = pos[:5, 0]                                  # head == tail rows
@@ -404,26 +393,130 @@ def test_shard_route_post_push_pull_virtual_ranks(eng_mod, world):
         assert np.array_equal(want[pw[:, 0] - R], pos[:, 0]) and np.array_equal(want[pw[:, 1] - R], pos[:, 1])
         assert np.array_equal(pw[:, 2], pos[:, 2]) and np.array_equal(want[nw - R], neg)
         e.shard_post(uniq, cuts, world, k, cap, pa(inbox), pa(meta))
-        uniqs.append(want)
-    for o in range(world):
-        e.shard_push(shards[o], R - begins[o], inbox[o], meta[o], world, cap, R, pa(W))
-    for k in range(world):
-        got = W[k].cpu().numpy()
-        assert np.array_equal(got[R:R + len(uniqs[k])], table[uniqs[k]])
-        assert not got[R + len(uniqs[k]):].any()
-    for o in range(world):
-        e.shard_pull(shards[o], R - begins[o], inbox[o], meta[o], world, cap, R, pa(Dl), add_replicated=True)
-    rel = table[:R].copy()
-    for k in range(world):
-        rel += Dl[k].cpu().numpy()[:R]
-    for o in range(world):
-        assert np.array_equal(shards[o].cpu().numpy()[:R], rel)   # replicated block: same order everywhere
-    expect = table.copy()
-    for k in range(world):                                       # rank order, float32 adds
-        expect[uniqs[k]] += Dl[k].cpu().numpy()[R:R + len(uniqs[k])]
-    for o in range(world):
-        n_o = shards[o].shape[0] - R
-        assert np.array_equal(shards[o].cpu().numpy()[R:], expect[begins[o]:begins[o] + n_o])
+        for o in range(world):
+            lo, hi = cuts_h[o], cuts_h[o + 1]
+            got = inbox[o][k].cpu().numpy()
+            assert np.array_equal(got[:hi - lo], want[lo:hi]) and (got[hi - lo:] == -7).all()
+            assert meta[o][k].tolist() == [hi - lo, lo]
+
+
+class _VirtualRanks:
+    """`world` ranks of the row-sharded step on ONE GPU: one engine (library context) per rank, every
+    "peer" buffer a local tensor.  A step runs its compute half on every rank, then its apply half on
+    every rank, all on one stream -- so every flag a kernel waits for has been set by an earlier
+    kernel of the stream."""
+
+    def __init__(self, eng_mod, kg, world, B):
+        from graphembeddings_b200.sharded import row_partition
+        self.world, self.B, self.R = world, B, kg.n_relations
+        off, ids = D.build_type_csr(kg.type_of)
+        self.rows_per = row_partition(kg.n_entities, world)
+        self.engs, self.bufs = [], []
+        for k in range(world):
+            e = eng_mod.HoleEngine(kg.n_relations + 3 * B, kg.dim).set_types(kg.type_of, off, ids)
+            e.set_relation_count(kg.n_relations)
+            dev, w, cap = e.device, e.row_stride, 3 * B
+            shard = torch.zeros((self.R + self.rows_per, w), dtype=torch.float32, device=dev)
+            b0 = self.R + k * self.rows_per
+            b1 = min(kg.n_rows, b0 + self.rows_per)
+            full = eng_mod.HoleEngine(kg.n_rows, kg.dim).set_embeddings(kg.E)
+            shard[: self.R] = full.table[: self.R]
+            shard[self.R: self.R + (b1 - b0)] = full.table[b0:b1]
+            full.close()
+            self.bufs.append([shard,
+                              torch.zeros((world, cap, w), dtype=torch.float32, device=dev),
+                              torch.zeros((world, max(self.R, 1), w), dtype=torch.float32, device=dev),
+                              torch.zeros((2, world, cap), dtype=torch.int32, device=dev),
+                              torch.zeros((2, world, 2), dtype=torch.int32, device=dev),
+                              torch.zeros((2, world), dtype=torch.int32, device=dev),
+                              torch.zeros(1, dtype=torch.int32, device=dev)])
+            self.engs.append(e)
+        for k, e in enumerate(self.engs):
+            pa = e.peer_array
+            e.shard_init(world, k, self.R, kg.n_entities, self.rows_per, B, self.bufs[k][0],
+                         *[pa([self.bufs[j][i] for j in range(world)]) for i in range(6)], self.bufs[k][6], 5.0)
+        self.kg = kg
+
+    def step(self, slices, seed, step, margin, lr, ahead=None):
+        losses = []
+        for k, e in enumerate(self.engs):
+            if ahead is not None:
+                e.shard_prepare(ahead[k], seed, step + 1)
+            losses.append(e.shard_step(slices[k], seed, step, margin, lr, phase="compute"))
+        for e in self.engs:
+            e.shard_step(None, seed, step, margin, lr, phase="apply")
+        return losses
+
+    def table(self):
+        """[N, dim] gathered from the shards; also checks that the relation replicas are bit-identical."""
+        kg = self.kg
+        rel = self.bufs[0][0][: self.R]
+        ents = []
+        for k in range(self.world):
+            assert torch.equal(self.bufs[k][0][: self.R], rel)
+            assert not self.engs[k].shard_poll()
+            b0 = self.R + k * self.rows_per
+            b1 = min(kg.n_rows, b0 + self.rows_per)
+            ents.append(self.bufs[k][0][self.R: self.R + (b1 - b0)])
+        tab = torch.cat([rel] + ents)
+        tmp = self.engs[0].__class__(kg.n_rows, kg.dim)
+        tmp.table = tab.contiguous()
+        out = tmp.embeddings().cpu().numpy()
+        tmp.table = None
+        tmp.close()
+        return out
+
+
+@pytest.mark.parametrize("world,dim,B", [(1, 150, 300), (2, 256, 257), (3, 150, 129), (4, 64, 200), (8, 150, 65),
+                                         (2, 512, 96)])
+def test_sharded_step_virtual_ranks_matches_single_gpu(eng_mod, world, dim, B):
+    """hole_shard_step (rows gathered from the owners' shards and deltas staged at the owners by the
+    training kernel itself) with `world` virtual ranks against the single-GPU step on the concatenated
+    global batch: identical corruption (global triple index), loss <= 2e-6, table <= 2e-6 after 3
+    chained steps; heavy cross-rank duplicates (Zipf entities), ragged B, d not a multiple of 8."""
+    steps = 3
+    kg = D.synthetic_kg(7, 2000, steps * world * B, 5, dim, seed=500 + world, trained_scale=True, zipf_entities=True)
+    vr = _VirtualRanks(eng_mod, kg, world, B)
+    e, off, ids = _engine(eng_mod, kg)
+    dev = e.device
+    tri = torch.from_numpy(kg.triples).to(dev).view(steps, world, B, 3)
+    for s in range(steps):
+        slices = [tri[s, k].contiguous() for k in range(world)]
+        ahead = [tri[s + 1, k].contiguous() for k in range(world)] if s + 1 < steps and s % 2 == 0 else None
+        if ahead is not None:
+            keep_ahead = ahead
+        if s > 0 and s % 2 == 1:
+            slices = keep_ahead                  # the tensors the step was prepared for
+        losses = vr.step(slices, 11, s, 0.2, 0.1, ahead)
+        gb = kg.triples[s * world * B:(s + 1) * world * B]
+        side, neg = e.corrupt_batch(gb, 11, s)
+        want = e.train_step(gb, neg, side, 0.2, 0.1).cpu().numpy().reshape(world, B)
+        for k in range(world):
+            assert np.abs(losses[k].cpu().numpy() - want[k]).max() <= 2e-6
+    got = vr.table()
+    ref = e.embeddings().cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-6
+    assert np.abs(ref - kg.E).max() > 1e-4
+
+
+def test_sharded_steps_call_matches_step_by_step(eng_mod):
+    """hole_shard_steps (the multi-step entry, one step prepared ahead) == hole_shard_step called per
+    step, bit for bit, and its loss sums are the sums of the per-triple losses (world = 1)."""
+    B, steps, dim = 500, 6, 150
+    kg = D.synthetic_kg(7, 3000, steps * B, 5, dim, seed=61, trained_scale=True, zipf_entities=True)
+    lrs = [0.1 / (1 + s) for s in range(steps)]
+    a, b = _VirtualRanks(eng_mod, kg, 1, B), _VirtualRanks(eng_mod, kg, 1, B)
+    tri = torch.from_numpy(kg.triples).to(a.engs[0].device)
+    sums = a.engs[0].shard_steps(tri, B, 3, 10, 0.2, lrs).cpu().numpy()
+    want = []
+    for s in range(steps):
+        loss = b.step([tri[s * B:(s + 1) * B]], 3, 10 + s, 0.2, lrs[s])[0]
+        want.append(float(loss.double().sum()))
+    assert np.abs(sums - np.array(want)).max() <= 1e-3
+    assert np.array_equal(a.table(), b.table())
+    host = _VirtualRanks(eng_mod, kg, 1, B)
+    hs = host.engs[0].shard_steps_host(kg.triples, B, 3, 10, 0.2, lrs)
+    assert np.array_equal(hs, sums) and np.array_equal(host.table(), a.table())
 
 
 def test_delta_mode_writes_every_used_row(eng_mod):
