@@ -35,6 +35,15 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 WORKLOAD = "diffbot_d256"
+
+
+def workload_desc(batch):
+    """The same string in both arms and at every N (the driver compares config.workload)."""
+    return ("diffbot_d256: BASELINE.json configs[1], HolE d=256, 1,200,014-row shared table (14 relations + "
+            "1.2M typed entities, 12 types, one holding 99 %), Zipf relations, type-safe Philox corruption, "
+            f"B={batch} triples per step per GPU")
+
+
 MARGIN, LR0 = 0.2, 0.1
 #: dram__bytes_read.sum + dram__bytes_write.sum per step (K1 + K3) from the `ncu --set full`
 #: captures under profiles/ for (batch, dim); other configurations report null
@@ -200,7 +209,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD}: HolE d=256, 1,200,014-row table, type-safe corruption",
+        "config": {"workload": workload_desc(B),
                    "batch": B, "note": "CPU port of holE.py arithmetic (TensorFlow 1.2 not installable)"},
         "cpu_baseline": {"value": v, "unit": "triples/s", "cores": R.threads(), "kind": "port",
                          "sample": sample},
@@ -285,8 +294,7 @@ def run_ours(args):
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{WORKLOAD}: BASELINE.json configs[1], HolE d=256, 1,200,014-row shared table "
-                        "(14 relations + 1.2M typed entities), type-safe Philox corruption",
+            "workload": workload_desc(B),
             "batch": B, "margin": MARGIN, "lr0": LR0, "triples_generated": int(kg.triples.shape[0]),
             "epoch_triples": 30_000_000, "l2": "table (1.2 GB) larger than L2; no flush",
             "mean_loss_last_pass": mean_loss, "gen_seconds": round(t_gen, 1)},
@@ -325,6 +333,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32768)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-ranking", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="N > 1: skip the 20M-entity d=512 sub-record")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -47,6 +47,7 @@ SIGNATURES = {
     "hole_shard_steps": (_int, [_p, _p, _i64, _i64, _u64, _u64, _f32, _p, _p, _p]),
     "hole_shard_steps_host": (_int, [_p, _p, _i64, _i64, _u64, _u64, _f32, _p, _p, _p]),
     "hole_shard_poll": (_int, [_p, C.POINTER(_int), _p]),
+    "hole_shard_profile_read": (_int, [_p, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "hole_enable_peer_access": (_int, [_p, _int]),
     "hole_gather_rows": (_int, [_p, _p, _p, _i64, _p, _i64, _p]),
     "hole_add_rows": (_int, [_p, _p, _p, _i64, _p, _i64, _p]),

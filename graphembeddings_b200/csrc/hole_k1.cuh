@@ -381,6 +381,10 @@ __device__ __forceinline__ void hole_k1_body(const hole_k1_args& a, const hole_k
   }
   pdl_launch_dependents();    // K3 of this step may start its prologue
   flush_relation();
+  // DM 2: this thread's delta rows went to peer memory with plain stores; the "delivered" flag is raised
+  // by a later kernel from ONE thread, whose fence does not cover stores other SMs still have in flight on
+  // NVLink -- every writer makes its own stores visible system-wide before the kernel ends
+  if (DM == 2) __threadfence_system();
 }
 
 #ifndef HOLE_K1_MAXTHREADS

@@ -31,19 +31,20 @@
 
 constexpr int SHARD_LOSS_CHUNK = 64;     // steps whose loss rows are kept before they are summed
 
-struct hole_shard_prep {                 // table-independent part of one step, built ahead
-  int32_t* uniq = nullptr;               // [cap]      request list: sorted unique global entity rows
-  int32_t* cuts = nullptr;               // [world+1]  first request-list slot per owner
-  int32_t* pos_w = nullptr;              // [B,3]      triples as request-list rows (R + slot), relation kept
-  int32_t* neg_w = nullptr;              // [B]
-  int32_t* neg = nullptr;                // [B]        corrupt entity (global row)
-  const int32_t* pos = nullptr;          // the triples this was built for
-  int64_t B = -1;
-  uint64_t seed = 0, step = 0;
-  int side = 0;
+constexpr int SHARD_PREP_STEPS = 16;     // steps whose table-independent part is built per launch chain
+
+struct hole_shard_prep {                 // table-independent part of a chunk of steps, built ahead
+  int32_t* uniq = nullptr;               // [S][cap]     request lists: sorted unique global entity rows
+  int32_t* cuts = nullptr;               // [S][HOLE_MAX_RANKS+1]  first request-list slot per owner
+  int32_t* pos_w = nullptr;              // [S][B,3]     triples as request-list rows (R + slot), relation kept
+  int32_t* neg_w = nullptr;              // [S][B]
+  int32_t* neg = nullptr;                // [S][B]       corrupt entity (global row)
+  const int32_t* pos = nullptr;          // the triples this was built for: [n_steps][B,3]
+  int64_t B = -1, n_steps = 0, consumed = 0;
+  uint64_t seed = 0, first_step = 0;
   int plan_slot = 0;
   bool valid = false, used = false;
-  cudaEvent_t freed = nullptr;           // recorded when the step that consumed this slot has been enqueued
+  cudaEvent_t freed = nullptr;           // recorded when the last step that reads this slot has been enqueued
 };
 
 struct hole_shard_state {
@@ -68,6 +69,8 @@ struct hole_shard_state {
   hole_shard_prep prep[2];
   int prep_toggle = 0;
   int epoch = 0;                         // steps completed
+  std::vector<cudaEvent_t> prof_ev;      // hole_profile_enable: 6 events per step (phase boundaries)
+  size_t prof_used = 0;
 };
 
 // ------------------------------------------------------------------------------------ kernels
@@ -223,6 +226,7 @@ static void shard_free(hole_ctx* c) {
   }
   cudaFree(s->Drel); cudaFree(s->done); cudaFree(s->loss); cudaFree(s->loss_sum); cudaFree(s->stage_tri);
   cudaFree(s->sums_dev);
+  for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
   if (s->loss_pinned) cudaFreeHost(s->loss_pinned);
   delete s;
   c->shard_state = nullptr;
@@ -242,8 +246,14 @@ extern "C" int hole_shard_init(hole_ctx* c, int world, int me, int64_t n_relatio
   HOLE_CHECK_ARG(max_batch > 0 && 4 * max_batch < (int64_t(1) << 31));
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   shard_free(c);
-  int rc = hole_ws_reserve(c, max_batch, 1);
+  // the training kernel of a sharded step is NVLink-bound: keep a few SMs' worth of block slots free so
+  // that the side stream's routing / plan kernels of the next chunk run beside it, not after it
+  int reserve = 12;
+  if (const char* e = getenv("HOLE_SHARD_RESERVE_SMS")) reserve = atoi(e);
+  int rc = hole_ws_reserve(c, max_batch, SHARD_PREP_STEPS);
   if (rc) return rc;
+  if (world > 1 && reserve > 0 && reserve < c->sm_count / 2)
+    c->k1_groups = c->k1_groups / c->sm_count * (c->sm_count - reserve);
   hole_shard_state* s = new hole_shard_state();
   c->shard_state = s;
   s->world = world; s->me = me; s->R = n_relations; s->n_ent = n_entities; s->rows_per = rows_per_rank;
@@ -274,47 +284,51 @@ extern "C" int hole_shard_init(hole_ctx* c, int world, int me, int64_t n_relatio
   SH_ALLOC(s->loss, (size_t)SHARD_LOSS_CHUNK * max_batch * 4);
   SH_ALLOC(s->loss_sum, (size_t)SHARD_LOSS_CHUNK * 4);
   for (int b = 0; b < 2; ++b) {
-    SH_ALLOC(s->prep[b].uniq, (size_t)s->cap * 4);
-    SH_ALLOC(s->prep[b].cuts, (size_t)(HOLE_MAX_RANKS + 1) * 4);
-    SH_ALLOC(s->prep[b].pos_w, (size_t)max_batch * 12);
-    SH_ALLOC(s->prep[b].neg_w, (size_t)max_batch * 4);
-    SH_ALLOC(s->prep[b].neg, (size_t)max_batch * 4);
+    const size_t S = SHARD_PREP_STEPS;
+    SH_ALLOC(s->prep[b].uniq, S * (size_t)s->cap * 4);
+    SH_ALLOC(s->prep[b].cuts, S * (size_t)(HOLE_MAX_RANKS + 1) * 4);
+    SH_ALLOC(s->prep[b].pos_w, S * (size_t)max_batch * 12);
+    SH_ALLOC(s->prep[b].neg_w, S * (size_t)max_batch * 4);
+    SH_ALLOC(s->prep[b].neg, S * (size_t)max_batch * 4);
     s->prep[b].plan_slot = b;
     HOLE_CUDA_TRY(cudaEventCreateWithFlags(&s->prep[b].freed, cudaEventDisableTiming));
   }
 #undef SH_ALLOC
   HOLE_CUDA_TRY(cudaMemset(s->Drel, 0, std::max<size_t>(1, (size_t)s->R) * rowb));
   HOLE_CUDA_TRY(cudaMemset(s->done, 0, 2 * sizeof(unsigned)));
-  rc = route_reserve(c, 3 * max_batch);
+  rc = route_reserve(c, 3 * max_batch, SHARD_PREP_STEPS);
   if (rc) { shard_free(c); return rc; }
   HOLE_CUDA_TRY(cudaDeviceSynchronize());
   return HOLE_OK;
 }
 
-// corruption + routing + update plan of one step on the library's side stream, once `st` has reached
-// this point (pos must be complete by then)
-static int shard_prepare(hole_ctx* c, const int32_t* pos, int64_t B, uint64_t seed, uint64_t step, cudaStream_t st) {
+// Corruption + routing + update plan of n_steps (<= SHARD_PREP_STEPS) consecutive steps on the library's
+// side stream; pos = [n_steps][B,3].  wait_caller: the side stream first waits for everything enqueued
+// on `st` so far (the triples may have been produced there).
+static int shard_prepare(hole_ctx* c, const int32_t* pos, int64_t B, int64_t n_steps, uint64_t seed,
+                         uint64_t first_step, cudaStream_t st, bool wait_caller) {
   hole_shard_state* s = c->shard_state;
   hole_shard_prep& p = s->prep[s->prep_toggle];
   s->prep_toggle ^= 1;
   cudaStream_t ps = c->plan_stream;
-  HOLE_CUDA_TRY(cudaEventRecord(c->ev_entry, st));
-  HOLE_CUDA_TRY(cudaStreamWaitEvent(ps, c->ev_entry, 0));
-  if (p.used) HOLE_CUDA_TRY(cudaStreamWaitEvent(ps, p.freed, 0));      // its last consumer has been enqueued and is done
-  p.pos = pos; p.B = B; p.seed = seed; p.step = step;
-  p.side = hole_side_coin(seed, step);
+  if (wait_caller) {
+    HOLE_CUDA_TRY(cudaEventRecord(c->ev_entry, st));
+    HOLE_CUDA_TRY(cudaStreamWaitEvent(ps, c->ev_entry, 0));
+  }
+  if (p.used) HOLE_CUDA_TRY(cudaStreamWaitEvent(ps, p.freed, 0));      // its last consumer is done
+  p.pos = pos; p.B = B; p.n_steps = n_steps; p.consumed = 0; p.seed = seed; p.first_step = first_step;
   const uint64_t index_base = (uint64_t)s->me * (uint64_t)B;           // my slice of the global batch
-  dim3 grid((unsigned)std::min<int64_t>((B + 255) / 256, 65535), 1);
-  hole_corrupt_kernel<<<grid, 256, 0, ps>>>(pos, B, 1, s->type_of, s->csr_off, s->csr_ids, seed, step, index_base,
-                                            p.neg, nullptr);
+  dim3 grid((unsigned)std::min<int64_t>((B + 255) / 256, 65535), (unsigned)n_steps);
+  hole_corrupt_kernel<<<grid, 256, 0, ps>>>(pos, B, (int)n_steps, s->type_of, s->csr_off, s->csr_ids, seed,
+                                            first_step, index_base, p.neg, nullptr);
   HOLE_LAUNCHED();
   int rc = shard_route(c, pos, p.neg, B, s->R, s->R + s->rows_per * s->world, s->rows_per, s->world, p.uniq, p.cuts,
-                       p.pos_w, p.neg_w, ps);
+                       p.pos_w, p.neg_w, ps, n_steps, s->cap);
   if (rc) return rc;
   hole_plan& pl = c->plan[p.plan_slot];
   pl.prepared_B = -1;
   pl.prepared_pos = pl.prepared_neg = nullptr;
-  rc = plan_steps(c, pl, p.pos_w, B, 1, nullptr, nullptr, nullptr, 0, 0, p.neg_w, ps);
+  rc = plan_steps(c, pl, p.pos_w, B, n_steps, nullptr, nullptr, nullptr, 0, 0, p.neg_w, ps);
   if (rc) return rc;
   p.valid = true;
   return HOLE_OK;
@@ -332,7 +346,24 @@ extern "C" int hole_shard_prepare(hole_ctx* c, const int32_t* pos, int64_t B, ui
   int rc = shard_check_args(c, pos, B);
   if (rc) return rc;
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
-  return shard_prepare(c, pos, B, seed, step, (cudaStream_t)stream);
+  return shard_prepare(c, pos, B, 1, seed, step, (cudaStream_t)stream, true);
+}
+
+// measurement hook (hole_profile_enable): phase boundary `which` (0..5) of the running step
+static int shard_mark(hole_ctx* c, int which, cudaStream_t st) {
+  hole_shard_state* s = c->shard_state;
+  if (!c->profile) return HOLE_OK;
+  if (which == 0) {
+    if (s->prof_used + 6 > s->prof_ev.size())
+      for (int q = 0; q < 6; ++q) {
+        cudaEvent_t e;
+        HOLE_CUDA_TRY(cudaEventCreate(&e));
+        s->prof_ev.push_back(e);
+      }
+    s->prof_used += 6;
+  }
+  HOLE_CUDA_TRY(cudaEventRecord(s->prof_ev[s->prof_used - 6 + which], st));
+  return HOLE_OK;
 }
 
 // post + K1 + K3 + finish of the step
@@ -344,17 +375,27 @@ extern "C" int hole_shard_step_compute(hole_ctx* c, const int32_t* pos, int64_t 
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   hole_shard_state* s = c->shard_state;
   cudaStream_t st = (cudaStream_t)stream;
+  // the prepared chunk this step belongs to (its next unconsumed step), else prepare it now
   int pi = -1;
-  for (int b = 0; b < 2; ++b)
-    if (s->prep[b].valid && s->prep[b].pos == pos && s->prep[b].B == B && s->prep[b].seed == seed &&
-        s->prep[b].step == step)
+  for (int b = 0; b < 2; ++b) {
+    const hole_shard_prep& q = s->prep[b];
+    if (q.valid && q.B == B && q.seed == seed && q.consumed < q.n_steps && step == q.first_step + (uint64_t)q.consumed &&
+        pos == q.pos + (size_t)q.consumed * B * 3)
       pi = b;
+  }
   if (pi < 0) {
     pi = s->prep_toggle;
-    rc = shard_prepare(c, pos, B, seed, step, st);
+    rc = shard_prepare(c, pos, B, 1, seed, step, st, true);
     if (rc) return rc;
   }
   hole_shard_prep& p = s->prep[pi];
+  const int64_t k = p.consumed;                              // step of the chunk
+  const int32_t* p_uniq = p.uniq + (size_t)k * s->cap;
+  const int32_t* p_cuts = p.cuts + (size_t)k * (HOLE_MAX_RANKS + 1);
+  const int32_t* p_pos_w = p.pos_w + (size_t)k * B * 3;
+  const int32_t* p_neg_w = p.neg_w + (size_t)k * B;
+  const int32_t* p_neg = p.neg + (size_t)k * B;
+  const int side = hole_side_coin(seed, step);
   hole_plan& pl = c->plan[p.plan_slot];
   HOLE_CUDA_TRY(cudaStreamWaitEvent(st, pl.ready, 0));       // corruption, routing and plan are complete
   const int par = s->epoch & 1;
@@ -365,27 +406,33 @@ extern "C" int hole_shard_step_compute(hole_ctx* c, const int32_t* pos, int64_t 
     ib.p[k] = k < world ? static_cast<int32_t*>(s->p_inbox.p[k]) + (size_t)par * world * s->cap : nullptr;
     mt.p[k] = k < world ? static_cast<int32_t*>(s->p_meta.p[k]) + (size_t)par * world * 2 : nullptr;
   }
+  if ((rc = shard_mark(c, 0, st))) return rc;
   hole_shard_post_kernel<<<(unsigned)std::min<int64_t>((3 * B + 255) / 256, c->sm_count * 2), 256, 0, st>>>(
-      p.uniq, p.cuts, world, me, s->cap, ib, mt);
+      p_uniq, p_cuts, world, me, s->cap, ib, mt);
   HOLE_LAUNCHED();
+  if ((rc = shard_mark(c, 1, st))) return rc;
   hole_k1_shard sh = {};
-  sh.tri_w = p.pos_w; sh.neg_w = p.neg_w; sh.cuts = p.cuts;
+  sh.tri_w = p_pos_w; sh.neg_w = p_neg_w; sh.cuts = p_cuts;
   sh.flags = static_cast<const int*>(s->p_flags.p[me]);
   sh.err = s->err; sh.wait_epoch = s->epoch; sh.R = (int)s->R; sh.rows_per = (int)s->rows_per;
   sh.me = me; sh.world = world; sh.cap = s->cap; sh.timeout_ns = s->timeout_ns;
   sh.shard = s->p_shard; sh.stage = s->p_stage;
-  rc = run_step(c, pl, s->shard, p.pos_w, p.neg_w, p.side, B, margin, lr, loss_out, nullptr, 0, st, s->Drel, false, 0,
-                &sh, pos, p.neg);
+  rc = run_step(c, pl, s->shard, p_pos_w, p_neg_w, side, B, margin, lr, loss_out, nullptr, k, st, s->Drel, false, 0,
+                &sh, pos, p_neg, c->profile ? s->prof_ev[s->prof_used - 6 + 2] : nullptr);
   if (rc) return rc;
-  pl.used = true;
-  HOLE_CUDA_TRY(cudaEventRecord(pl.released, st));
-  p.used = true;
-  p.valid = false;
-  HOLE_CUDA_TRY(cudaEventRecord(p.freed, st));
+  if ((rc = shard_mark(c, 3, st))) return rc;
+  p.consumed += 1;
+  if (p.consumed == p.n_steps) {                             // the chunk's buffers and plan are free again
+    pl.used = true;
+    HOLE_CUDA_TRY(cudaEventRecord(pl.released, st));
+    p.used = true;
+    p.valid = false;
+    HOLE_CUDA_TRY(cudaEventRecord(p.freed, st));
+  }
   const unsigned fgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((s->R + (256 / c->gs) - 1) / (256 / c->gs), c->sm_count));
   HOLE_DISPATCH(c, hole_shard_finish_kernel, fgrid, 256, st, s->Drel, (int)s->R, me, world, s->p_relstage, s->p_flags,
                 s->epoch + 1, s->done, c->nvec, c->row_stride);
-  return HOLE_OK;
+  return shard_mark(c, 4, st);
 }
 
 // apply of the step: every peer's deltas -> my shard
@@ -403,6 +450,27 @@ extern "C" int hole_shard_step_apply(hole_ctx* c, void* stream) {
                 static_cast<const int*>(s->p_flags.p[me]), s->epoch + 1, s->err, s->timeout_ns, s->p_flags,
                 s->epoch + 1, s->done + 1, c->nvec, c->row_stride);
   s->epoch += 1;
+  return shard_mark(c, 5, (cudaStream_t)stream);
+}
+
+// Measurement hook: with hole_profile_enable on, every sharded step records events at its phase
+// boundaries; returns the summed milliseconds of [post, K1 (incl. its wait for the peers' shards), K3,
+// finish, apply (incl. its wait for the peers' deltas)] and the number of steps since the last enable.
+extern "C" int hole_shard_profile_read(hole_ctx* c, double* phase_ms5, int64_t* n_steps) {
+  HOLE_CHECK_ARG(c && phase_ms5 && n_steps);
+  if (c->shard_state == nullptr) return hole_set_error(HOLE_ERR_ARG, "hole_shard_init has not been called");
+  HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  HOLE_CUDA_TRY(cudaDeviceSynchronize());
+  hole_shard_state* s = c->shard_state;
+  for (int q = 0; q < 5; ++q) phase_ms5[q] = 0.0;
+  for (size_t b = 0; b + 6 <= s->prof_used; b += 6)
+    for (int q = 0; q < 5; ++q) {
+      float t = 0.f;
+      HOLE_CUDA_TRY(cudaEventElapsedTime(&t, s->prof_ev[b + q], s->prof_ev[b + q + 1]));
+      phase_ms5[q] += t;
+    }
+  *n_steps = (int64_t)(s->prof_used / 6);
+  s->prof_used = 0;
   return HOLE_OK;
 }
 
@@ -413,33 +481,35 @@ extern "C" int hole_shard_step(hole_ctx* c, const int32_t* pos, int64_t B, uint6
   return hole_shard_step_apply(c, stream);
 }
 
-// n_steps consecutive steps on device-resident triples [n_steps*B, 3] (this rank's slices), the
-// table-independent part of step k+1 built while step k runs.  loss_sum_out: device float32[n_steps].
+// n_steps consecutive steps on device-resident triples [n_steps*B, 3] (this rank's slices).  The
+// table-independent part is built a chunk of SHARD_PREP_STEPS steps at a time, one chunk ahead of the
+// chunk that is training.  loss_sum_out: device float32[n_steps].  copy_ready[i] (optional): event that
+// marks the arrival of triple chunk i (copy_steps steps each; a multiple of SHARD_PREP_STEPS).
 static int shard_steps(hole_ctx* c, const int32_t* triples, int64_t B, int64_t n_steps, uint64_t seed,
                        uint64_t first_step, float margin, const float* lr, float* loss_sum_out,
-                       cudaStream_t st, const cudaEvent_t* chunk_ready, int64_t chunk_steps) {
+                       cudaStream_t st, const cudaEvent_t* copy_ready, int64_t copy_steps) {
   hole_shard_state* s = c->shard_state;
+  const int64_t PS = SHARD_PREP_STEPS;
   int rc;
-  for (int64_t k0 = 0; k0 < n_steps; k0 += SHARD_LOSS_CHUNK) {
-    const int64_t n = std::min<int64_t>(SHARD_LOSS_CHUNK, n_steps - k0);
-    for (int64_t k = k0; k < k0 + n; ++k) {
-      if (chunk_ready && k % chunk_steps == 0) HOLE_CUDA_TRY(cudaStreamWaitEvent(st, chunk_ready[k / chunk_steps], 0));
-      if (k == 0) {
-        rc = shard_prepare(c, triples, B, seed, first_step, st);
-        if (rc) return rc;
-      }
-      if (k + 1 < n_steps) {
-        if (chunk_ready && (k + 1) % chunk_steps == 0)
-          HOLE_CUDA_TRY(cudaStreamWaitEvent(st, chunk_ready[(k + 1) / chunk_steps], 0));
-        rc = shard_prepare(c, triples + (size_t)(k + 1) * B * 3, B, seed, first_step + (uint64_t)(k + 1), st);
-        if (rc) return rc;
-      }
-      rc = hole_shard_step(c, triples + (size_t)k * B * 3, B, seed, first_step + (uint64_t)k, margin, lr[k],
-                           s->loss + (size_t)(k - k0) * B, st);
+  auto prepare_chunk = [&](int64_t k0, bool first) -> int {
+    const int64_t n = std::min<int64_t>(PS, n_steps - k0);
+    if (copy_ready && k0 % copy_steps == 0)
+      HOLE_CUDA_TRY(cudaStreamWaitEvent(c->plan_stream, copy_ready[k0 / copy_steps], 0));
+    return shard_prepare(c, triples + (size_t)k0 * B * 3, B, n, seed, first_step + (uint64_t)k0, st, first);
+  };
+  rc = prepare_chunk(0, true);
+  if (rc) return rc;
+  for (int64_t k = 0; k < n_steps; ++k) {
+    if (k % PS == 0 && k + PS < n_steps) {                   // next chunk, while this one trains
+      rc = prepare_chunk(k + PS, false);
       if (rc) return rc;
     }
-    if (loss_sum_out != nullptr) {
-      hole_loss_sum_kernel<<<(unsigned)n, 256, 0, st>>>(s->loss, B, loss_sum_out + k0);
+    const int64_t l0 = k / SHARD_LOSS_CHUNK * SHARD_LOSS_CHUNK;
+    rc = hole_shard_step(c, triples + (size_t)k * B * 3, B, seed, first_step + (uint64_t)k, margin, lr[k],
+                         s->loss + (size_t)(k - l0) * B, st);
+    if (rc) return rc;
+    if (loss_sum_out != nullptr && (k + 1 == n_steps || (k + 1) % SHARD_LOSS_CHUNK == 0)) {
+      hole_loss_sum_kernel<<<(unsigned)(k + 1 - l0), 256, 0, st>>>(s->loss, B, loss_sum_out + l0);
       HOLE_LAUNCHED();
     }
   }
@@ -486,6 +556,7 @@ extern "C" int hole_shard_steps_host(hole_ctx* c, const int32_t* triples_host, i
     HOLE_CUDA_TRY(cudaDeviceSynchronize());
     if (s->loss_pinned) cudaFreeHost(s->loss_pinned);
     cudaFree(s->sums_dev);
+  for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     s->loss_pinned = nullptr;
     s->sums_dev = nullptr;
     s->pinned_cap = 0;
@@ -494,8 +565,8 @@ extern "C" int hole_shard_steps_host(hole_ctx* c, const int32_t* triples_host, i
     s->pinned_cap = n_steps;
   }
   float* sums = s->sums_dev;
-  // H2D in chunks of 16 steps on the copy stream; a step waits for its chunk only
-  const int64_t CS = 16, nchunks = (n_steps + CS - 1) / CS;
+  // H2D in chunks of SHARD_PREP_STEPS steps on the copy stream; a chunk's preparation waits for its copy only
+  const int64_t CS = SHARD_PREP_STEPS, nchunks = (n_steps + CS - 1) / CS;
   std::vector<cudaEvent_t> ready((size_t)nchunks);
   HOLE_CUDA_TRY(cudaEventRecord(c->ev_entry, st));
   HOLE_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0));   // the staging buffer's last readers are done

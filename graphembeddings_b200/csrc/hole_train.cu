@@ -945,6 +945,7 @@ hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __r
       span *= C;
     }
   }
+  if (sh.world > 0) __threadfence_system();   // delta rows stored to peer memory: see hole_k1_body
 }
 
 // ---------------------------------------------------------------------------------------
@@ -985,14 +986,17 @@ hole_gather_rows_kernel(const float* __restrict__ E, const int64_t* __restrict__
 // Multi-GPU step routing.  The table is row-sharded; a rank's step touches the
 // entity rows {h, t, corrupt entity} of its B triples.  Everything below runs on the device
 // with device-side counts, so that a sharded step never returns to the host:
-//   route : dedup the 3B ids (radix sort + one-block scan), sorted unique list `uniq`,
-//           per-owner cut points, triples re-indexed to step-table rows R + slot
+//   route : dedup the 3B ids (radix sort + tiled scan), sorted unique request list `uniq`,
+//           per-owner cut points, triples re-indexed to request-list rows R + slot
 //   post  : write each owner's slice of `uniq` into THAT owner's inbox (peer memory)
-//   push  : the owner copies the requested rows into the requester's step table (peer memory)
-//   pull  : the owner reads the requester's delta rows (peer memory) and adds them to its shard
+// The route kernels handle a chunk of steps per launch (grid.y = step of the chunk), like the
+// plan kernels: the chain's latency (~30 dependent launches) is paid once per chunk.
 // ---------------------------------------------------------------------------------------
 __global__ void hole_shard_keys_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ neg,
                                        int B, uint32_t* __restrict__ keys) {
+  pos += (size_t)blockIdx.y * 3 * B;
+  neg += (size_t)blockIdx.y * B;
+  keys += (size_t)blockIdx.y * 3 * B;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
     keys[i] = (uint32_t)pos[3 * i];
     keys[B + i] = (uint32_t)pos[3 * i + 1];
@@ -1013,6 +1017,10 @@ hole_shard_count_kernel(const uint32_t* __restrict__ sk, int M, int* __restrict_
                         const int32_t* __restrict__ pos, int B, int32_t* __restrict__ pos_w) {
   __shared__ int wsum[RT_THREADS / 32];
   const int tid = threadIdx.x;
+  sk += (size_t)blockIdx.y * M;
+  tile_heads += (size_t)blockIdx.y * (gridDim.x + 1);       // [tiles] + the step's total
+  pos += (size_t)blockIdx.y * 3 * B;
+  pos_w += (size_t)blockIdx.y * 3 * B;
   int cnt = 0;
 #pragma unroll
   for (int u = 0; u < RT_ITERS; ++u) {
@@ -1034,12 +1042,19 @@ hole_shard_count_kernel(const uint32_t* __restrict__ sk, int M, int* __restrict_
 
 __global__ void __launch_bounds__(RT_THREADS)
 hole_shard_assign_kernel(const uint32_t* __restrict__ sk, const uint32_t* __restrict__ sp, int M, int B,
-                         int R, const int* __restrict__ tile_heads, int* __restrict__ total,
+                         int R, int* __restrict__ tile_heads, int64_t uniq_stride,
                          int32_t* __restrict__ uniq, int32_t* __restrict__ pos_w,
                          int32_t* __restrict__ neg_w) {
   __shared__ int wsum[RT_THREADS / 32];
   __shared__ int base_s;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  sk += (size_t)blockIdx.y * M;
+  sp += (size_t)blockIdx.y * M;
+  tile_heads += (size_t)blockIdx.y * (gridDim.x + 1);
+  int* total = tile_heads + gridDim.x;
+  uniq += (size_t)blockIdx.y * uniq_stride;
+  pos_w += (size_t)blockIdx.y * 3 * B;
+  neg_w += (size_t)blockIdx.y * B;
   if (w == 0) {                                   // heads in the tiles before mine
     int t = 0;
     for (int q = lane; q < (int)blockIdx.x; q += 32) t += tile_heads[q];
@@ -1080,11 +1095,14 @@ hole_shard_assign_kernel(const uint32_t* __restrict__ sk, const uint32_t* __rest
   if (blockIdx.x == gridDim.x - 1 && tid == 0) *total = base;
 }
 
-__global__ void hole_shard_cuts_kernel(const int32_t* __restrict__ uniq, const int* __restrict__ total,
+__global__ void hole_shard_cuts_kernel(const int32_t* __restrict__ uniq, int64_t uniq_stride,
+                                       const int* __restrict__ tile_heads, int tiles,
                                        int R, int64_t rows_per, int world, int32_t* __restrict__ cuts) {
   const int tid = threadIdx.x;
   if (tid > world) return;
-  const int U = *total;
+  uniq += (size_t)blockIdx.x * uniq_stride;
+  cuts += (size_t)blockIdx.x * (HOLE_MAX_RANKS + 1);
+  const int U = tile_heads[(size_t)blockIdx.x * (tiles + 1) + tiles];
   const int64_t bound = (int64_t)R + rows_per * tid;     // first row of rank `tid`
   int a = 0, b = U;
   while (a < b) {
@@ -1109,6 +1127,7 @@ __global__ void hole_shard_post_kernel(const int32_t* __restrict__ uniq, const i
     m[2 * me] = cuts[gtid + 1] - cuts[gtid];     // how many rows I want from rank gtid
     m[2 * me + 1] = cuts[gtid];                  // where they sit in my step table (after R)
   }
+  __threadfence_system();                        // peer stores: visible before a later kernel raises the flag
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1626,7 +1645,7 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
                     int side, int64_t B, float margin, float lr, float* loss_out, float* sigma_out,
                     int64_t slot, cudaStream_t st, float* delta_out = nullptr, bool k1_follows_k3 = false,
                     int flags = 0, const hole_k1_shard* shard = nullptr, const int32_t* shard_tri = nullptr,
-                    const int32_t* shard_neg = nullptr) {
+                    const int32_t* shard_neg = nullptr, cudaEvent_t k1_done_mark = nullptr) {
   const int M = (int)(4 * B);
   const size_t off = (size_t)slot * M;
   cudaEvent_t* pe = nullptr;
@@ -1673,6 +1692,7 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
                 c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out, flags);
   }
   if (pe) HOLE_CUDA_TRY(cudaEventRecord(pe[1], st));
+  if (k1_done_mark) HOLE_CUDA_TRY(cudaEventRecord(k1_done_mark, st));
   const unsigned k3_grid = std::min<unsigned>(grid_for_groups(pl.heads_cap, c->gs), (unsigned)c->sm_count * 4);
   HOLE_DISPATCH_PDL(c, hole_apply_kernel, k3_grid, 256, 0, st, table, c->G,
                 pl.heads + (size_t)slot * pl.heads_cap, pl.nheads + slot, c->counters, M, c->nvec,
@@ -1867,52 +1887,61 @@ extern "C" int hole_add_rows(hole_ctx* c, float* table, const int64_t* ids, int6
 // ---------------------------------------------------------------------------------------
 // multi-GPU step routing: host side (see the kernels above)
 // ---------------------------------------------------------------------------------------
-static int route_reserve(hole_ctx* c, int64_t M) {
-  if (M <= c->route_cap) return HOLE_OK;
+// scratch of the request routing for chunks of S steps of M = 3B keys
+static int route_reserve(hole_ctx* c, int64_t M, int64_t S = 1) {
+  if (M * S <= c->route_cap) return HOLE_OK;
   HOLE_CUDA_TRY(cudaDeviceSynchronize());
   cudaFree(c->route_buf);
   c->route_buf = nullptr;
   c->route_cap = 0;
   const size_t tiles = (M + ST_TILE - 1) / ST_TILE;
-  if (cudaMalloc((void**)&c->route_buf, (4 * (size_t)M + 256 * tiles) * 4) != cudaSuccess) {
+  const size_t rtiles = (M + RT_TILE - 1) / RT_TILE;
+  const size_t words = (size_t)S * (4 * (size_t)M + std::max<size_t>(256 * tiles, rtiles + 1));
+  if (cudaMalloc((void**)&c->route_buf, words * 4) != cudaSuccess) {
     cudaGetLastError();
     return hole_set_error(HOLE_ERR_ALLOC, "route workspace allocation failed");
   }
-  c->route_cap = M;
+  c->route_cap = M * S;
   return HOLE_OK;
 }
 
+// S steps at once: pos [S][B][3], neg_ent [S][B] -> uniq_out [S][uniq_stride], cuts_out [S][HOLE_MAX_RANKS+1]
+// (S == 1: exactly world+1 entries are written), pos_w [S][B][3], neg_w [S][B]
 static int shard_route(hole_ctx* c, const int32_t* pos, const int32_t* neg_ent, int64_t B,
                        int64_t n_relations, int64_t n_rows_global, int64_t rows_per_rank,
                        int world, int32_t* uniq_out, int32_t* cuts_out, int32_t* pos_w,
-                       int32_t* neg_w, void* stream) {
+                       int32_t* neg_w, void* stream, int64_t S = 1, int64_t uniq_stride = 0) {
   HOLE_CHECK_ARG(c && pos && neg_ent && uniq_out && cuts_out && pos_w && neg_w);
-  HOLE_CHECK_ARG(B > 0 && 3 * B < (int64_t(1) << 31) && world >= 1 && world <= HOLE_MAX_RANKS);
+  HOLE_CHECK_ARG(B > 0 && 3 * B < (int64_t(1) << 31) && world >= 1 && world <= HOLE_MAX_RANKS && S >= 1);
   HOLE_CHECK_ARG(n_relations >= 0 && rows_per_rank > 0 && n_rows_global > n_relations &&
                  n_rows_global <= (int64_t(1) << 31));
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   const int M = (int)(3 * B);
-  int rc = route_reserve(c, M);
+  if (uniq_stride <= 0) uniq_stride = M;
+  int rc = route_reserve(c, M, S);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  uint32_t *kA = c->route_buf, *kB = kA + M, *vA = kB + M, *vB = vA + M, *ghist = vB + M;
+  const size_t SM_ = (size_t)S * M;
+  uint32_t *kA = c->route_buf, *kB = kA + SM_, *vA = kB + SM_, *vB = vA + SM_, *ghist = vB + SM_;
   int passes = 1;
   while (passes < 4 && (n_rows_global - 1) >> (8 * passes)) ++passes;
-  hole_shard_keys_kernel<<<(unsigned)std::min<int64_t>((B + 255) / 256, 1024), 256, 0, st>>>(pos, neg_ent, (int)B, kA);
+  dim3 kgrid((unsigned)std::min<int64_t>((B + 255) / 256, 1024), (unsigned)S);
+  hole_shard_keys_kernel<<<kgrid, 256, 0, st>>>(pos, neg_ent, (int)B, kA);
   HOLE_LAUNCHED();
   uint32_t *sk, *sp;
-  rc = radix_sort(ghist, kA, kB, vA, vB, nullptr, 1, M, passes, st, &sk, &sp);
+  rc = radix_sort(ghist, kA, kB, vA, vB, nullptr, S, M, passes, st, &sk, &sp);
   if (rc) return rc;
-  // the sort's tile histogram is free again: tile head counts + the total live there
+  // the sort's tile histogram is free again: per step, tile head counts + the total live there
   const int tiles = (M + RT_TILE - 1) / RT_TILE;
   int* tile_heads = reinterpret_cast<int*>(ghist);
-  int* total = tile_heads + tiles;
-  hole_shard_count_kernel<<<tiles, RT_THREADS, 0, st>>>(sk, M, tile_heads, pos, (int)B, pos_w);
+  dim3 tgrid((unsigned)tiles, (unsigned)S);
+  hole_shard_count_kernel<<<tgrid, RT_THREADS, 0, st>>>(sk, M, tile_heads, pos, (int)B, pos_w);
   HOLE_LAUNCHED();
-  hole_shard_assign_kernel<<<tiles, RT_THREADS, 0, st>>>(sk, sp, M, (int)B, (int)n_relations, tile_heads, total,
-                                                        uniq_out, pos_w, neg_w);
+  hole_shard_assign_kernel<<<tgrid, RT_THREADS, 0, st>>>(sk, sp, M, (int)B, (int)n_relations, tile_heads,
+                                                        uniq_stride, uniq_out, pos_w, neg_w);
   HOLE_LAUNCHED();
-  hole_shard_cuts_kernel<<<1, 32, 0, st>>>(uniq_out, total, (int)n_relations, rows_per_rank, world, cuts_out);
+  hole_shard_cuts_kernel<<<(unsigned)S, 32, 0, st>>>(uniq_out, uniq_stride, tile_heads, tiles, (int)n_relations,
+                                                    rows_per_rank, world, cuts_out);
   HOLE_LAUNCHED();
   return HOLE_OK;
 }

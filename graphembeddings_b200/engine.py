@@ -247,6 +247,14 @@ class HoleEngine:
                                              out.ctypes.data_as(C.c_void_p), _stream()))
         return out
 
+    def shard_profile_read(self):
+        """-> ({phase: ms per step}, n_steps) of the sharded steps since profile(True)."""
+        ms = (C.c_double * 5)()
+        n = C.c_int64(0)
+        check(self.lib.hole_shard_profile_read(self._ctx, ms, C.byref(n)))
+        k = max(int(n.value), 1)
+        return {nm: ms[i] / k for i, nm in enumerate(("post", "k1", "k3", "finish", "apply"))}, int(n.value)
+
     def shard_poll(self):
         """True if a peer failed to arrive at a step barrier (synchronises the stream)."""
         v = C.c_int(0)

@@ -396,17 +396,30 @@ class P2PRowShardedTrainer(RowShardedTrainer):
                                self.shard, *[pa([p[i] for p in peers]) for i in range(6)], self.barrier_err,
                                timeout_s)
 
+    def close(self):
+        """Collective: drop the mappings of the peers' buffers on every rank BEFORE anybody frees the
+        memory behind them (CUDA IPC: the exporter must outlive every importer's mapping)."""
+        if getattr(self, "_peers", None) is None:
+            return
+        torch.cuda.synchronize()
+        self._peers = None
+        if self.world > 1:
+            self.dist.barrier()
+        self.shard = self.stage = self.relstage = self.inbox = self.meta = self.flags = None
+
     def load_embeddings(self, E):
         E = torch.as_tensor(E)
         mine = torch.cat([E[: self.R], E[self.begin:self.end]], dim=0)
         self.shard.zero_()
         self.shard[: mine.shape[0]].copy_(self.be.pad_rows(mine))
-        return self
+        return self.shards_ready()
 
-    def load_shard(self, rows):
-        """rows: device [R + n_mine, row_stride] already in the padded layout (bench: generated on the GPU)."""
-        self.shard.zero_()
-        self.shard[: rows.shape[0]].copy_(rows)
+    def shards_ready(self):
+        """Collective: call after writing self.shard directly.  The peers' training kernels READ this
+        shard over NVLink, so nobody may start a step before every rank's shard is in place."""
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
         return self
 
     def check_barriers(self):
@@ -466,11 +479,158 @@ class P2PRowShardedTrainer(RowShardedTrainer):
 
 
 # --------------------------------------------------------------------------------------
+# parity of the multi-GPU product path (tools/multi_gpu_check.py, tests/test_gpu_multi.py, bench.py)
+# --------------------------------------------------------------------------------------
+def parity_case(dist, rank, world, local, dim, Bl, steps, n_ent, seed, chunked, log=None):
+    """Row-sharded training over the real peers + sharded ranking against a single-GPU engine run on
+    rank 0 over the same global batches.  Returns (ok on every rank, result dict on rank 0)."""
+    from . import data as D
+    from .engine import HoleEngine
+    kg = D.synthetic_kg(9, n_ent, Bl * world * steps, 5, dim, seed=seed, trained_scale=True, zipf_entities=True)
+    off, ids = D.build_type_csr(kg.type_of)
+    be = CudaBackend(kg.n_relations, kg.dim, Bl, local, kg.type_of, off, ids)
+    tr = make_trainer(kg.n_relations, kg.n_entities, kg.dim, be, dist, log=log).load_embeddings(kg.E)
+    mine = torch.from_numpy(kg.triples).view(steps, world, Bl, 3)[:, rank].contiguous().cuda()
+    lrs = [0.1 / (1 + 0.01 * s) for s in range(steps)]
+    if chunked and isinstance(tr, P2PRowShardedTrainer):
+        tr.train_steps(mine.view(-1, 3), Bl, 3, 0, 0.2, lrs)
+    else:
+        for s in range(steps):
+            tr.train_step(mine[s], 3, s, 0.2, lrs[s], next_pos=mine[s + 1] if s + 1 < steps else None)
+    full = tr.gather_embeddings()
+    q = torch.from_numpy(kg.triples[:1000])
+    raw, filt = tr.rank(q, 0)
+    res = {"trainer": type(tr).__name__, "world": world, "dim": dim, "batch_per_gpu": Bl, "steps": steps,
+           "chunked_call": bool(chunked)}
+    ok = True
+    if rank == 0:
+        e = HoleEngine(kg.n_rows, kg.dim, local).set_embeddings(kg.E).set_types(kg.type_of, off, ids)
+        for s in range(steps):
+            gb = kg.triples[s * Bl * world:(s + 1) * Bl * world]
+            side, neg = e.corrupt_batch(gb, 3, s)
+            e.train_step(gb, neg, side, 0.2, lrs[s])
+        want = e.embeddings()
+        diff = (full - want).abs().amax(dim=1)
+        err = float(diff.max())
+        bad = torch.nonzero(diff > 2e-6).flatten()
+        if len(bad):                      # diagnostics: which rows, whose
+            rows_per = row_partition(kg.n_entities, world)
+            res["bad_rows"] = int(len(bad))
+            res["bad_relation_rows"] = int((bad < kg.n_relations).sum())
+            res["bad_rows_by_owner"] = [int(((bad >= kg.n_relations + o * rows_per) &
+                                             (bad < kg.n_relations + (o + 1) * rows_per)).sum()) for o in range(world)]
+            res["bad_first"] = [int(x) for x in bad[:8]]
+        moved = float((want.cpu() - torch.from_numpy(kg.E)).abs().max())
+        # ranking on the single-GPU table that equals the gathered sharded table up to ~1e-7
+        e2 = HoleEngine(kg.n_rows, kg.dim, local).set_embeddings(full)
+        r1, f1, _ = e2.rank(q, 0, kg.n_relations, kg.n_rows)
+        same = float((r1 == raw).float().mean())
+        res.update({"max_abs_err": err, "moved": moved, "rank_counts_equal": same,
+                    "rank_counts_max_diff": int((r1 - raw).abs().max())})
+        ok = err <= 2e-6 and moved > 1e-4 and same == 1.0
+        res["ok"] = ok
+        e.close()
+        e2.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    if hasattr(tr, "close"):
+        tr.close()
+    be.eng.close()
+    return bool(flag.item()), res
+
+
+# --------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1)
 # --------------------------------------------------------------------------------------
+def _nvlink_bytes_per_dir(B, world, dim_stride):
+    """Per GPU and direction, one step: rows gathered from remote owners + deltas received as an owner
+    (in), rows served + deltas sent (out): 2 * 3B * (G-1)/G rows of 4*stride bytes (k = 4)."""
+    return 2.0 * 3.0 * B * (world - 1) / world * 4.0 * dim_stride
+
+
+def _timed_device(dist, fn):
+    """Device time of fn() in ms, max over ranks; also the host time fn() took to enqueue."""
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    h0 = time.perf_counter()
+    fn()
+    host_ms = (time.perf_counter() - h0) * 1e3
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), host_ms
+
+
+def _timed_wall(dist, fn):
+    """Wall-clock ms of a blocking fn(), max over ranks."""
+    torch.cuda.synchronize()
+    dist.barrier()
+    h0 = time.perf_counter()
+    out = fn()
+    t = torch.tensor([(time.perf_counter() - h0) * 1e3], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), out
+
+
+def bench_config4(args, dist, rank, world, local_rank, steps, warmup):
+    """BASELINE.json configs[4]: HolE d=512, 20 M entities (41 GB fp32 table), row-sharded; every
+    rank trains `--batch` triples per step.  The shards, type tables and triples are generated on
+    the device (the table is never materialised on the host)."""
+    from . import data as D
+    cfg = D.CONFIGS["sharded_d512"]
+    R, n_ent, dim, n_types = cfg["n_relations"], cfg["n_entities"], cfg["dim"], cfg["n_types"]
+    Bl = args.batch
+    rng = np.random.default_rng(cfg["seed"])
+    p = np.full(n_types, (1.0 - cfg["dominant_type_frac"]) / (n_types - 1))
+    p[0] = cfg["dominant_type_frac"]
+    type_of = np.concatenate([np.zeros(R, np.int32), 1 + rng.choice(n_types, size=n_ent, p=p).astype(np.int32)])
+    off, ids = D.build_type_csr(type_of)
+    be = CudaBackend(R, dim, Bl, local_rank, type_of, off, ids)
+    tr = P2PRowShardedTrainer(R, n_ent, dim, be, dist)
+    gen = torch.Generator(device=be.device)
+    gen.manual_seed(cfg["seed"] + 1)                       # relation replicas identical on every rank
+    sd = D.xavier_stddev(R + n_ent, dim)
+    tr.shard[:R].normal_(0.0, 1.0, generator=gen).clamp_(-2.0, 2.0).mul_(sd)
+    gen.manual_seed(cfg["seed"] + 2 + rank)
+    n_mine = tr.end - tr.begin
+    tr.shard[R:R + n_mine].normal_(0.0, 1.0, generator=gen).clamp_(-2.0, 2.0).mul_(sd)
+    tr.shards_ready()
+    n = (steps + warmup) * Bl
+    h = torch.randint(R, R + n_ent, (n,), generator=gen, device=be.device, dtype=torch.int32)
+    t = torch.randint(R, R + n_ent, (n,), generator=gen, device=be.device, dtype=torch.int32)
+    w = 1.0 / torch.arange(1, R + 1, device=be.device, dtype=torch.float64)
+    r = torch.multinomial(w / w.sum(), n, replacement=True, generator=gen).to(torch.int32)
+    tri = torch.stack([h, t, r], dim=1).contiguous()
+    lrs = np.full(steps + warmup, 0.1, np.float32)
+    tr.train_steps(tri[: warmup * Bl], Bl, 1, 0, 0.2, lrs[:warmup])
+    ms, host_ms = _timed_device(dist, lambda: tr.train_steps(tri[warmup * Bl:], Bl, 1, warmup, 0.2, lrs[warmup:]))
+    tr.check_barriers()
+    value = steps * Bl * world / (ms * 1e-3)
+    nv = _nvlink_bytes_per_dir(Bl, world, be.width) / (ms / steps * 1e-3) / 1e9
+    out = {"workload": f"sharded_d512: BASELINE.json configs[4], HolE d=512, {n_ent:,} entities + {R} relations "
+                       f"({(R + n_ent) * dim * 4 / 1e9:.1f} GB fp32 table) row-sharded over {world} GPUs, "
+                       "uniform entities, Zipf relations, Xavier-scale rows generated on the device",
+           "value": value, "unit": "triples/s", "ms_per_step": ms / steps, "batch_per_gpu": Bl, "steps": steps,
+           "shard_gb_per_gpu": float(tr.shard.numel() * 4 / 1e9), "host_enqueue_us_per_step": host_ms / steps * 1e3,
+           "roofline": {"bound": "nvlink", "achieved": nv, "peak": 900.0, "unit": "GB/s per direction per GPU",
+                        "frac": nv / 900.0, "peak_source": "nominal NVLink 5 (18 links x 50 GB/s per direction)",
+                        "bytes_per_dir_per_step": _nvlink_bytes_per_dir(Bl, world, be.width)}}
+    tr.close()
+    del tr
+    be.eng.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def bench(args, dist, rank, world, local_rank):
-    """Weak scaling: every rank trains `--batch` triples per step on the row-sharded
-    BASELINE config 1 table.  Device time, max over ranks; rank 0 prints the JSON line."""
+    """Weak scaling: every rank trains `--batch` triples per step on the row-sharded BASELINE config 1
+    table (value / e2e), then config 4 and the sharded ranking as sub-records.  Device time, max over
+    ranks; rank 0 prints the JSON line."""
     import bench as B_
     from . import data as D
     from .engine import HOLE_SIDE_TAIL
@@ -481,32 +641,12 @@ def bench(args, dist, rank, world, local_rank):
     be = CudaBackend(kg.n_relations, kg.dim, Bl, local_rank, kg.type_of, off, ids)
     tr = make_trainer(kg.n_relations, kg.n_entities, kg.dim, be, dist,
                       log=lambda m: print(m, file=sys.stderr) if rank == 0 else None).load_embeddings(kg.E)
-    cls = type(tr)
+    p2p = isinstance(tr, P2PRowShardedTrainer)
     # step s, rank r takes triples [(s*world + r)*Bl, +Bl)
     mine = torch.from_numpy(kg.triples).view(K + W, world, Bl, 3)[:, rank].contiguous()
     dev_tri = mine.cuda()
     host_tri = mine.pin_memory()
-    lrs = B_.lr_schedule(3 * (K + W), 0, 30_000_000 // (Bl * world))
-
-    def sync_all():
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        h0 = time.perf_counter()
-        fn()
-        host_ms[0] = (time.perf_counter() - h0) * 1e3      # host time to enqueue the region
-        e1.record()
-        sync_all()
-        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    host_ms = [0.0]
+    lrs = B_.lr_schedule(5 * (K + W), 0, 30_000_000 // (Bl * world))
 
     # nvidia-smi's start-up (NVML initialisation) disturbs running GPU work for a few hundred
     # ms: start the clock sampler before the warm-up, not inside the timed region
@@ -514,77 +654,105 @@ def bench(args, dist, rank, world, local_rank):
     if rank == 0 and os.environ.get("HOLE_NO_SAMPLER") != "1":
         sampler.start()
         time.sleep(1.0)
-    for s in range(W):
-        tr.train_step(dev_tri[s], 1, s, B_.MARGIN, float(lrs[s]), next_pos=dev_tri[s + 1])
+
+    def run_steps(k0, n, first_step):
+        if p2p:
+            return tr.train_steps(dev_tri[k0:k0 + n].view(-1, 3), Bl, 1, first_step, B_.MARGIN, lrs[first_step:])
+        for s in range(n):
+            tr.train_step(dev_tri[k0 + s], 1, first_step + s, B_.MARGIN, float(lrs[first_step + s]),
+                          next_pos=dev_tri[k0 + s + 1] if s + 1 < n else None)
+
+    run_steps(0, W, 0)
     be.eng.reset_launch_count()
-    stamps = []
-
-    def value_pass():
-        for s in range(K):
-            stamps.append(time.perf_counter())
-            tr.train_step(dev_tri[W + s], 1, W + s, B_.MARGIN, float(lrs[W + s]),
-                          next_pos=dev_tri[W + s + 1] if s + 1 < K else None)
-        stamps.append(time.perf_counter())
-
-    ms = timed(value_pass)
-    if os.environ.get("HOLE_BENCH_TRACE") == "1":
-        gaps = np.diff(np.asarray(stamps)) * 1e6
-        big = np.flatnonzero(gaps > 1000)
-        print(f"[trace rank {rank}] host us/step: median {np.median(gaps):.0f}, mean {gaps.mean():.0f}, "
-              f"max {gaps.max():.0f}; steps > 1 ms: {[(int(i), int(gaps[i])) for i in big[:12]]}", flush=True)
+    ms, host_ms = _timed_device(dist, lambda: run_steps(W, K, W))
     launches = be.eng.launch_count()
-    host_enqueue_us = host_ms[0] / K * 1e3
-    if hasattr(tr, "check_barriers"):
+    if p2p:
         tr.check_barriers()
     value = K * Bl * world / (ms * 1e-3)
 
-    losses = []
-    stage = [torch.empty_like(dev_tri[0]) for _ in range(2)]
-
-    def e2e_pass():
-        # two device staging slots, filled from pinned host memory one step ahead
-        stage[0].copy_(host_tri[W], non_blocking=True)
-        for s in range(K):
-            nxt = None
-            if s + 1 < K:
-                nxt = stage[(s + 1) & 1]
-                nxt.copy_(host_tri[W + s + 1], non_blocking=True)
-            loss = tr.train_step(stage[s & 1], 1, K + W + s, B_.MARGIN, float(lrs[K + W + s]), next_pos=nxt)
-            losses.append(float(loss.sum().item()))        # device -> host read of the step's result
-
-    ms_e2e = timed(e2e_pass)
+    # end to end: pinned host triples in, per-step loss sums out, inside the timed region
+    if p2p:
+        # warm-up with a call of the same shape (staging / pinned buffers are sized on first use)
+        tr.train_steps_host(host_tri[W:].view(-1, 3), Bl, 1, K + W, B_.MARGIN, lrs[K + W:])
+        ms_e2e, hs = _timed_wall(dist, lambda: tr.train_steps_host(host_tri[W:].view(-1, 3), Bl, 1, K + 2 * W,
+                                                                   B_.MARGIN, lrs[K + 2 * W:]))
+        mean_loss = float(hs[-1]) / Bl
+    else:
+        def e2e_pass():
+            tot = 0.0
+            for s in range(K):
+                loss = tr.train_step(host_tri[W + s], 1, K + W + s, B_.MARGIN, float(lrs[K + W + s]))
+                tot = float(loss.sum().item())
+            return tot
+        ms_e2e, last = _timed_wall(dist, e2e_pass)
+        mean_loss = last / Bl
     e2e = K * Bl * world / (ms_e2e * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
+    phases = None
+    if p2p:       # where a step's time goes: stream events at the phase boundaries (separate pass)
+        be.eng.profile(True)
+        run_steps(W, K, 3 * (K + W))
+        ph, _ = be.eng.shard_profile_read()
+        be.eng.profile(False)
+        t = torch.tensor([ph[k] for k in ("post", "k1", "k3", "finish", "apply")], device="cuda", dtype=torch.float64)
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        phases = {k: [round(float(tmin[i]) * 1e3, 1), round(float(tmax[i]) * 1e3, 1)]
+                  for i, k in enumerate(("post", "k1", "k3", "finish", "apply"))}
 
-    # sharded ranking: 20k replicated queries x 1.2M candidates split over the ranks
+    # sharded ranking: configs[3], 100k replicated queries x 1.2M candidates split over the ranks
+    nq = int(os.environ.get("HOLE_BENCH_RANK_QUERIES", 100000))
     rng = np.random.default_rng(20170906)
-    q = torch.from_numpy(kg.triples[rng.integers(0, len(kg.triples), size=20000)])
+    q = torch.from_numpy(kg.triples[rng.integers(0, len(kg.triples), size=nq)])
     tr.rank(q, HOLE_SIDE_TAIL)
-    ms_rank = timed(lambda: tr.rank(q, HOLE_SIDE_TAIL))
+    ms_rank, _ = _timed_device(dist, lambda: tr.rank(q, HOLE_SIDE_TAIL))
+    stride = be.width
+    if p2p:
+        tr.close()
+    del tr
+    be.eng.close()
+    torch.cuda.empty_cache()
+
+    # parity of this very path on the real peers (small problem, after the timed regions)
+    ok, par = parity_case(dist, rank, world, local_rank, 256, 2048, 4, 50000, 77, True)
+    cfg4 = None
+    if not getattr(args, "no_config4", False):
+        try:
+            cfg4 = bench_config4(args, dist, rank, world, local_rank, max(3, min(K, 20)), 3)
+        except Exception as exc:          # reported beside the headline, never instead of it
+            cfg4 = {"error": repr(exc)}
     if rank == 0:
-        peak, src, _ = B_.peaks()
         alg = (32 * kg.dim + 20)
+        hbm_peak, src, _ = B_.peaks()
+        nv = _nvlink_bytes_per_dir(Bl, world, stride) / (ms / K * 1e-3) / 1e9
         print(json.dumps({
             "metric": "HolE train triples/s", "value": value, "unit": "triples/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{B_.WORKLOAD}: BASELINE.json configs[1] table row-sharded over {world} GPUs "
-                                   "(relations replicated); requests posted, rows pushed and deltas pulled by our kernels "
-                                   "over NVLink peer memory; no NCCL call inside a step" if cls is P2PRowShardedTrainer else
-                                   f"{B_.WORKLOAD}: table row-sharded over {world} GPUs, NCCL all-to-all of rows and row deltas",
-                       "batch_per_gpu": Bl, "global_batch": Bl * world, "margin": B_.MARGIN, "lr0": B_.LR0,
-                       "parallelism": f"rowshard{world}", "l2": "table shard larger than L2; no flush",
-                       "host_enqueue_us_per_step": host_enqueue_us,
-                       "mean_loss_last_step": losses[-1] / Bl if losses else None},
-            "e2e": {"value": e2e, "unit": "triples/s", "h2d_bytes_per_step": 12 * Bl, "d2h_bytes_per_step": 4,
-                    "call": "P2PRowShardedTrainer.train_step (pinned host triples in, loss sum out), per rank"},
+            "config": {"workload": B_.workload_desc(Bl), "batch": Bl, "global_batch": Bl * world,
+                       "sharding": (f"table row-sharded over {world} GPUs (relations replicated); the training kernel "
+                                    "gathers rows from the owners' shards and stages row deltas at the owners over "
+                                    "NVLink peer memory; no NCCL call and no host synchronisation inside a step"
+                                    if p2p else f"table row-sharded over {world} GPUs, NCCL all-to-all of rows and deltas"),
+                       "margin": B_.MARGIN, "lr0": B_.LR0, "parallelism": f"rowshard{world}",
+                       "l2": "table shard larger than L2; no flush",
+                       "host_enqueue_us_per_step": host_ms / K * 1e3, "mean_loss_last_step": mean_loss,
+                       "phase_us_min_max_over_ranks": phases},
+            "e2e": {"value": e2e, "unit": "triples/s", "h2d_bytes_per_step": 12 * Bl * world, "d2h_bytes_per_step": 4 * world,
+                    "call": "hole_shard_steps_host per rank (pinned host triples in, per-step loss sums out)"},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": value * alg / 1e9 / world, "peak": peak, "unit": "GB/s",
-                         "frac": value * alg / 1e9 / world / peak, "traffic": None, "peak_source": src,
-                         "kernel": "whole sharded step per GPU (NVLink exchange included)"},
+            "roofline": {"bound": "nvlink", "achieved": nv, "peak": 900.0, "unit": "GB/s per direction per GPU",
+                         "frac": nv / 900.0, "traffic": None,
+                         "peak_source": "nominal NVLink 5 (18 links x 50 GB/s per direction)",
+                         "kernel": "hole_k1_kernel<.,.,2> (row gather + delta scatter over peer memory) + apply",
+                         "bytes_per_dir_per_step": _nvlink_bytes_per_dir(Bl, world, stride),
+                         "hbm_frac_per_gpu": value * alg / 1e9 / world / hbm_peak, "hbm_peak_source": src},
             "cpu_baseline": None,
-            "ranking": {"workload": f"20000 queries x 1,200,000 candidates sharded over {world} GPUs (tail side)",
-                        "ms": ms_rank, "scores_per_s": 20000 * 1.2e6 / (ms_rank * 1e-3)},
+            "parity": par,
+            "config4": cfg4,
+            "ranking": {"workload": f"rank_diffbot_d256: {nq} queries x 1,200,000 candidates sharded over {world} GPUs (tail side)",
+                        "ms": ms_rank, "scores_per_s": nq * 1.2e6 / (ms_rank * 1e-3)},
         }))
     dist.barrier()
     dist.destroy_process_group()

@@ -202,6 +202,10 @@ HOLE_API int hole_shard_steps_host(hole_ctx* ctx, const int32_t* triples_host, i
                                    uint64_t seed, uint64_t first_step, float margin, const float* lr,
                                    float* loss_sum_host, void* stream);
 HOLE_API int hole_shard_poll(hole_ctx* ctx, int* timed_out, void* stream);
+/* Measurement hook: with hole_profile_enable on, summed milliseconds of the step's phases
+ * [post, K1 (incl. its wait for the peers' shards), K3, finish, apply (incl. its wait for the peers'
+ * deltas)] -> phase_ms5 [host, double[5]], and the number of steps measured since the last read. */
+HOLE_API int hole_shard_profile_read(hole_ctx* ctx, double* phase_ms5, int64_t* n_steps);
 
 /* Building blocks of the step, exported for tests.
  * hole_shard_route: dedup the 3B entity rows {head, tail, corrupt entity} of this rank's B
