@@ -76,6 +76,10 @@ struct hole_k1_shard {
   unsigned long long timeout_ns;
   hole_peer_ptrs shard;     // PEER: rank o's shard [R + rows_per, stride]
   hole_peer_ptrs stage;     // PEER: rank o's delta staging [world][cap][stride]
+  // the step's request lists are posted by this kernel too: uniq[cuts[o]..cuts[o+1]) -> rank o's inbox
+  const int32_t* uniq;      // [U] my request list (sorted unique global rows)
+  hole_peer_ptrs inbox;     // PEER: rank o's inbox of this step's parity, int32 [world][cap] (row `me` is mine)
+  hole_peer_ptrs meta;      // PEER: rank o's meta of this step's parity, int32 [world][2]
 };
 
 // wait until every peer's flag (written into MY memory) reaches `epoch`
@@ -181,6 +185,23 @@ __device__ __forceinline__ void hole_k1_body(const hole_k1_args& a, const hole_k
   if (DM == 2 && threadIdx.x <= sh.world) s_cuts[threadIdx.x] = sh.cuts[threadIdx.x];
   __syncthreads();
 
+  if (DM == 2) {
+    // post my request lists: slice o of `uniq` goes to rank o's inbox, (count, offset) to its meta.
+    // (The inbox is double buffered by step parity, so this needs no flag; the fence at the end of the
+    // kernel makes it visible before the step's "delivered" flag is raised.)
+    const int U = s_cuts[sh.world];
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int j = gtid; j < U; j += gridDim.x * blockDim.x) {
+      int o = 0;
+      while (j >= s_cuts[o + 1]) ++o;
+      static_cast<int32_t*>(sh.inbox.p[o])[(size_t)sh.me * sh.cap + (j - s_cuts[o])] = sh.uniq[j];
+    }
+    if (gtid < sh.world) {
+      int32_t* m = static_cast<int32_t*>(sh.meta.p[gtid]);
+      m[2 * sh.me] = s_cuts[gtid + 1] - s_cuts[gtid];
+      m[2 * sh.me + 1] = s_cuts[gtid];
+    }
+  }
   const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
   const int64_t g0l = w * a.T;
   const bool have = g0l < B;
@@ -223,7 +244,10 @@ __device__ __forceinline__ void hole_k1_body(const hole_k1_args& a, const hole_k
   }
   pdl_wait();                 // the previous step's K3 has finished updating the table
   if (DM == 2) hole_flags_wait(sh.flags, sh.world, sh.wait_epoch, sh.err, sh.timeout_ns);   // every shard is current
-  if (!have) return;
+  if (!have) {
+    if (DM == 2) __threadfence_system();      // this thread may have posted request-list entries
+    return;
+  }
   fetch(c, 0);
   if (g0 + 1 < g1) fetch(n1, 1);
 

@@ -12,15 +12,16 @@
 //     the request list `uniq`, per-owner cut points, triples re-indexed to request-list rows)
 //     -> integer update plan
 //   compute stream:
-//     post    my request lists -> the owners' inboxes                       (peer stores, ids only)
-//     K1      waits until every peer's shard is current (flag A), GATHERS the rows of its triples
+//     K1      posts my request lists to the owners' inboxes (peer stores, ids only), waits until every
+//             peer's shard is current (flag A), GATHERS the rows of its triples
 //             straight from the owners' shards (bulk async copies over NVLink), computes, and
 //             stores every unique row's delta into my slice of the owner's staging buffer
 //             (peer stores) -- the exchange is fused into the compute kernel, tile by tile
 //     K3      ordered combine of rows used more than once -> same staging buffers
 //     finish  my relation deltas -> every peer's relation staging; then signals flag B
 //             ("my deltas and request lists of this step are delivered") to every peer
-//     apply   waits for flag B of every peer; adds the staged deltas to my shard -- a row
+//     claim   waits for flag B of every peer; indexes the request lists by owned row
+//     apply   adds the staged deltas to my shard -- a row
 //             requested by several ranks gets its deltas in rank order, and the replicated
 //             relation block takes every rank's deltas in rank order, so the result is
 //             deterministic and the replicas stay bit-identical -- then signals flag A
@@ -59,6 +60,8 @@ struct hole_shard_state {
   const int32_t* csr_ids = nullptr;
   float* Drel = nullptr;                 // [R, stride] my relation deltas of the running step (zero between steps)
   unsigned* done = nullptr;              // [2] last-block-done counters (finish, apply)
+  unsigned* claim = nullptr;             // [rows_per] owner side: bit k = rank k lists the row this step
+  int32_t* slot = nullptr;               // [world][rows_per] where in rank k's list
   float* loss = nullptr;                 // [SHARD_LOSS_CHUNK, max_batch]
   float* loss_sum = nullptr;             // [SHARD_LOSS_CHUNK]
   int32_t* stage_tri = nullptr;          // device staging of hole_shard_steps_host
@@ -106,46 +109,54 @@ hole_shard_finish_kernel(float* __restrict__ Drel, int R, int me, int world, hol
   }
 }
 
-// first index in ids[0, n) with ids[.] >= x
-__device__ __forceinline__ int shard_lower_bound(const int32_t* __restrict__ ids, int n, int x) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (ids[mid] < x) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-// Owner side.  Items [0, R): replicated relation rows, shard[r] += relstage[k][r] for k = 0..world-1 in
-// order.  Items R + e: entry e of the concatenated request lists (inbox[k][g], every list ascending);
-// the group of the LOWEST rank that lists a row adds the staged deltas of every rank that lists it,
-// in rank order; the other groups of that row do nothing.  The last block signals flag A.
-template <int GS, int V>
+// Owner side, pass 1.  Waits for flag B of every peer (their deltas and request lists of this step are
+// here), then records for every entry g of every rank k's request list (inbox[k][g], a row of mine):
+// claim[row] |= 1 << k and slot[k][row] = g, so that pass 2 finds every rank's delta of a row directly.
 __global__ void __launch_bounds__(256)
-hole_shard_apply_kernel(float* __restrict__ shard, int64_t id_offset, const int32_t* __restrict__ inbox,
-                        const int32_t* __restrict__ meta, const float* __restrict__ stage,
-                        const float* __restrict__ relstage, int R, int world, int me, int64_t cap,
-                        const int* __restrict__ my_flags, int wait_epoch, int* __restrict__ err,
-                        unsigned long long timeout_ns, hole_peer_ptrs flags, int signal_epoch,
-                        unsigned* __restrict__ done, int nvec, int stride) {
-  constexpr int CH = (HOLE_MAX_RANKS + GS - 1) / GS;      // ranks per lane
-  __shared__ int s_n[HOLE_MAX_RANKS], s_pre[HOLE_MAX_RANKS + 1];
-  __shared__ bool s_last;
-  hole_flags_wait(my_flags + world, world, wait_epoch, err, timeout_ns);     // every peer's deltas are here
+hole_shard_claim_kernel(const int32_t* __restrict__ inbox, const int32_t* __restrict__ meta, int world,
+                        int64_t cap, int64_t row0, int64_t rows_per, unsigned* __restrict__ claim,
+                        int32_t* __restrict__ slot, const int* __restrict__ my_flags, int wait_epoch,
+                        int* __restrict__ err, unsigned long long timeout_ns) {
+  __shared__ int s_pre[HOLE_MAX_RANKS + 1];
+  hole_flags_wait(my_flags + world, world, wait_epoch, err, timeout_ns);
   if (threadIdx.x == 0) {
     int pre = 0;
-    for (int k = 0; k < world; ++k) {
-      const int n = meta[2 * k];
-      s_n[k] = n;
-      s_pre[k] = pre;
-      pre += n;
-    }
+    for (int k = 0; k < world; ++k) { s_pre[k] = pre; pre += meta[2 * k]; }
+    s_pre[world] = pre;
+  }
+  __syncthreads();
+  const int total = s_pre[world];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int k = 0;
+    while (e >= s_pre[k + 1]) ++k;
+    const int g = e - s_pre[k];
+    const int64_t row = (int64_t)inbox[(size_t)k * cap + g] - row0;
+    atomicOr(claim + row, 1u << k);
+    slot[(size_t)k * rows_per + row] = g;
+  }
+}
+
+// Owner side, pass 2.  Items [0, R): replicated relation rows, shard[r] += relstage[k][r] for
+// k = 0..world-1 in order.  Items R + e: entry e of the concatenated request lists; the group of the
+// LOWEST rank that lists a row adds the staged deltas of every rank that lists it, in rank order (and
+// clears the row's claim word); the other groups of that row do nothing.  The last block signals flag A.
+template <int GS, int V>
+__global__ void __launch_bounds__(256)
+hole_shard_apply_kernel(float* __restrict__ shard, const int32_t* __restrict__ inbox,
+                        const int32_t* __restrict__ meta, const float* __restrict__ stage,
+                        const float* __restrict__ relstage, int R, int world, int me, int64_t cap,
+                        int64_t row0, int64_t rows_per, unsigned* __restrict__ claim,
+                        const int32_t* __restrict__ slot, hole_peer_ptrs flags, int signal_epoch,
+                        unsigned* __restrict__ done, int nvec, int stride) {
+  __shared__ int s_pre[HOLE_MAX_RANKS + 1];
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    int pre = 0;
+    for (int k = 0; k < world; ++k) { s_pre[k] = pre; pre += meta[2 * k]; }
     s_pre[world] = pre;
   }
   __syncthreads();
   const int lane = threadIdx.x % GS;
-  const int gbase = (threadIdx.x % 32) / GS * GS;
-  const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << gbase);
   const int total = R + s_pre[world];
   const int gstride = (gridDim.x * blockDim.x) / GS;
   for (int item = (blockIdx.x * blockDim.x + threadIdx.x) / GS; item < total; item += gstride) {
@@ -163,43 +174,21 @@ hole_shard_apply_kernel(float* __restrict__ shard, int64_t id_offset, const int3
     const int e = item - R;
     int k = 0;
     while (e >= s_pre[k + 1]) ++k;
-    const int g = e - s_pre[k];
-    const int id = inbox[(size_t)k * cap + g];
-    // lane l (+ GS, ...) looks the row up in rank l's list
-    int pos[CH];
-    unsigned present = 0;
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch) {
-      const int l = ch * GS + lane;
-      int p = -1;
-      if (l < world) {
-        if (l == k) p = g;
-        else {
-          const int32_t* ids = inbox + (size_t)l * cap;
-          const int q = shard_lower_bound(ids, s_n[l], id);
-          if (q < s_n[l] && ids[q] == id) p = q;
-        }
-      }
-      pos[ch] = p;
-      const unsigned b = (__ballot_sync(gmask, p >= 0) >> gbase) & ((GS == 32) ? 0xffffffffu : ((1u << GS) - 1u));
-      present |= b << (ch * GS);
-    }
-    if (__ffs(present) - 1 != k) continue;               // a lower rank's group owns this row
-    float* erow = shard + (size_t)(id + id_offset) * stride;
+    const int64_t row = (int64_t)inbox[(size_t)k * cap + (e - s_pre[k])] - row0;
+    unsigned m = __ldcg(claim + row);
+    if ((m & (0u - m)) != (1u << k)) continue;           // a lower rank's group owns this row (or it is done)
+    float* erow = shard + (size_t)(R + row) * stride;
     Row<V> x, d;
     row_load<GS, V, false>(x, erow, lane, nvec);
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch) {
-      for (int j = 0; j < GS; ++j) {
-        const int l = ch * GS + j;
-        if (l >= world) break;
-        const int p = __shfl_sync(gmask, pos[ch], gbase + j);
-        if (p < 0) continue;
-        row_load<GS, V, false>(d, stage + ((size_t)l * cap + p) * stride, lane, nvec);
-        row_add(x, d);
-      }
+    while (m != 0) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const int g = __ldcg(slot + (size_t)l * rows_per + row);
+      row_load<GS, V, false>(d, stage + ((size_t)l * cap + g) * stride, lane, nvec);
+      row_add(x, d);
     }
     row_store<GS, V>(x, erow, lane, nvec);
+    if (lane == 0) claim[row] = 0;                       // ready for the next step
   }
   __threadfence_system();
   __syncthreads();
@@ -224,6 +213,7 @@ static void shard_free(hole_ctx* c) {
     cudaFree(s->prep[b].neg_w); cudaFree(s->prep[b].neg);
     if (s->prep[b].freed) cudaEventDestroy(s->prep[b].freed);
   }
+  cudaFree(s->claim); cudaFree(s->slot);
   cudaFree(s->Drel); cudaFree(s->done); cudaFree(s->loss); cudaFree(s->loss_sum); cudaFree(s->stage_tri);
   cudaFree(s->sums_dev);
   for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
@@ -281,6 +271,8 @@ extern "C" int hole_shard_init(hole_ctx* c, int world, int me, int64_t n_relatio
   const size_t rowb = (size_t)c->row_stride * sizeof(float);
   SH_ALLOC(s->Drel, std::max<size_t>(1, (size_t)s->R) * rowb);
   SH_ALLOC(s->done, 2 * sizeof(unsigned));
+  SH_ALLOC(s->claim, (size_t)rows_per_rank * sizeof(unsigned));
+  SH_ALLOC(s->slot, (size_t)world * rows_per_rank * sizeof(int32_t));
   SH_ALLOC(s->loss, (size_t)SHARD_LOSS_CHUNK * max_batch * 4);
   SH_ALLOC(s->loss_sum, (size_t)SHARD_LOSS_CHUNK * 4);
   for (int b = 0; b < 2; ++b) {
@@ -296,6 +288,7 @@ extern "C" int hole_shard_init(hole_ctx* c, int world, int me, int64_t n_relatio
 #undef SH_ALLOC
   HOLE_CUDA_TRY(cudaMemset(s->Drel, 0, std::max<size_t>(1, (size_t)s->R) * rowb));
   HOLE_CUDA_TRY(cudaMemset(s->done, 0, 2 * sizeof(unsigned)));
+  HOLE_CUDA_TRY(cudaMemset(s->claim, 0, (size_t)rows_per_rank * sizeof(unsigned)));
   rc = route_reserve(c, 3 * max_batch, SHARD_PREP_STEPS);
   if (rc) { shard_free(c); return rc; }
   HOLE_CUDA_TRY(cudaDeviceSynchronize());
@@ -407,9 +400,6 @@ extern "C" int hole_shard_step_compute(hole_ctx* c, const int32_t* pos, int64_t 
     mt.p[k] = k < world ? static_cast<int32_t*>(s->p_meta.p[k]) + (size_t)par * world * 2 : nullptr;
   }
   if ((rc = shard_mark(c, 0, st))) return rc;
-  hole_shard_post_kernel<<<(unsigned)std::min<int64_t>((3 * B + 255) / 256, c->sm_count * 2), 256, 0, st>>>(
-      p_uniq, p_cuts, world, me, s->cap, ib, mt);
-  HOLE_LAUNCHED();
   if ((rc = shard_mark(c, 1, st))) return rc;
   hole_k1_shard sh = {};
   sh.tri_w = p_pos_w; sh.neg_w = p_neg_w; sh.cuts = p_cuts;
@@ -417,6 +407,7 @@ extern "C" int hole_shard_step_compute(hole_ctx* c, const int32_t* pos, int64_t 
   sh.err = s->err; sh.wait_epoch = s->epoch; sh.R = (int)s->R; sh.rows_per = (int)s->rows_per;
   sh.me = me; sh.world = world; sh.cap = s->cap; sh.timeout_ns = s->timeout_ns;
   sh.shard = s->p_shard; sh.stage = s->p_stage;
+  sh.uniq = p_uniq; sh.inbox = ib; sh.meta = mt;          // the request lists are posted by K1 itself
   rc = run_step(c, pl, s->shard, p_pos_w, p_neg_w, side, B, margin, lr, loss_out, nullptr, k, st, s->Drel, false, 0,
                 &sh, pos, p_neg, c->profile ? s->prof_ev[s->prof_used - 6 + 2] : nullptr);
   if (rc) return rc;
@@ -444,11 +435,16 @@ extern "C" int hole_shard_step_apply(hole_ctx* c, void* stream) {
   const int par = s->epoch & 1, world = s->world, me = s->me;
   const int32_t* inbox = static_cast<const int32_t*>(s->p_inbox.p[me]) + (size_t)par * world * s->cap;
   const int32_t* meta = static_cast<const int32_t*>(s->p_meta.p[me]) + (size_t)par * world * 2;
-  HOLE_DISPATCH(c, hole_shard_apply_kernel, (unsigned)c->sm_count * 4, 256, (cudaStream_t)stream, s->shard,
-                s->R - (s->R + (int64_t)me * s->rows_per), inbox, meta, static_cast<const float*>(s->p_stage.p[me]),
-                static_cast<const float*>(s->p_relstage.p[me]), (int)s->R, world, me, s->cap,
-                static_cast<const int*>(s->p_flags.p[me]), s->epoch + 1, s->err, s->timeout_ns, s->p_flags,
-                s->epoch + 1, s->done + 1, c->nvec, c->row_stride);
+  const int64_t row0 = s->R + (int64_t)me * s->rows_per;     // first global row of my block
+  cudaStream_t st = (cudaStream_t)stream;
+  hole_shard_claim_kernel<<<(unsigned)c->sm_count * 2, 256, 0, st>>>(
+      inbox, meta, world, s->cap, row0, s->rows_per, s->claim, s->slot, static_cast<const int*>(s->p_flags.p[me]),
+      s->epoch + 1, s->err, s->timeout_ns);
+  HOLE_LAUNCHED();
+  HOLE_DISPATCH(c, hole_shard_apply_kernel, (unsigned)c->sm_count * 16, 256, st, s->shard, inbox, meta,
+                static_cast<const float*>(s->p_stage.p[me]), static_cast<const float*>(s->p_relstage.p[me]),
+                (int)s->R, world, me, s->cap, row0, s->rows_per, s->claim, s->slot, s->p_flags, s->epoch + 1,
+                s->done + 1, c->nvec, c->row_stride);
   s->epoch += 1;
   return shard_mark(c, 5, (cudaStream_t)stream);
 }
