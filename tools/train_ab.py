@@ -14,18 +14,11 @@ sys.path.insert(0, ROOT)
 PKG = os.path.join(ROOT, "graphembeddings_b200")
 
 VARIANTS = [  # (name, env)
-    ("v1 kernel, no ramp", {"HOLE_K1": "v1", "HOLE_PLAN_RAMP": "0"}),
-    ("v1 kernel, ramp 2x4", {"HOLE_K1": "v1", "HOLE_PLAN_RAMP": "2,4"}),
-    ("v2 256x2, no ramp", {"HOLE_PLAN_RAMP": "0"}),
-    ("v2 256x2, ramp 1x2", {"HOLE_PLAN_RAMP": "1,2"}),
-    ("v2 256x2, ramp 2x2", {"HOLE_PLAN_RAMP": "2,2"}),
-    ("v2 256x2, ramp 2x4", {"HOLE_PLAN_RAMP": "2,4"}),
-    ("v2 256x2, ramp 4x4", {"HOLE_PLAN_RAMP": "4,4"}),
-    ("v2 128x5 (96 regs), ramp 2x4", {"HOLE_B200_LIB": os.path.join(PKG, "libhole_b200_128x5.so"),
-                                      "HOLE_K1_BLOCK": "128", "HOLE_PLAN_RAMP": "2,4"}),
-    ("v2 128x4, ramp 2x4", {"HOLE_K1_BLOCK": "128", "HOLE_PLAN_RAMP": "2,4"}),
-    ("v2 256x2 fast sigmoid, ramp 2x4", {"HOLE_B200_LIB": os.path.join(PKG, "libhole_b200_fastsig.so"),
-                                         "HOLE_PLAN_RAMP": "2,4"}),
+    ("K1 v2 (default)", {}),
+    ("K1 v1 (round 1 kernel)", {"HOLE_K1": "v1"}),
+    ("K1 v2, trained-scale table (clips fire)", {"AB_TRAINED": "1"}),
+    ("K1 v2, B=512", {"AB_BATCH": "512"}),
+    ("K1 v2, B=8192", {"AB_BATCH": "8192"}),
 ]
 
 
