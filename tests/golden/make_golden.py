@@ -147,6 +147,18 @@ def gen_fb15k_fixtures():
                 dst.write(line)
 
 
+def gen_fb15k_full_triples():
+    """The complete id-mapped FB15k test / valid triple files (59,071 / 50,000 rows: BASELINE config 2's
+    real queries) as one compressed int32 fixture -- data, not source; the GPU box has no /root/reference."""
+    out = {}
+    for name, key in (("test_positive_triples.txt", "test"), ("triples-valid.txt", "valid")):
+        arr = np.loadtxt(os.path.join(REF, "diffbot_data/FB15k", name), dtype=np.int64, delimiter="\t")
+        assert arr.min() >= 0 and arr.max() < 2 ** 31
+        out[key] = arr.astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "fb15k_test_valid_triples.npz"), **out)
+    print("fb15k_test_valid_triples.npz:", {k: v.shape for k, v in out.items()})
+
+
 def gen_train_step_golden():
     from oracle import hole_oracle as O
     from graphembeddings_b200 import data as D
@@ -196,5 +208,6 @@ def gen_logloss_step_golden():
 if __name__ == "__main__":
     gen_ranking_golden()
     gen_fb15k_fixtures()
+    gen_fb15k_full_triples()
     gen_train_step_golden()
     gen_logloss_step_golden()

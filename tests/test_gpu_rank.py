@@ -49,7 +49,7 @@ def _exact_from_operands(e, kg, queries, side, ent_begin, ent_end, raw, filt, ts
     hi = (S <= thr[:, None] + eps).sum(1) - 1      # minus the true candidate itself
     exact = ((S < thr[:, None]) | ((S == thr[:, None]) & (ids[None, :] < tj[:, None]))).sum(1)
     assert np.all(raw >= lo) and np.all(raw <= hi)
-    assert np.mean(raw == exact) > 0.99
+    assert np.all((raw == exact) | (hi > lo))            # outside a near-tie the count is exact
     if foff is not None:
         for q in range(len(queries)):
             f = fids[foff[q]:foff[q + 1]].astype(np.int64) - ent_begin
@@ -182,10 +182,12 @@ def test_ragged_sizes_and_ties(eng_mod):
     ids = np.arange(S.shape[1])
     exact = ((S < thr[:, None]) | ((S == thr[:, None]) & (ids[None] < tj[:, None]))).sum(1)
     raw = raw.cpu().numpy()
-    # exact ties (identical rows) are resolved exactly; fp32-noise near-ties may move others
-    assert np.mean(raw == exact) > 0.97
+    # exact ties (identical rows) are resolved exactly; only fp32-noise near-ties may move a count, and
+    # then only inside the band
     strict = (S < thr[:, None] - 2e-6).sum(1)
-    assert np.all(raw >= strict + want_extra)
+    loose = (S <= thr[:, None] + 2e-6).sum(1) - 1
+    assert np.all(raw >= strict + want_extra) and np.all(raw <= loose)
+    assert np.all((raw == exact) | (loose > strict + want_extra))
 
 
 def test_empty_queries_and_errors(eng_mod):
@@ -250,7 +252,7 @@ def test_full_size_config3_sample_against_fp64_contraction(eng_mod):
     assert bool(((r >= lo) & (r <= hi)).all())
     ids = torch.arange(N, device="cuda")
     exact = ((S < thr[:, None]) | ((S == thr[:, None]) & (ids[None, :] < tj[:, None]))).sum(1)
-    assert float((r == exact).double().mean()) > 0.9
+    assert bool(((r == exact) | (hi > lo)).all())       # a count differs only where a near-tie exists
     # candidate-shard invariance at full size: two halves accumulate to the same counts
     raw2 = torch.zeros_like(raw); f2 = torch.zeros_like(raw)
     mid = b + 600_123
@@ -284,5 +286,6 @@ def test_split_bf16_precision_matches_fp64_oracle(eng_mod, dim, side):
     frac_x3 = np.mean(raw == exact)
     raw_bf, _, _ = e.rank(kg.triples, side, b, en)
     frac_bf = np.mean(raw_bf.cpu().numpy() == exact)
-    assert frac_x3 > 0.97 and frac_x3 > frac_bf
+    assert np.all((raw == exact) | (hi > lo))            # exact wherever no candidate sits inside the band
+    assert frac_x3 >= frac_bf
     assert np.all(filt <= raw) and np.all(filt >= 0)
