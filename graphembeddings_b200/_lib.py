@@ -54,6 +54,9 @@ SIGNATURES = {
     "hole_train_steps": (_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _u64, _u64, _f32, _p, _p, _p, _p]),
     "hole_train_steps_host": (_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _u64, _u64, _f32, _p, _p, _p]),
     "hole_rank": (_int, [_p, _p, _i64, _i64, _p, _i64, _int, _int, _p, _p, _p, _int, _p, _p, _p]),
+    "hole_rank_ex": (_int, [_p, _p, _i64, _i64, _p, _p, _i64, _int, _int, _p, _p, _p, _int, _p, _p, _p]),
+    "hole_rank_prepare": (_int, [_p, _p, _i64, _i64, _int, _p]),
+    "hole_rank_invalidate": (_int, [_p]),
     "hole_rank_debug_operands": (_int, [_p, _p, _p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_int), _p]),
     "hole_profile_enable": (_int, [_p, _int]),
     "hole_profile_read": (_int, [_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),

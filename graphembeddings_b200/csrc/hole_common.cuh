@@ -129,6 +129,7 @@ struct hole_peer_ptrs { void* p[HOLE_MAX_RANKS]; };
 
 int hole_ws_reserve(hole_ctx* ctx, int64_t B, int64_t S);
 void hole_rank_ws_free(hole_ctx* ctx);
+void hole_rank_cache_invalidate(hole_ctx* ctx);   // a training call changes the table: drop the packed operand
 
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 (must match oracle/philox.py bit for bit)

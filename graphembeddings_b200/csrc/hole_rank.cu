@@ -784,7 +784,16 @@ struct hole_rank_ws {
   bool attr_set = false;
   int64_t last_npad = 0, last_qpad = 0;
   int last_K = 0;
+  // packed candidate operand kept across calls (hole_rank_prepare): valid for exactly this table / range
+  const float* cache_table = nullptr;
+  int64_t cache_begin = -1, cache_end = -1;
+  int cache_parts = 0;
+  bool cache_valid = false;
 };
+
+void hole_rank_cache_invalidate(hole_ctx* c) {
+  if (c->rank != nullptr) c->rank->cache_valid = false;
+}
 
 void hole_rank_ws_free(hole_ctx* c) {
   if (c->rank == nullptr) return;
@@ -793,15 +802,21 @@ void hole_rank_ws_free(hole_ctx* c) {
   c->rank = nullptr;
 }
 
-extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int64_t ent_end,
-                         const int32_t* queries, int64_t Q, int side, int precision,
-                         const int64_t* filter_off, const int32_t* filter_ids, float* true_score_io,
-                         int compute_true, int32_t* raw_before, int32_t* filt_before, void* stream) {
+// prepare_only: pack (and keep) the candidate operand, nothing else
+static int rank_impl(hole_ctx* c, const float* table, int64_t ent_begin, int64_t ent_end,
+                     const float* query_table, const int32_t* queries, int64_t Q, int side, int precision,
+                     const int64_t* filter_off, const int32_t* filter_ids, float* true_score_io,
+                     int compute_true, int32_t* raw_before, int32_t* filt_before, void* stream,
+                     bool prepare_only) {
   HOLE_CHECK_ARG(c && Q >= 0 && ent_begin >= 0 && ent_end >= ent_begin && ent_end <= c->n_rows);
   HOLE_CHECK_ARG(side == HOLE_SIDE_TAIL || side == HOLE_SIDE_HEAD || side == HOLE_SIDE_BOTH);
-  if (Q == 0 || ent_end == ent_begin) return HOLE_OK;
+  if ((Q == 0 && !prepare_only) || ent_end == ent_begin) return HOLE_OK;
   if (side == HOLE_SIDE_BOTH) Q *= 2;    // output rows: [tail ranks of all queries | head ranks]
-  HOLE_CHECK_ARG(table && queries && true_score_io && raw_before && filt_before);
+  const bool count = raw_before != nullptr;          // without count buffers: true scores only
+  HOLE_CHECK_ARG(table != nullptr && (prepare_only || (queries && true_score_io)));
+  HOLE_CHECK_ARG((raw_before == nullptr) == (filt_before == nullptr));
+  HOLE_CHECK_ARG(prepare_only || count || compute_true);
+  if (query_table == nullptr) query_table = table;
   HOLE_CHECK_ARG((filter_off == nullptr) == (filter_ids == nullptr));
   HOLE_CHECK_ARG(precision == HOLE_RANK_BF16 || precision == HOLE_RANK_BF16X3);
   const int parts = (precision == HOLE_RANK_BF16X3) ? 2 : 1;
@@ -836,6 +851,7 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
   if ((size_t)Npad * Kall > w->cand_cap) {
     HOLE_CUDA_TRY(cudaStreamSynchronize(st));
     cudaFree(w->cand); w->cand = nullptr; w->cand_cap = 0;
+    w->cache_valid = false;
     if (cudaMalloc((void**)&w->cand, (size_t)Npad * Kall * 2) != cudaSuccess) {
       cudaGetLastError();
       return hole_set_error(HOLE_ERR_ALLOC, "ranking candidate operand allocation failed");
@@ -861,11 +877,22 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
     w->attr_set = true;
   }
 
-  w->last_npad = Npad; w->last_qpad = Qpad; w->last_K = Kall;
-  // operands
-  hole_rank_pack_cand_kernel<<<(unsigned)((Npad + 7) / 8), 256, 0, st>>>(table, c->row_stride, c->H, ent_begin, Nc, Npad, K, parts, w->cand);
-  HOLE_LAUNCHED();
-  hole_rank_pack_query_kernel<<<(unsigned)((Qpad + 7) / 8), 256, 0, st>>>(table, c->row_stride, c->H, queries, (int)Q, Qpad, side, ent_begin, K, parts, w->qp, w->true_idx);
+  w->last_npad = Npad; w->last_K = Kall;
+  // operands: the candidate operand is reused when hole_rank_prepare packed exactly this table / range
+  const bool cached = w->cache_valid && w->cache_table == table && w->cache_begin == ent_begin &&
+                      w->cache_end == ent_end && w->cache_parts == parts;
+  if (!cached) {
+    w->cache_valid = false;
+    hole_rank_pack_cand_kernel<<<(unsigned)((Npad + 7) / 8), 256, 0, st>>>(table, c->row_stride, c->H, ent_begin, Nc, Npad, K, parts, w->cand);
+    HOLE_LAUNCHED();
+  }
+  if (prepare_only) {
+    w->cache_table = table; w->cache_begin = ent_begin; w->cache_end = ent_end; w->cache_parts = parts;
+    w->cache_valid = true;
+    return HOLE_OK;
+  }
+  w->last_qpad = Qpad;
+  hole_rank_pack_query_kernel<<<(unsigned)((Qpad + 7) / 8), 256, 0, st>>>(query_table, c->row_stride, c->H, queries, (int)Q, Qpad, side, ent_begin, K, parts, w->qp, w->true_idx);
   HOLE_LAUNCHED();
 
   CUtensorMap mapA, mapB;
@@ -903,6 +930,7 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
     HOLE_LAUNCHED();
   }
 
+  if (!count) return HOLE_OK;                      // true scores only (first phase of the sharded ranking)
   rc = make_map(&mapB, w->cand, Npad, Kall, use_pair ? BN / 2 : BN);
   if (rc) return rc;
   p.mode = MODE_COUNT;
@@ -933,6 +961,34 @@ extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int
     hole_rank_filter_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, st>>>(w->qp, w->cand, K, parts, filter_off, filter_ids, ent_begin, Nc, true_score_io, w->true_idx, (int)Q, filt_before);
     HOLE_LAUNCHED();
   }
+  return HOLE_OK;
+}
+
+extern "C" int hole_rank(hole_ctx* c, const float* table, int64_t ent_begin, int64_t ent_end,
+                         const int32_t* queries, int64_t Q, int side, int precision,
+                         const int64_t* filter_off, const int32_t* filter_ids, float* true_score_io,
+                         int compute_true, int32_t* raw_before, int32_t* filt_before, void* stream) {
+  return rank_impl(c, table, ent_begin, ent_end, nullptr, queries, Q, side, precision, filter_off, filter_ids,
+                   true_score_io, compute_true, raw_before, filt_before, stream, false);
+}
+
+extern "C" int hole_rank_ex(hole_ctx* c, const float* table, int64_t ent_begin, int64_t ent_end,
+                            const float* query_table, const int32_t* queries, int64_t Q, int side, int precision,
+                            const int64_t* filter_off, const int32_t* filter_ids, float* true_score_io,
+                            int compute_true, int32_t* raw_before, int32_t* filt_before, void* stream) {
+  return rank_impl(c, table, ent_begin, ent_end, query_table, queries, Q, side, precision, filter_off, filter_ids,
+                   true_score_io, compute_true, raw_before, filt_before, stream, false);
+}
+
+extern "C" int hole_rank_prepare(hole_ctx* c, const float* table, int64_t ent_begin, int64_t ent_end,
+                                 int precision, void* stream) {
+  return rank_impl(c, table, ent_begin, ent_end, nullptr, nullptr, 0, HOLE_SIDE_TAIL, precision, nullptr, nullptr,
+                   nullptr, 0, nullptr, nullptr, stream, true);
+}
+
+extern "C" int hole_rank_invalidate(hole_ctx* c) {
+  HOLE_CHECK_ARG(c != nullptr);
+  hole_rank_cache_invalidate(c);
   return HOLE_OK;
 }
 

@@ -1395,6 +1395,7 @@ static int k1_prepare(hole_ctx* c);
 
 // Workspace for chunks of S steps of batch B.  Reallocation synchronises the device.
 int hole_ws_reserve(hole_ctx* c, int64_t B, int64_t S) {
+  hole_rank_cache_invalidate(c);     // every training entry point comes through here
   if (!c->k1_ready) {
     int rc = k1_prepare(c);
     if (rc) return rc;

@@ -55,6 +55,39 @@ def _load_triples_native(path):
     return out
 
 
+def check_triple_ids(triples, entity_count, relation_count=None, what="triples"):
+    """The reference's embedding_lookup raises InvalidArgument on an out-of-range id; the kernels index
+    the table unchecked, so the host checks once per file (one numpy pass)."""
+    t = np.asarray(triples)
+    if t.size == 0:
+        return
+    if t.min() < 0:
+        raise ValueError(f"{what}: negative id {int(t.min())}")
+    if int(t[:, :2].max()) >= entity_count:
+        raise ValueError(f"{what}: entity id {int(t[:, :2].max())} >= entity_count {entity_count} "
+                         "(entity_metadata.tsv has fewer rows than the triples use)")
+    rmax = int(t[:, 2].max())
+    if rmax >= entity_count:                  # relations are rows of the same table (holE.py:186, 263-264)
+        raise ValueError(f"{what}: relation id {rmax} outside the table of {entity_count} rows")
+    if relation_count and rmax >= relation_count:
+        raise ValueError(f"{what}: relation id {rmax} >= relation_count {relation_count} (relation_ids.txt)")
+
+
+def rows_in(a, b):
+    """Boolean mask: which triples of `a` [n,3] (a few 1e5 rows) occur in `b` [m,3] (up to 1e8 rows) --
+    without walking `b` in Python: `b` is first cut down to the rows whose (head, relation) occurs in `a`
+    (one sort-based np.isin over int64 keys)."""
+    a = np.asarray(a, dtype=np.int64).reshape(-1, 3)
+    b = np.asarray(b, dtype=np.int64).reshape(-1, 3)
+    if len(a) == 0 or len(b) == 0:
+        return np.zeros(len(a), dtype=bool)
+    ka = (a[:, 0] << 32) | a[:, 2]
+    kb = (b[:, 0] << 32) | b[:, 2]
+    near = b[np.isin(kb, ka)]
+    seen = set(map(tuple, near.tolist()))
+    return np.fromiter((tuple(x) in seen for x in a.tolist()), dtype=bool, count=len(a))
+
+
 def count_lines(path):
     """holE.py:52-53 count lines with ``sum(1 for line in open(f))``."""
     with open(path, "rb") as f:
@@ -237,14 +270,10 @@ def synthetic_kg(n_relations, n_entities, n_triples, n_types, dim, seed, zipf_en
     return SyntheticKG(n_relations, n_entities, dim, triples, type_of, E)
 
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                       "tests", "golden")
-
-
 def fb15k_type_histogram():
-    """The 815-class entity type histogram of the real FB15k metadata (372 singletons),
-    committed as tests/golden/fb15k_types.json by tests/golden/make_golden.py."""
-    with open(os.path.join(_GOLDEN, "fb15k_types.json")) as f:
+    """The 815-class entity type histogram of the real FB15k metadata (372 singletons): package data,
+    written by tests/golden/make_golden.py from diffbot_data/FB15k/entity_metadata.tsv."""
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fb15k_types.json")) as f:
         return json.load(f)["entity_type_histogram"]
 
 

@@ -340,6 +340,25 @@ class HoleEngine:
                                  _stream()))
         return raw_before, filt_before, true_score
 
+    def rank_prepare(self, ent_begin, ent_end, precision=HOLE_RANK_BF16):
+        """Pack the candidate operand of [ent_begin, ent_end) once; later rank() calls on the same table /
+        range reuse it (until a training call on this engine or rank_invalidate())."""
+        check(self.lib.hole_rank_prepare(self._ctx, _ptr(self.table), int(ent_begin), int(ent_end), int(precision),
+                                         _stream()))
+
+    def rank_invalidate(self):
+        check(self.lib.hole_rank_invalidate(self._ctx))
+
+    def rank_ex(self, queries_i32, side, ent_begin, ent_end, query_table=None, filter_off=None, filter_ids=None,
+                precision=HOLE_RANK_BF16, true_score=None, compute_true=True, raw_before=None, filt_before=None):
+        """hole_rank_ex on device tensors as they are (no conversions): queries int32 [Q,3]; query_table = the
+        table the queries' other-entity / relation rows are read from (None: self.table); raw_before /
+        filt_before None = true scores only."""
+        check(self.lib.hole_rank_ex(self._ctx, _ptr(self.table), int(ent_begin), int(ent_end), _ptr(query_table),
+                                    _ptr(queries_i32), queries_i32.shape[0], int(side), int(precision),
+                                    _ptr(filter_off), _ptr(filter_ids), _ptr(true_score), 1 if compute_true else 0,
+                                    _ptr(raw_before), _ptr(filt_before), _stream()))
+
     def rank_debug_operands(self):
         """(candidate operand [n_pad, K], query operand [q_pad, K]) of the last rank() call as
         bf16 CUDA tensors -- test hook."""

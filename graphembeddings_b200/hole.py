@@ -8,7 +8,8 @@ Function names follow the reference: init_data (holE.py:44-94), evaluate_batch (
 run_training (249-370), init_inference_data (381-424), eval_link_prediction (427-472),
 score_mrr (475-490), infer_triples (530-582).  Differences, all deliberate and listed in
 DESIGN.md: triples come from a device-resident per-epoch permutation instead of a TF shuffle
-queue; corruption is the Philox sampler (--padded_size accepted, unused); `--infer` runs the
+queue; every validation point scores the WHOLE triples-valid.txt on the device (the reference's TODO,
+holE.py:350) and writes the reference's scalar / histogram summaries to a TensorBoard events file; corruption is the Philox sampler (--padded_size accepted, unused); `--infer` runs the
 all-entity filtered head+tail protocol with the unreachable `infer_threshold` gate off unless
 --infer_gate is given; --save_embeddings is rejected (a py2-only debug dump).  --log_loss,
 --negative_ratio and --l2_regularization select the logistic branch (holE.py:194-196, 206-220).
@@ -25,6 +26,7 @@ import torch
 
 from . import data as D
 from . import tf_bundle
+from . import tf_events
 from .engine import (HOLE_RANK_BF16, HOLE_RANK_BF16X3, HOLE_SIDE_HEAD, HOLE_SIDE_TAIL, HoleEngine,
                      inverse_time_decay)
 
@@ -85,6 +87,11 @@ def init_data(flags=None):
     data.triples = D.load_triples(train_triple_file)
     data.triple_count = data.triples.shape[0]
     data.validation_triples = D.load_triples(valid_triple_file)
+    D.check_triple_ids(data.triples, data.entity_count, data.relation_count, train_triple_file)
+    D.check_triple_ids(data.validation_triples, data.entity_count, data.relation_count, valid_triple_file)
+    if len(data.id_to_type) != data.entity_count or (data.id_to_type and max(data.id_to_type) != data.entity_count - 1):
+        raise ValueError(f"{entity_file}: the Index column must cover rows 0..{data.entity_count - 1} exactly once "
+                         "(every table row needs a type for the corruption sampler)")
     print('Entities: ', data.entity_count - data.relation_count, 'Relations: ', data.relation_count,
           'Triples: ', data.triple_count)
     print('Types: ', {k: len(v) for k, v in data.type_to_ids.items()} if len(data.type_to_ids) < 40
@@ -107,6 +114,7 @@ def init_inference_data(flags=None):
         data.id_to_metadata[index] = meta
     data.relation_count = D.count_lines(os.path.join(flags.data_dir, 'relation_ids.txt'))
     data.test = D.load_triples(os.path.join(flags.data_dir, 'test_positive_triples.txt'))
+    D.check_triple_ids(data.test, data.entity_count, data.relation_count, 'test_positive_triples.txt')
     for h, t, r in data.test.tolist():
         data.test_triples[h][r].add(t)
     known = []
@@ -114,9 +122,14 @@ def init_inference_data(flags=None):
         path = os.path.join(flags.data_dir, name)
         if os.path.exists(path):
             known.append(D.load_triples(path))
+            D.check_triple_ids(known[-1], data.entity_count, data.relation_count, name)
     data.known = np.concatenate(known) if known else np.zeros((0, 3), np.int32)
-    for h, t, r in data.known.tolist():
-        if h in data.test_triples and r in data.test_triples[h]:
+    # true_triples[h][r] only for (h, r) pairs present in test (holE.py:421-422): cut the known triples
+    # down to those pairs with one sort-based pass instead of walking 3e7 rows in Python
+    if len(data.known) and len(data.test):
+        kq = (data.test[:, 0].astype(np.int64) << 32) | data.test[:, 2].astype(np.int64)
+        kk = (data.known[:, 0].astype(np.int64) << 32) | data.known[:, 2].astype(np.int64)
+        for h, t, r in data.known[np.isin(kk, kq)].tolist():
             data.true_triples[h][r].add(t)
     return data
 
@@ -129,9 +142,12 @@ def make_engine(entity_count, relation_count, dim, embeddings, id_to_type=None, 
     eng.set_relation_count(max(1, relation_count))
     if id_to_type is not None:
         names = {}
-        type_of = np.zeros(entity_count, dtype=np.int32)
+        type_of = np.full(entity_count, -1, dtype=np.int32)
         for idx, t in id_to_type.items():
             type_of[idx] = names.setdefault(t, len(names))
+        if (type_of < 0).any():
+            raise ValueError(f"{int((type_of < 0).sum())} table rows have no type in the metadata "
+                             f"(first: {int(np.flatnonzero(type_of < 0)[0])})")
         off, ids = D.build_type_csr(type_of, len(names))
         eng.set_types(type_of, off, ids)
     return eng
@@ -219,7 +235,9 @@ def run_training(data, flags=None, seed=0, max_steps=None, log=print):
     gen = torch.Generator(device=eng.device)
     gen.manual_seed(seed)
     vrng = np.random.default_rng(seed + 1)
+    valid_dev = torch.from_numpy(np.ascontiguousarray(valid)).to(eng.device) if len(valid) else None
     log_path = os.path.join(flags.output_dir, 'summaries.tsv')
+    events = tf_events.EventFileWriter(flags.output_dir)      # summary_writer (holE.py:317)
     pocket_loss = 2.
     steps_done = 0
     t_start = time.time()
@@ -234,7 +252,13 @@ def run_training(data, flags=None, seed=0, max_steps=None, log=print):
                 batch = 1                       # for batch in range(1, batch_count)  (holE.py:340)
                 while batch < batch_count:
                     if batch % valid_every == 0 and len(valid) > 0:
-                        vb = valid[vrng.integers(0, len(valid), size=B)]
+                        # The reference scores ONE shuffled batch of the validation file and notes
+                        # "TODO: this should run the entire validation set" (holE.py:350): the whole file
+                        # is scored on the device here (--valid_sample restores the sampled batch).
+                        if getattr(flags, "valid_sample", False):
+                            vb = valid[vrng.integers(0, len(valid), size=B)]
+                        else:
+                            vb = valid_dev
                         if flags.log_loss:
                             vloss = evaluate_batch_logloss(eng, vb, seed, global_step, flags.l2_regularization,
                                                            flags.negative_ratio)
@@ -250,6 +274,23 @@ def run_training(data, flags=None, seed=0, max_steps=None, log=print):
                             row.update({f"{nm}_{k}": v for k, v in summarize(var).items()})
                         slog.write("\t".join(f"{k}={v}" for k, v in row.items()) + "\n")
                         slog.flush()
+                        # the merged summaries of holE.py:352-353: the validation twin's scalars and
+                        # histograms, the training graph's on the next training batch (scored, not
+                        # trained on), and the learning rate -- under the reference's name scopes
+                        scal, hist = {"batch/learn/learning_rate": lr_now}, {}
+                        scopes = {"pos": "validation/positive/eval", "neg": "validation/corrupt/eval",
+                                  "loss": "validation"}
+                        for nm, var in parts:
+                            sc_, hi_ = tf_events.summarize_tags(scopes[nm], var.float().cpu().numpy())
+                            scal.update(sc_); hist.update(hi_)
+                        if not flags.log_loss:
+                            tb = shuffled[(batch - 1) * B:batch * B]
+                            tl, tp, tn = evaluate_batch(eng, tb, seed, global_step, flags.margin)
+                            for scope, var in (("batch/eval/positive/eval", tp), ("batch/eval/corrupt/eval", tn),
+                                               ("batch/eval", tl)):
+                                sc_, hi_ = tf_events.summarize_tags(scope, var.float().cpu().numpy())
+                                scal.update(sc_); hist.update(hi_)
+                        events.add_summary(global_step, scal, hist)
                         log('\tStep {} Validation Loss: {}...'.format(global_step, vlm))
                         if vlm < pocket_loss:       # pocket checkpoint (holE.py:357-360)
                             pocket_loss = vlm
@@ -280,6 +321,7 @@ def run_training(data, flags=None, seed=0, max_steps=None, log=print):
         log('Done training -- step limit reached')
     finally:
         log('Stopping training...')
+        events.close()
     torch.cuda.synchronize()
     if not os.path.exists(os.path.join(flags.output_dir, 'model.ckpt.index')):
         save_checkpoint(eng, flags.output_dir, global_step)    # never validated: still leave a model
@@ -327,9 +369,7 @@ def eval_link_prediction(eng, queries, known, relation_count, entity_count, side
     Returns (raw_positions, filtered_positions) lists."""
     queries = np.unique(np.asarray(queries, dtype=np.int32).reshape(-1, 3), axis=0)   # test sets dedupe
     raw_positions, filtered_positions = [], []
-    known_set = set(map(tuple, np.asarray(known).reshape(-1, 3).tolist()))
-    keep = np.array([tuple(q) not in known_set for q in queries.tolist()], dtype=bool)
-    queries = queries[keep]
+    queries = queries[~D.rows_in(queries, known)]
     if len(queries) == 0:
         return raw_positions, filtered_positions
     for side_name in sides:
@@ -463,6 +503,8 @@ def build_parser():
                         help='Apply the reference\'s `min sigma < infer_threshold` gate (off: it never fires).')
     parser.add_argument('--rank_precision', choices=['bf16', 'bf16x3'], default='bf16x3',
                         help='Tensor-core operand precision of --infer (bf16x3 = split-bf16, ~fp32 ranks).')
+    parser.add_argument('--valid_sample', action='store_true',
+                        help='Validate on one sampled batch as holE.py does (default: the whole triples-valid.txt).')
     parser.add_argument('--seed', type=int, default=0)
     parser.add_argument('--max_steps', type=int, default=None, help='Stop after this many steps (testing).')
     return parser

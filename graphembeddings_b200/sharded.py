@@ -257,10 +257,15 @@ class RowShardedTrainer:
         return loss
 
     # ------------------------------------------------------------------ ranking
-    def rank(self, queries, side, filter_off=None, filter_ids=None):
-        """All-entity ranking of (replicated) queries [Q,3] with candidates sharded by row
-        block.  Returns (raw_before, filt_before) int32[Q], identical on every rank."""
-        from .engine import HOLE_SIDE_TAIL, HoleEngine
+    def rank(self, queries, side, filter_off=None, filter_ids=None, precision=None):
+        """All-entity ranking of (replicated) queries [Q,3] with candidates sharded by row block.
+        Returns (raw_before, filt_before) int32[Q], identical on every rank.
+
+        The candidate operand is my block of the shard as it lies (packed once per call); the rows of the
+        queries' other entities come from their owners into a small side table [relations | fetched rows].
+        Phase 1 computes only the true candidates' scores (each by its owner), phase 2 counts."""
+        from .engine import HOLE_RANK_BF16, HOLE_SIDE_TAIL, HoleEngine
+        precision = HOLE_RANK_BF16 if precision is None else precision
         dev = self.shard.device
         q = torch.as_tensor(queries).to(dev).long()
         Q, R = q.shape[0], self.R
@@ -270,44 +275,44 @@ class RowShardedTrainer:
         ids_in = self._a2a(uniq, send_counts, recv_counts)
         rows_in = self._a2a(self.shard.index_select(0, ids_in - self.begin + R), recv_counts, send_counts)
         n_mine = self.end - self.begin                                  # (the last shard may carry padding rows)
-        table = torch.cat([self.shard[:R + n_mine], rows_in], dim=0)    # [R | my block | fetched]
+        qtab = torch.cat([self.shard[:R], rows_in], dim=0)              # [relations | fetched rows]: small
         tr = q[:, true_col]
-        # true candidate: local index if mine, else below / above my candidate range
+        # true candidate: shard-local row if mine, else below / above my candidate range
         tr_loc = torch.where(tr < self.begin, torch.zeros_like(tr) - 1 + R,       # < ent_begin
                              torch.where(tr >= self.end, torch.full_like(tr, R + n_mine + 1),
                                          tr - self.begin + R))
-        ql = torch.empty_like(q)
-        ql[:, other_col] = R + n_mine + inv
-        ql[:, true_col] = tr_loc
-        ql[:, 2] = q[:, 2]
+        ql = torch.empty((Q, 3), dtype=torch.int32, device=dev)
+        ql[:, other_col] = (R + inv).to(torch.int32)                    # row of the side table
+        ql[:, true_col] = tr_loc.to(torch.int32)                        # index into my candidate range only
+        ql[:, 2] = q[:, 2].to(torch.int32)
         fo = fi = None
         if filter_off is not None:
-            fo = torch.as_tensor(filter_off).to(dev)
-            fi = (torch.as_tensor(filter_ids).to(dev).long() - self.begin + R).to(torch.int32)
-        # a ranking context sized for [relations | my block | fetched rows]
+            fo = torch.as_tensor(filter_off).to(dev).to(torch.int64).contiguous()
+            fi = (torch.as_tensor(filter_ids).to(dev).long() - self.begin + R).to(torch.int32).contiguous()
+        # a ranking context over my shard
         eng = getattr(self, "_rank_eng", None)
-        if eng is None or eng.n_rows < table.shape[0]:
+        if eng is None or eng.n_rows != self.shard.shape[0]:
             if eng is not None:
                 eng.close()
-            eng = self._rank_eng = HoleEngine(int(table.shape[0] * 1.25) + 1024, self.dim, dev.index or 0)
-        eng.table = table
+            eng = self._rank_eng = HoleEngine(int(self.shard.shape[0]), self.dim, dev.index or 0)
+        eng.table = self.shard
         try:
+            eng.rank_invalidate()                                       # the shard has been trained since
+            eng.rank_prepare(R, R + n_mine, precision)
             ts = torch.zeros(Q, dtype=torch.float32, device=dev)
-            scratch = torch.zeros(Q, dtype=torch.int32, device=dev)
-            eng.rank(ql.to(torch.int32), side, R, R + n_mine, None, None, true_score=ts,
-                     compute_true=True, raw_before=scratch, filt_before=scratch.clone())
+            eng.rank_ex(ql, side, R, R + n_mine, query_table=qtab, precision=precision, true_score=ts,
+                        compute_true=True)
             if self.world > 1:
                 self.dist.all_reduce(ts)          # exactly one owner wrote each entry, others hold 0
-            raw = torch.zeros(Q, dtype=torch.int32, device=dev)
-            filt = torch.zeros(Q, dtype=torch.int32, device=dev)
-            eng.rank(ql.to(torch.int32), side, R, R + n_mine, fo, fi, true_score=ts,
-                     compute_true=False, raw_before=raw, filt_before=filt)
+            cnt = torch.zeros((2, Q), dtype=torch.int32, device=dev)
+            eng.rank_ex(ql, side, R, R + n_mine, query_table=qtab, filter_off=fo, filter_ids=fi,
+                        precision=precision, true_score=ts, compute_true=False, raw_before=cnt[0],
+                        filt_before=cnt[1])
             if self.world > 1:
-                self.dist.all_reduce(raw)
-                self.dist.all_reduce(filt)
+                self.dist.all_reduce(cnt)
         finally:
             eng.table = None
-        return raw, filt
+        return cnt[0], cnt[1]
 
 
 class PeerMemoryUnavailable(RuntimeError):

@@ -273,6 +273,24 @@ HOLE_API int hole_rank(hole_ctx* ctx, const float* table, int64_t ent_begin, int
               float* true_score_io, int compute_true,
               int32_t* raw_before, int32_t* filt_before, void* stream);
 
+/* hole_rank_ex: as hole_rank, with two extensions used by the candidate-sharded ranking:
+ *   query_table  when non-NULL, the rows of a query's OTHER entity and of its relation are read from this
+ *                table (same row layout) instead of `table`; the query's true-candidate column is then only
+ *                an index into [ent_begin, ent_end) of `table` (it may lie outside: not in this shard);
+ *   raw_before == filt_before == NULL (with compute_true != 0): true scores only, no counting pass.
+ * hole_rank_prepare packs the candidate operand of [ent_begin, ent_end) once; later hole_rank / hole_rank_ex
+ * calls on the same (table, range, precision) reuse it instead of re-packing, until hole_rank_invalidate, a
+ * training call on this context, or a call with another table / range.  The caller must invalidate after
+ * changing the table by any other means. */
+HOLE_API int hole_rank_ex(hole_ctx* ctx, const float* table, int64_t ent_begin, int64_t ent_end,
+                 const float* query_table, const int32_t* queries, int64_t Q, int side, int precision,
+                 const int64_t* filter_off, const int32_t* filter_ids,
+                 float* true_score_io, int compute_true,
+                 int32_t* raw_before, int32_t* filt_before, void* stream);
+HOLE_API int hole_rank_prepare(hole_ctx* ctx, const float* table, int64_t ent_begin, int64_t ent_end,
+                      int precision, void* stream);
+HOLE_API int hole_rank_invalidate(hole_ctx* ctx);
+
 /* Test hook: copy the bf16 operands the last hole_rank call packed (device to device).
  * cand_out [n_pad, K] / query_out [q_pad, K] may be NULL to query the shapes only. */
 HOLE_API int hole_rank_debug_operands(hole_ctx* ctx, void* cand_out, void* query_out,

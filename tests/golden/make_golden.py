@@ -7,7 +7,7 @@
    touch only heapq, numpy, print and FLAGS.infer_threshold).  Inputs are seeded random
    sigma values; they are stored with the outputs so tests need neither the reference
    nor this script.
-2. fb15k_types.json -- the type histogram of diffbot_data/FB15k/entity_metadata.tsv
+2. graphembeddings_b200/fb15k_types.json (package data) -- the type histogram of diffbot_data/FB15k/entity_metadata.tsv
    (815 classes, 372 singletons) used by the synthetic FB15k-shape generator, and
    fb15k_head.tsv files: the first lines of the real triple/metadata files as loader
    fixtures (data, not source).
@@ -130,7 +130,7 @@ def gen_fb15k_fixtures():
             if i < 40 or 1340 <= i < 1400:
                 lines.append(line)
     hist = sorted(types_count.values(), reverse=True)
-    with open(os.path.join(HERE, "fb15k_types.json"), "w") as f:
+    with open(os.path.join(ROOT, "graphembeddings_b200", "fb15k_types.json"), "w") as f:
         json.dump({"source": "diffbot_data/FB15k/entity_metadata.tsv col 4",
                    "n_relation_rows": n_rel, "entity_type_histogram": hist}, f)
     print("fb15k_types.json:", n_rel, "relations,", len(hist), "types,", sum(hist), "entities,",

@@ -40,6 +40,20 @@ def test_train_checkpoint_resume_infer(tmp_path):
     for name in ("model.ckpt.index", "model.ckpt.data-00000-of-00001", "checkpoint",
                  "projector_config.pbtxt", "summaries.tsv"):
         assert os.path.exists(os.path.join(out, name)), name
+    ev = [f for f in os.listdir(out) if f.startswith("events.out.tfevents.")]
+    assert len(ev) == 1
+    from graphembeddings_b200 import tf_events
+    recs = tf_events.read_events(os.path.join(out, ev[0]))              # (both CRCs of every record checked)
+    tags = {t for e in recs for t in list(e["scalars"]) + list(e["histograms"])}
+    for want in ("validation/summaries/mean", "validation/positive/eval/summaries/stddev_1",
+                 "validation/corrupt/eval/summaries/histogram", "batch/eval/summaries/max",
+                 "batch/learn/learning_rate"):
+        assert want in tags, (want, sorted(tags)[:5])
+    assert recs[0]["file_version"] == "brain.Event:2" and len(recs) >= 3
+    rows = [dict(kv.split("=") for kv in line.split("\t")) for line in open(os.path.join(out, "summaries.tsv"))]
+    # the whole validation file is scored at every validation point (holE.py:350 TODO)
+    assert abs(recs[1]["histograms"]["validation/summaries/histogram"]["num"] - 600) < 0.5
+    assert abs(recs[1]["scalars"]["validation/summaries/mean"] - float(rows[0]["valid_loss_mean"])) < 1e-6
     b = tf_bundle.load_bundle(os.path.join(out, "model.ckpt"))
     assert b["embeddings"].shape == (kg.n_rows, 64) and np.isfinite(b["embeddings"]).all()
     # refuses to clobber an existing output_dir (holE.py:254-255) ...

@@ -111,3 +111,68 @@ def test_native_triple_parser_matches_numpy(tmp_path, golden_dir):
     neg.write_text("1\t-2\t3\n")
     with pytest.raises(ValueError):
         D.load_triples(str(neg))
+
+
+def test_event_file_round_trip_and_tensorboard_can_read_it(tmp_path):
+    """The events file of --output_dir (holE.py:317, 353): TFRecord framing with masked CRC32C, Event /
+    Summary protos encoded by hand -- parsed back by our reader and by TensorBoard's own proto classes."""
+    from graphembeddings_b200 import tf_events as T
+    rng = np.random.default_rng(0)
+    vals = rng.uniform(0.27, 0.73, 1000)
+    w = T.EventFileWriter(str(tmp_path))
+    sc, hi = T.summarize_tags("validation/positive/eval", vals)          # holE.py:237-246
+    sc["batch/learn/learning_rate"] = 0.1
+    w.add_summary(7, sc, hi)
+    w.add_summary(123456789012, {"x": -1.5})
+    w.close()
+    ev = T.read_events(w.path)
+    assert [e["step"] for e in ev] == [0, 7, 123456789012] and ev[0]["file_version"] == "brain.Event:2"
+    assert abs(ev[1]["scalars"]["validation/positive/eval/summaries/mean"] - vals.mean()) < 1e-6
+    assert abs(ev[1]["scalars"]["validation/positive/eval/summaries/stddev_1"] - vals.std()) < 1e-6
+    assert ev[2]["scalars"] == {"x": -1.5}
+    h = ev[1]["histograms"]["validation/positive/eval/summaries/histogram"]
+    assert h["num"] == 1000 and h["min"] == vals.min() and h["max"] == vals.max()
+    assert abs(h["sum"] - vals.sum()) < 1e-9 and h["bucket"].sum() == 1000
+    assert len(h["bucket"]) == len(h["bucket_limit"]) and np.all(np.diff(h["bucket_limit"]) > 0)
+    # every value falls in the bucket whose limit is the first one >= value
+    assert h["bucket_limit"][-1] >= vals.max() and h["bucket_limit"][0] >= vals.min()
+    event_pb2 = pytest.importorskip("tensorboard.compat.proto.event_pb2")
+    import struct
+    buf = open(w.path, "rb").read()
+    pos, n_ok = 0, 0
+    while pos < len(buf):
+        (n,) = struct.unpack_from("<Q", buf, pos)
+        e = event_pb2.Event()
+        e.ParseFromString(buf[pos + 12:pos + 12 + n])
+        if n_ok == 1:
+            got = {v.tag: v.simple_value for v in e.summary.value if v.HasField("simple_value")}
+            assert abs(got["batch/learn/learning_rate"] - 0.1) < 1e-7 and e.step == 7
+            hp = [v for v in e.summary.value if v.HasField("histo")][0].histo
+            assert hp.num == 1000 and len(hp.bucket) == len(h["bucket"])
+        pos += 16 + n
+        n_ok += 1
+    assert n_ok == 3
+    # a flipped byte is caught by the record CRC
+    bad = bytearray(buf)
+    bad[40] ^= 1
+    p2 = tmp_path / "bad"
+    p2.write_bytes(bytes(bad))
+    with pytest.raises(ValueError):
+        T.read_events(str(p2))
+
+
+def test_rows_in_and_id_checks():
+    known = np.array([[1, 2, 0], [1, 3, 0], [4, 2, 1], [1, 2, 0]], dtype=np.int32)
+    q = np.array([[1, 2, 0], [1, 2, 1], [4, 2, 1], [9, 9, 0]], dtype=np.int32)
+    assert D.rows_in(q, known).tolist() == [True, False, True, False]
+    assert D.rows_in(q, np.zeros((0, 3), np.int32)).tolist() == [False] * 4
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 50, size=(300, 3)).astype(np.int32)
+    b = rng.integers(0, 50, size=(5000, 3)).astype(np.int32)
+    want = [tuple(x) in set(map(tuple, b.tolist())) for x in a.tolist()]
+    assert D.rows_in(a, b).tolist() == want
+    D.check_triple_ids(np.array([[5, 6, 1]]), 7, 2)
+    for bad in ([[5, 7, 1]], [[-1, 6, 1]], [[5, 6, 2]], [[5, 6, 9]]):
+        with pytest.raises(ValueError):
+            D.check_triple_ids(np.array(bad), 7, 2)
+    D.check_triple_ids(np.zeros((0, 3), np.int32), 7, 2)               # an empty file is fine
