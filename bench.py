@@ -47,7 +47,7 @@ def workload_desc(batch):
 MARGIN, LR0 = 0.2, 0.1
 #: dram__bytes_read.sum + dram__bytes_write.sum per step (K1 + K3) from the `ncu --set full`
 #: captures under profiles/ for (batch, dim); other configurations report null
-NCU_TRAFFIC = {(32768, 256): 160.5e6}   # profiles/r01_k1_raw.csv (146.1 MB) + r01_k3_raw.csv (14.4 MB)
+NCU_TRAFFIC = {(32768, 256): 158.4e6}   # profiles/r02_k1_raw.csv (98.5 + 45.5 MB) + r01_k3_raw.csv (14.4 MB)
 
 
 def peaks():
@@ -217,6 +217,102 @@ def run_reference(args):
     }))
 
 
+def timed_train(eng, dev_tri, B, K, W, batch_count, first_step=0):
+    """(triples/s, ms per step) of one hole_train_steps call of K steps after W warm-up steps."""
+    import torch
+    eng.train_steps(dev_tri[: W * B], B, 1, first_step, MARGIN, lr_schedule(W, first_step, batch_count))
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    eng.train_steps(dev_tri[W * B:(W + K) * B], B, 1, first_step + W, MARGIN, lr_schedule(K, first_step + W, batch_count))
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    return K * B / (ms * 1e-3), ms / K
+
+
+def coverage_records(args, eng1, kg1, dev_tri1, peak):
+    """The other shapes north_star names, measured beside the headline with the same timer (one
+    hole_train_steps call of K steps, CUDA events): BASELINE configs[0] (FB15k shape, d=150 -- the 9.8 MB
+    table is L2-resident, so its "fraction of the HBM roofline" is an algorithmic-bytes rate that can
+    exceed 1), the script's default B=512 (launch-latency bound), and the trained-scale / Zipf-entity
+    variants of configs[1] (clip backward and deep combine trees inside the timed region)."""
+    import torch
+    from graphembeddings_b200 import data as D
+    from graphembeddings_b200.engine import HoleEngine
+    K, W = args.steps, args.warmup
+    out = {}
+
+    def record(name, eng, kg, tri, B, note):
+        v, ms = timed_train(eng, tri, B, K, W, max(16, kg.triples.shape[0] // B), first_step=1000)
+        out[name] = {"workload": note, "batch": B, "value": v, "unit": "triples/s", "ms_per_step": ms, "steps": K,
+                     "frac_of_hbm_roofline": v * (32 * kg.dim + 20) / 1e9 / peak}
+
+    # configs[1] at the drop-in default batch size (holE.py:602)
+    record("diffbot_d256_B512", eng1, kg1, dev_tri1, 512,
+           "configs[1] table, B=512 (holE.py's default batch size): launch-latency bound")
+    for tag, kw, note in (("trained_scale", dict(trained_scale=True), "row norms ~U(0.5,1.5): every clip-backward branch runs"),
+                          ("zipf_entities", dict(zipf_entities=True), "Zipf(1) entities: hot rows with thousands of uses per step")):
+        kg = D.make_config(WORKLOAD, n_triples=(K + W) * args.batch, **kw)
+        off, ids = D.build_type_csr(kg.type_of)
+        eng = HoleEngine(kg.n_rows, kg.dim).set_embeddings(kg.E).set_types(kg.type_of, off, ids)
+        eng.set_relation_count(kg.n_relations)
+        record("diffbot_d256_" + tag, eng, kg, torch.from_numpy(kg.triples).cuda(), args.batch,
+               f"configs[1] shape, B={args.batch}, {note}")
+        eng.close()
+        del eng, kg
+    for tag, kw in (("uniform", {}), ("zipf", dict(zipf_entities=True))):
+        kg = D.make_config("fb15k_d150", n_triples=max((K + W) * args.batch, 483142), **kw)
+        off, ids = D.build_type_csr(kg.type_of)
+        eng = HoleEngine(kg.n_rows, kg.dim).set_embeddings(kg.E).set_types(kg.type_of, off, ids)
+        eng.set_relation_count(kg.n_relations)
+        tri = torch.from_numpy(kg.triples).cuda()
+        record(f"fb15k_d150_{tag}_B{args.batch}", eng, kg, tri, args.batch,
+               f"BASELINE.json configs[0]: FB15k shape (16,296 x 150 table, L2-resident), {tag} entities, B={args.batch}")
+        if tag == "uniform":
+            record("fb15k_d150_uniform_B512", eng, kg, tri, 512,
+                   "BASELINE.json configs[0]: FB15k shape, B=512 (holE.py's default batch size)")
+        eng.close()
+    return out
+
+
+def config4_single_gpu(args, peak):
+    """BASELINE.json configs[4] (20 M entities x d=512 = 41 GB) on ONE GPU: the N=1 point of that config's
+    scaling curve (the sharded runs report it at N > 1).  Table generated on the device."""
+    import torch
+    from graphembeddings_b200 import data as D
+    from graphembeddings_b200.engine import HoleEngine
+    cfg = D.CONFIGS["sharded_d512"]
+    R, n_ent, dim, n_types = cfg["n_relations"], cfg["n_entities"], cfg["dim"], cfg["n_types"]
+    B, K, W = args.batch, min(args.steps, 20), 3
+    rng = np.random.default_rng(cfg["seed"])
+    p = np.full(n_types, (1.0 - cfg["dominant_type_frac"]) / (n_types - 1))
+    p[0] = cfg["dominant_type_frac"]
+    type_of = np.concatenate([np.zeros(R, np.int32), 1 + rng.choice(n_types, size=n_ent, p=p).astype(np.int32)])
+    off, ids = D.build_type_csr(type_of)
+    eng = HoleEngine(R + n_ent, dim).set_types(type_of, off, ids)
+    eng.set_relation_count(R)
+    gen = torch.Generator(device=eng.device)
+    gen.manual_seed(cfg["seed"] + 1)
+    eng.table = torch.empty((R + n_ent, eng.row_stride), dtype=torch.float32, device=eng.device)
+    eng.table.normal_(0.0, 1.0, generator=gen).clamp_(-2.0, 2.0).mul_(D.xavier_stddev(R + n_ent, dim))
+    n = (K + W) * B
+    h = torch.randint(R, R + n_ent, (n,), generator=gen, device=eng.device, dtype=torch.int32)
+    t = torch.randint(R, R + n_ent, (n,), generator=gen, device=eng.device, dtype=torch.int32)
+    w = 1.0 / torch.arange(1, R + 1, device=eng.device, dtype=torch.float64)
+    r = torch.multinomial(w / w.sum(), n, replacement=True, generator=gen).to(torch.int32)
+    tri = torch.stack([h, t, r], dim=1).contiguous()
+    v, ms = timed_train(eng, tri, B, K, W, 500_000_000 // B)
+    out = {"workload": f"sharded_d512: BASELINE.json configs[4], HolE d=512, {n_ent:,} entities + {R} relations "
+                       "(41.0 GB fp32 table) on one GPU, uniform entities, Zipf relations",
+           "value": v, "unit": "triples/s", "ms_per_step": ms, "batch": B, "steps": K,
+           "frac_of_hbm_roofline": v * (32 * dim + 20) / 1e9 / peak}
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -304,7 +400,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((B, kg.dim)), "peak_source": peak_src,
-                     "kernel": "hole_train_fwd_bwd_kernel + hole_apply_kernel (one step)",
+                     "kernel": "hole_k1_kernel + hole_apply_kernel (one step)",
                      "k1_us": k1_ms * 1e3 / max(n_prof, 1), "k3_us": k3_ms * 1e3 / max(n_prof, 1),
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "whole_step_frac": value * (32 * kg.dim + 20) / 1e9 / peak},
@@ -312,6 +408,11 @@ def run_ours(args):
                          "sample": f"{cpu_steps} steps of B={B} ({cpu_dt:.1f} s) of the same workload, "
                                    "oracle/hole_ref.c (C/OpenMP)"},
     }
+    if not args.no_coverage:
+        try:
+            out["coverage"] = coverage_records(args, eng, kg, dev_tri, peak)
+        except Exception as exc:      # reported beside the headline, never instead of it
+            out["coverage"] = {"error": repr(exc)}
     ranking = None
     if not args.no_ranking:
         try:
@@ -321,6 +422,14 @@ def run_ours(args):
             ranking = {"error": repr(exc)}
     if ranking is not None:
         out["ranking"] = ranking
+    if not args.no_config4:
+        eng.close()
+        del eng, dev_tri
+        torch.cuda.empty_cache()
+        try:
+            out["config4"] = config4_single_gpu(args, peak)
+        except Exception as exc:
+            out["config4"] = {"error": repr(exc)}
     print(json.dumps(out))
 
 
@@ -333,7 +442,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32768)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-ranking", action="store_true")
-    ap.add_argument("--no-config4", action="store_true", help="N > 1: skip the 20M-entity d=512 sub-record")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 20M-entity d=512 sub-record")
+    ap.add_argument("--no-coverage", action="store_true", help="N = 1: skip the configs[0] / B=512 / variant sub-records")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -408,6 +408,9 @@ class P2PRowShardedTrainer(RowShardedTrainer):
             return
         torch.cuda.synchronize()
         self._peers = None
+        if getattr(self, "_rank_eng", None) is not None:
+            self._rank_eng.close()
+            self._rank_eng = None
         if self.world > 1:
             self.dist.barrier()
         self.shard = self.stage = self.relstage = self.inbox = self.meta = self.flags = None
@@ -547,6 +550,11 @@ def parity_case(dist, rank, world, local, dim, Bl, steps, n_ent, seed, chunked, 
 # --------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1)
 # --------------------------------------------------------------------------------------
+#: measured peer-copy bandwidth per direction on this pool's B200s (B200_PROFILING.md; nominal 900 GB/s)
+NVLINK_PEAK = 770.0
+NVLINK_PEAK_SRC = "measured peer copy, 770 GB/s per direction (B200_PROFILING.md; nominal NVLink 5: 900)"
+
+
 def _nvlink_bytes_per_dir(B, world, dim_stride):
     """Per GPU and direction, one step: rows gathered from remote owners + deltas received as an owner
     (in), rows served + deltas sent (out): 2 * 3B * (G-1)/G rows of 4*stride bytes (k = 4)."""
@@ -622,8 +630,8 @@ def bench_config4(args, dist, rank, world, local_rank, steps, warmup):
                        "uniform entities, Zipf relations, Xavier-scale rows generated on the device",
            "value": value, "unit": "triples/s", "ms_per_step": ms / steps, "batch_per_gpu": Bl, "steps": steps,
            "shard_gb_per_gpu": float(tr.shard.numel() * 4 / 1e9), "host_enqueue_us_per_step": host_ms / steps * 1e3,
-           "roofline": {"bound": "nvlink", "achieved": nv, "peak": 900.0, "unit": "GB/s per direction per GPU",
-                        "frac": nv / 900.0, "peak_source": "nominal NVLink 5 (18 links x 50 GB/s per direction)",
+           "roofline": {"bound": "nvlink", "achieved": nv, "peak": NVLINK_PEAK, "unit": "GB/s per direction per GPU",
+                        "frac": nv / NVLINK_PEAK, "peak_source": NVLINK_PEAK_SRC,
                         "bytes_per_dir_per_step": _nvlink_bytes_per_dir(Bl, world, be.width)}}
     tr.close()
     del tr
@@ -674,6 +682,21 @@ def bench(args, dist, rank, world, local_rank):
     if p2p:
         tr.check_barriers()
     value = K * Bl * world / (ms * 1e-3)
+
+    # the same steps when every rank trains the triples whose HEAD it owns (a head-partitioned triple file):
+    # one of the three entity rows of a triple is then local, a third of the NVLink traffic disappears
+    head_local = None
+    if p2p:
+        loc = dev_tri.clone()
+        n_mine = tr.end - tr.begin
+        loc[:, :, 0] = tr.begin + (loc[:, :, 0] - kg.n_relations) % n_mine
+        tr.train_steps(loc[:W].view(-1, 3), Bl, 1, 2 * (K + W), B_.MARGIN, lrs[2 * (K + W):])
+        ms_hl, _ = _timed_device(dist, lambda: tr.train_steps(loc[W:].view(-1, 3), Bl, 1, 2 * (K + W) + W, B_.MARGIN,
+                                                               lrs[2 * (K + W) + W:]))
+        tr.check_barriers()
+        head_local = {"workload": "same table and batch, each rank's triples have heads it owns (head-partitioned triple file)",
+                      "value": K * Bl * world / (ms_hl * 1e-3), "unit": "triples/s", "ms_per_step": ms_hl / K}
+        del loc
 
     # end to end: pinned host triples in, per-step loss sums out, inside the timed region
     if p2p:
@@ -747,14 +770,14 @@ def bench(args, dist, rank, world, local_rank):
             "e2e": {"value": e2e, "unit": "triples/s", "h2d_bytes_per_step": 12 * Bl * world, "d2h_bytes_per_step": 4 * world,
                     "call": "hole_shard_steps_host per rank (pinned host triples in, per-step loss sums out)"},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "nvlink", "achieved": nv, "peak": 900.0, "unit": "GB/s per direction per GPU",
-                         "frac": nv / 900.0, "traffic": None,
-                         "peak_source": "nominal NVLink 5 (18 links x 50 GB/s per direction)",
+            "roofline": {"bound": "nvlink", "achieved": nv, "peak": NVLINK_PEAK, "unit": "GB/s per direction per GPU",
+                         "frac": nv / NVLINK_PEAK, "traffic": None, "peak_source": NVLINK_PEAK_SRC,
                          "kernel": "hole_k1_kernel<.,.,2> (row gather + delta scatter over peer memory) + apply",
                          "bytes_per_dir_per_step": _nvlink_bytes_per_dir(Bl, world, stride),
                          "hbm_frac_per_gpu": value * alg / 1e9 / world / hbm_peak, "hbm_peak_source": src},
             "cpu_baseline": None,
             "parity": par,
+            "head_local": head_local,
             "config4": cfg4,
             "ranking": {"workload": f"rank_diffbot_d256: {nq} queries x 1,200,000 candidates sharded over {world} GPUs (tail side)",
                         "ms": ms_rank, "scores_per_s": nq * 1.2e6 / (ms_rank * 1e-3)},
