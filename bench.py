@@ -362,7 +362,8 @@ def run_ours(args):
     mean_loss = float(sums.mean().item()) / B
 
     # ---- end to end from pinned host triples ("e2e")
-    eng.train_steps_host(host_tri[: W * B], B, 1, W + K, MARGIN, lr_schedule(W, W + K, batch_count))
+    # (warm-up with a call of the timed call's shape: staging and pinned buffers are sized on first use)
+    eng.train_steps_host(host_tri[W * B:(W + K) * B], B, 1, W + K, MARGIN, lr_schedule(K, W + K, batch_count))
     barrier()
     t0 = time.perf_counter()
     hs = eng.train_steps_host(host_tri[W * B:(W + K) * B], B, 1, 2 * W + K, MARGIN,

@@ -84,6 +84,7 @@ struct hole_ctx {
   int k1v2_smem = 0;   // dynamic shared memory of hole_k1_kernel at k1_block threads
   int k1_groups = 0;   // lane groups resident on the whole GPU (sizes T, the triples per group)
   int ramp_first = 0;  // hole_train_steps: steps in the first planned chunk, then x ramp_factor; 0 = no ramp
+  int host_first = 0;  // hole_train_steps_host: steps in a short first chunk; 0 = off (measured slower: r02_e2e_ab.jsonl)
   int ramp_factor = 4; //   (HOLE_PLAN_RAMP=first,factor; measured slower than no ramp, profiles/r02_train_ab.txt:
                        //   a plan's latency is ~120 us of dependent launches whatever its size)
   int row_passes = 1;  // 8-bit radix passes for row keys

@@ -1329,6 +1329,7 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
   if (const char* e = getenv("HOLE_K1")) c->k1_gen = (e[0] == '1' || !strcmp(e, "v1")) ? 1 : 2;
   if (const char* e = getenv("HOLE_K1_BLOCK")) c->k1_block = atoi(e);
   if (c->k1_block != 128 && c->k1_block != 192 && c->k1_block != 256) c->k1_block = 256;
+  if (const char* e = getenv("HOLE_HOST_FIRST")) c->host_first = atoi(e);
   if (const char* e = getenv("HOLE_PLAN_RAMP")) {     // "first,factor"; "0" disables the ramp
     int a = 0, b = 4;
     if (sscanf(e, "%d,%d", &a, &b) >= 1) { c->ramp_first = a; c->ramp_factor = b < 2 ? 2 : b; }
@@ -1990,15 +1991,20 @@ static int64_t plan_chunk(int64_t B) {
 // Chunk sizes of an n_steps call.  The first chunk's plan cannot overlap anything (nothing is
 // training yet), so it is kept short -- ramp_first steps -- and the chunks grow by ramp_factor up to
 // plan_chunk(B): every later plan is hidden behind the previous chunk's steps.
-static std::vector<int64_t> chunk_sizes(const hole_ctx* c, int64_t B, int64_t n_steps) {
+// from_host: HOLE_HOST_FIRST=n starts the host-buffer path with a chunk of n steps (its copy is exposed
+// too); off by default -- measured slower at every n (profiles/r02_e2e_ab.jsonl: a second plan chain costs
+// more than the shorter first copy saves).
+static std::vector<int64_t> chunk_sizes(const hole_ctx* c, int64_t B, int64_t n_steps, bool from_host = false) {
   const int64_t S = plan_chunk(B);
   std::vector<int64_t> v;
-  int64_t cur = c->ramp_first > 0 ? std::min<int64_t>(S, c->ramp_first) : S;
+  int64_t first = c->ramp_first;
+  if (from_host && first <= 0 && c->host_first > 0 && n_steps > 2 * c->host_first) first = c->host_first;
+  int64_t cur = first > 0 ? std::min<int64_t>(S, first) : S;
   for (int64_t left = n_steps; left > 0;) {
     const int64_t n = std::min(cur, left);
     v.push_back(n);
     left -= n;
-    cur = std::min<int64_t>(S, cur * std::max(2, c->ramp_factor));
+    cur = (from_host && c->ramp_first <= 0) ? S : std::min<int64_t>(S, cur * std::max(2, c->ramp_factor));
   }
   return v;
 }
@@ -2090,16 +2096,18 @@ extern "C" int hole_train_steps_host(hole_ctx* c, float* table, const int32_t* t
     }
     c->cap_stage = stage_elems;
   }
-  if (n_steps > c->cap_pinned) {
+  if (n_steps > c->cap_pinned) {     // (sized generously: a page-locked allocation costs ~a step)
     if (c->loss_sum_pinned) cudaFreeHost(c->loss_sum_pinned);
     c->loss_sum_pinned = nullptr;
-    HOLE_CUDA_TRY(cudaMallocHost((void**)&c->loss_sum_pinned, n_steps * sizeof(float)));
-    c->cap_pinned = n_steps;
+    c->cap_pinned = 0;
+    const int64_t want = std::max<int64_t>(n_steps, 16384);
+    HOLE_CUDA_TRY(cudaMallocHost((void**)&c->loss_sum_pinned, want * sizeof(float)));
+    c->cap_pinned = want;
   }
   cudaStream_t st = (cudaStream_t)stream;
   HOLE_CUDA_TRY(cudaEventRecord(c->ev_entry, st));
   HOLE_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0));
-  const std::vector<int64_t> sizes = chunk_sizes(c, B, n_steps);
+  const std::vector<int64_t> sizes = chunk_sizes(c, B, n_steps, true);
   const int64_t nchunks = (int64_t)sizes.size();
   std::vector<int64_t> starts(nchunks, 0);
   for (int64_t ci = 1; ci < nchunks; ++ci) starts[ci] = starts[ci - 1] + sizes[ci - 1];
