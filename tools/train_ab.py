@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 PKG = os.path.join(ROOT, "graphembeddings_b200")
 
-VARIANTS = [  # (name, env)
+VARIANTS = [  # (name, env); earlier rounds of variants: profiles/r02_train_ab_README.md
     ("K1 v2 (default)", {}),
     ("K1 v1 (round 1 kernel)", {"HOLE_K1": "v1"}),
     ("K1 v2, trained-scale table (clips fire)", {"AB_TRAINED": "1"}),
