@@ -79,7 +79,6 @@ struct hole_ctx {
   int key_bits = 0;    // bits needed for a row id
   int k1_smem = 0;     // dynamic shared memory of the first-generation K1 body (--log_loss passes)
   bool k1_ready = false;   // kernel attributes set (lazily, on the first training call)
-  int k1_gen = 2;      // 2 = hole_k1_kernel (bulk-copy pipeline); 1 = first-generation kernel (A/B)
   int k1_block = 256;  // threads per K1 block
   int k1v2_smem = 0;   // dynamic shared memory of hole_k1_kernel at k1_block threads
   int k1_groups = 0;   // lane groups resident on the whole GPU (sizes T, the triples per group)

@@ -797,24 +797,11 @@ hole_train_fwd_bwd_body(float* __restrict__ E, const int32_t* __restrict__ tri,
   flush_relation();
 }
 
-template <int GS, int V>
-__global__ void __launch_bounds__(256)
-hole_train_fwd_bwd_kernel(float* __restrict__ E, const int32_t* __restrict__ tri,
-                          const int32_t* __restrict__ neg, const int32_t* __restrict__ perm,
-                          const uint32_t* __restrict__ gslot, int side, int B, int T, int nvec,
-                          int stride, float margin, float lr, float* __restrict__ G,
-                          float* __restrict__ loss, float* __restrict__ sigma, float* __restrict__ Dtab,
-                          int flags) {
-  // specialise on the corruption side and on "every lane owns valid float4s" (nvec == GS*V)
-  const bool full = (nvec == GS * V);
 #define HOLE_K1_BODY(SIDE, FULL_, LL) \
   hole_train_fwd_bwd_body<GS, V, SIDE, FULL_, LL>(E, tri, neg, perm, gslot, B, T, nvec, stride, margin, lr, G, loss, sigma, Dtab, flags)
-  if (side) { if (full) HOLE_K1_BODY(1, true, false); else HOLE_K1_BODY(1, false, false); }
-  else      { if (full) HOLE_K1_BODY(0, true, false); else HOLE_K1_BODY(0, false, false); }
-}
 
-// the --log_loss passes: a kernel of their own (generic-width body), so that the hinge kernel's
-// register allocation is not the maximum over both
+// the --log_loss passes run the first-generation body (cp.async landing buffers, rows clipped in
+// registers); the hinge step runs hole_k1_kernel (hole_k1.cuh)
 template <int GS, int V>
 __global__ void __launch_bounds__(256)
 hole_train_fwd_bwd_ll_kernel(float* __restrict__ E, const int32_t* __restrict__ tri,
@@ -1326,7 +1313,6 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
   // lane group.  Kernel attributes are set lazily by k1_prepare(): scoring / ranking contexts never
   // need them.
   c->k1_smem = (256 / c->gs) * (K1_STAGES * 3 + 1) * c->row_stride * (int)sizeof(float);
-  if (const char* e = getenv("HOLE_K1")) c->k1_gen = (e[0] == '1' || !strcmp(e, "v1")) ? 1 : 2;
   if (const char* e = getenv("HOLE_K1_BLOCK")) c->k1_block = atoi(e);
   if (c->k1_block != 128 && c->k1_block != 192 && c->k1_block != 256) c->k1_block = 256;
   if (const char* e = getenv("HOLE_HOST_FIRST")) c->host_first = atoi(e);
@@ -1557,7 +1543,7 @@ static int k1_prepare(hole_ctx* c) {
   }
   HOLE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1_fn<0>(c), c->k1_block, c->k1v2_smem));
   c->k1_groups = c->sm_count * std::max(nb, 1) * (c->k1_block / c->gs);
-  if (c->k1_smem <= limit) {       // first-generation body (--log_loss passes; HOLE_K1=v1)
+  if (c->k1_smem <= limit) {       // first-generation body (--log_loss passes)
     cudaError_t ea = cudaSuccess;
 #define HOLE_K1_ATTR(KERNEL)                                                                                   \
     if (c->gs == 8) ea = cudaFuncSetAttribute(KERNEL<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);          \
@@ -1565,15 +1551,10 @@ static int k1_prepare(hole_ctx* c) {
     else if (c->v == 1) ea = cudaFuncSetAttribute(KERNEL<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);     \
     else if (c->v == 2) ea = cudaFuncSetAttribute(KERNEL<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);     \
     else ea = cudaFuncSetAttribute(KERNEL<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->k1_smem);
-    HOLE_K1_ATTR(hole_train_fwd_bwd_kernel)
-    HOLE_CUDA_TRY(ea);
     HOLE_K1_ATTR(hole_train_fwd_bwd_ll_kernel)
     HOLE_CUDA_TRY(ea);
 #undef HOLE_K1_ATTR
-  } else if (c->k1_gen == 1) {
-    c->k1_gen = 2;
   }
-  if (c->k1_gen == 1) c->k1_groups = c->sm_count * 2 * (256 / c->gs);   // two resident 256-thread blocks per SM
   c->k1_ready = true;
   return HOLE_OK;
 }
@@ -1670,7 +1651,7 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
     k3s.cuts = shard->cuts; k3s.R = shard->R; k3s.me = shard->me; k3s.world = shard->world;
     k3s.cap = shard->cap; k3s.stage = shard->stage;
   }
-  if ((flags & 3) == 0 && c->k1_gen == 2) {
+  if ((flags & 3) == 0) {
     hole_k1_args ka = {};
     ka.E = table; ka.tri = shard ? shard_tri : pos; ka.neg = shard ? shard_neg : neg;
     ka.perm = pl.perm + (size_t)slot * B; ka.gslot = pl.gslot + off;
@@ -1680,16 +1661,11 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
     const int dm = shard ? 2 : (delta_out ? 1 : 0);
     int rc = k1_launch(c, dm, ka, shard ? *shard : no_shard, st, k1_follows_k3 && !c->profile);
     if (rc) return rc;
-  } else if ((flags & 3) != 0) {
-    HOLE_DISPATCH_SMEM(c, hole_train_fwd_bwd_ll_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
-                       c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
-                c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out, flags);
-  } else if (k1_follows_k3 && !c->profile) {
-    HOLE_DISPATCH_PDL(c, hole_train_fwd_bwd_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
-                      c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
-                c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out, flags);
   } else {
-    HOLE_DISPATCH_SMEM(c, hole_train_fwd_bwd_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
+    if (c->k1_smem > 227 * 1024)
+      return hole_set_error(HOLE_ERR_UNSUPPORTED, "embedding_dim %d: the --log_loss kernel needs %d bytes of shared memory",
+                            c->dim, c->k1_smem);
+    HOLE_DISPATCH_SMEM(c, hole_train_fwd_bwd_ll_kernel, grid_for_groups((B + pl.T - 1) / pl.T, c->gs), 256,
                        c->k1_smem, st, table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->nvec,
                 c->row_stride, margin, lr, c->G, loss_out, sigma_out, delta_out, flags);
   }

@@ -2,13 +2,16 @@
 
 TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py for who may import this.
 
-PARITY UNPINNED for the floating-point arithmetic: the reference computes it inside
-TensorFlow 1.2 (GraphDef producer 22), which is neither vendored under /root/reference
-nor installable offline, and the reference ships no tests, golden vectors or
-known-answer values for this path.  Every function
-below cites the holE.py lines it restates; TF-internal conventions (clip formula,
-gradient seed, tie conventions, slice order) follow SURVEY.md App. B, which was
-recovered from the archived GraphDefs.  What *is* pinned:
+PARITY PINNED MODULO A TENSORFLOW SHIM.  The reference computes this arithmetic inside TensorFlow 1.2
+(GraphDef producer 22), which is neither vendored under /root/reference nor installable offline, and it
+ships no tests or golden vectors for this path.  The pin is
+tests/golden/tfshim_step.npz: the outputs of /root/reference/holE.py's OWN corrupt_batch / get_embedding /
+evaluate_triples / evaluate_batch / GradientDescentOptimizer.minimize source, executed unmodified on the
+torch-backed `tensorflow` stand-in tests/golden/tfshim.py (which states the TF-internal conventions of
+SURVEY.md App. B once: clip formula and axes, Minimum/Maximum tie routing, ones gradient seed, slice
+order, sequential ScatterSub, fp32 inverse_time_decay).  tests/test_tfshim_golden.py holds sgd_step and
+logloss_step to 1e-12 (fp64) and 5e-7 (fp32) against it.  Every function below cites the holE.py lines
+it restates.  Also pinned:
   * the ranking / metric routines, against the reference's own pure-Python
     eval_link_prediction / score_mrr (holE.py:427-490) executed here with TensorFlow
     stubbed out -- see tests/golden/make_golden.py and tests/golden/ranking_ref.json;

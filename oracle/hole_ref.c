@@ -2,8 +2,10 @@
  * (TEST INFRASTRUCTURE ONLY: the CPU baseline bench.py times, and a second opinion for
  * the NumPy oracle; never linked into the product).
  *
- * PARITY UNPINNED for the floating-point arithmetic (TensorFlow 1.2 is not installable
- * here and the reference ships no golden vectors); it is checked against
+ * PARITY PINNED MODULO A TENSORFLOW SHIM: TensorFlow 1.2 is not installable here and the
+ * reference ships no golden vectors, so the pin is tests/golden/tfshim_step.npz -- the outputs of
+ * holE.py's own evaluate_batch / minimize source executed on tests/golden/tfshim.py -- which this
+ * port matches to 5e-6 (tests/test_tfshim_golden.py); it is also checked against
  * oracle/hole_oracle.py in tests/test_oracle_c.py.  Cites: get_embedding holE.py:161-168,
  * score holE.py:191-192, sigmoid holE.py:198, hinge holE.py:231, SGD holE.py:296 with the
  * TF conventions of SURVEY.md App. B (clip formula, sum-of-losses seed, >= hinge/clip

@@ -14,11 +14,10 @@ sys.path.insert(0, ROOT)
 PKG = os.path.join(ROOT, "graphembeddings_b200")
 
 VARIANTS = [  # (name, env); earlier rounds of variants: profiles/r02_train_ab_README.md
-    ("K1 v2 (default)", {}),
-    ("K1 v1 (round 1 kernel)", {"HOLE_K1": "v1"}),
-    ("K1 v2, trained-scale table (clips fire)", {"AB_TRAINED": "1"}),
-    ("K1 v2, B=512", {"AB_BATCH": "512"}),
-    ("K1 v2, B=8192", {"AB_BATCH": "8192"}),
+    ("default", {}),
+    ("trained-scale table (clips fire)", {"AB_TRAINED": "1"}),
+    ("B=512", {"AB_BATCH": "512"}),
+    ("B=8192", {"AB_BATCH": "8192"}),
 ]
 
 
