@@ -44,12 +44,17 @@ struct hole_shard_state;   // hole_shard.cuh
 
 // Update plan of a chunk of S steps (integer-only; built ahead of the steps that use it).
 struct hole_plan {
-  uint32_t* keysA = nullptr;     // [S][4B] sort ping (unsorted row keys are written here)
-  uint32_t* keysB = nullptr;     // [S][4B] sort pong
+  uint32_t* keysA = nullptr;     // [S][4B] the step's row keys by position (kept: --log_loss reads them)
+  uint32_t* keysB = nullptr;     // [S][4B] keys of the duplicated uses, compacted: sort ping
+  uint32_t* keysC = nullptr;     // [S][4B] sort pong
+  uint32_t* seen = nullptr;      // [S][n_rows/32] bitmap: row used by the step
+  uint32_t* dup = nullptr;       // [S][n_rows/32] bitmap: row used more than once
+  int* blkcnt = nullptr;         // [S][tiles+1] duplicated uses per tile -> offsets; total last
+  int* mdup = nullptr;           // [S] duplicated uses of the step
   uint32_t* valsA = nullptr;
   uint32_t* valsB = nullptr;
   uint32_t* ghist = nullptr;     // [S][256][tiles] radix histograms
-  uint32_t* skey = nullptr;      // sorted keys (points into keysA or keysB)
+  uint32_t* skey = nullptr;      // sorted keys of the duplicated uses (points into keysB or keysC)
   uint32_t* spos = nullptr;      // sorted original positions (points into valsA or valsB)
   uint32_t* gslot = nullptr;     // [S][4B] per ORIGINAL position: G row of that use, or UNIQUE
   uint4* heads = nullptr;        // [S][heads_cap] leaves of the combine trees {j, seg start, n, row}

@@ -211,7 +211,8 @@ __global__ void hole_plan_keys_kernel(const int32_t* __restrict__ triples, int64
                                       const int64_t* __restrict__ csr_off,
                                       const int32_t* __restrict__ csr_ids, uint64_t seed,
                                       uint64_t first_step, const int32_t* __restrict__ neg_in,
-                                      int32_t* __restrict__ neg_out, uint32_t* __restrict__ keys) {
+                                      int32_t* __restrict__ neg_out, uint32_t* __restrict__ keys,
+                                      uint32_t* __restrict__ seen, uint32_t* __restrict__ dup, int W) {
   const int s = blockIdx.y;
   const uint64_t step = first_step + (uint64_t)s;
   const int side = hole_side_coin(seed, step);
@@ -237,6 +238,113 @@ __global__ void hole_plan_keys_kernel(const int32_t* __restrict__ triples, int64
     k[B + i] = (uint32_t)t;
     k[2 * B + i] = (uint32_t)h;
     k[3 * B + i] = (uint32_t)n;
+    // which rows the step uses more than once: a row's second (third, ...) use finds its `seen` bit set
+    uint32_t* sn = seen + (size_t)s * W;
+    uint32_t* dp = dup + (size_t)s * W;
+    auto mark = [&](uint32_t row) {
+      const uint32_t m = 1u << (row & 31u);
+      if (atomicOr(sn + (row >> 5), m) & m) atomicOr(dp + (row >> 5), m);
+    };
+    if (run_head) mark((uint32_t)r);
+    mark((uint32_t)t);
+    mark((uint32_t)h);
+    mark((uint32_t)n);
+  }
+}
+
+// Uses of rows that occur once in the step need no ordering at all (K1 updates them in place): only the
+// uses of duplicated rows -- typically ~10 % of the 4B -- go through the sort.  Three small kernels compact
+// them stably (in position order): flag + per-block count, per-step scan of the block counts, write.
+constexpr int DP_THREADS = 256;
+constexpr int DP_ITEMS = 4;
+constexpr int DP_TILE = DP_THREADS * DP_ITEMS;
+
+__device__ __forceinline__ bool plan_is_dup(const uint32_t* __restrict__ dp, uint32_t key) {
+  return key != HOLE_KEY_ABSENT && ((dp[key >> 5] >> (key & 31u)) & 1u);
+}
+
+// gslot[u] = UNIQUE for uses of rows that occur once; blkcnt[s][blk] = duplicated uses in the block's tile
+__global__ void __launch_bounds__(DP_THREADS)
+hole_plan_dupflag_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ dup, int M, int W,
+                         uint32_t* __restrict__ gslot, int* __restrict__ blkcnt) {
+  const int s = blockIdx.y, nblk = gridDim.x;
+  const uint32_t* k = keys + (size_t)s * M;
+  const uint32_t* dp = dup + (size_t)s * W;
+  int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < DP_ITEMS; ++i) {
+    const int u = blockIdx.x * DP_TILE + i * DP_THREADS + threadIdx.x;
+    bool d = false;
+    if (u < M) {
+      const uint32_t key = k[u];
+      d = plan_is_dup(dp, key);
+      if (!d && key != HOLE_KEY_ABSENT) gslot[(size_t)s * M + u] = HOLE_SLOT_UNIQUE;
+    }
+    cnt += __syncthreads_count(d);
+  }
+  if (threadIdx.x == 0) blkcnt[(size_t)s * (nblk + 1) + blockIdx.x] = cnt;
+}
+
+// per step: block counts -> exclusive offsets; the total goes to blkcnt[s][nblk] and mdup[s]
+__global__ void __launch_bounds__(256)
+hole_plan_dupscan_kernel(int* __restrict__ blkcnt, int nblk, int* __restrict__ mdup) {
+  __shared__ int wsum[8];
+  int* c = blkcnt + (size_t)blockIdx.x * (nblk + 1);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int per = (nblk + 255) / 256;
+  int tot = 0;
+  for (int q = tid * per; q < min(nblk, (tid + 1) * per); ++q) tot += c[q];
+  int inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  int base = inc - tot;
+  for (int q = 0; q < w; ++q) base += wsum[q];
+  for (int q = tid * per; q < min(nblk, (tid + 1) * per); ++q) {
+    const int v = c[q];
+    c[q] = base;
+    base += v;
+  }
+  if (tid == 255) { c[nblk] = base; mdup[blockIdx.x] = base; }
+}
+
+// (key, position) of every duplicated use, in position order
+__global__ void __launch_bounds__(DP_THREADS)
+hole_plan_compact_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ dup, int M, int W,
+                         const int* __restrict__ blkcnt, uint32_t* __restrict__ ckey, uint32_t* __restrict__ cval) {
+  __shared__ int wcnt[DP_THREADS / 32];
+  const int s = blockIdx.y, nblk = gridDim.x;
+  const uint32_t* k = keys + (size_t)s * M;
+  const uint32_t* dp = dup + (size_t)s * W;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int base = blkcnt[(size_t)s * (nblk + 1) + blockIdx.x];
+#pragma unroll 1
+  for (int i = 0; i < DP_ITEMS; ++i) {
+    const int u = blockIdx.x * DP_TILE + i * DP_THREADS + threadIdx.x;
+    uint32_t key = HOLE_KEY_ABSENT;
+    if (u < M) key = k[u];
+    const bool d = u < M && plan_is_dup(dp, key);
+    const unsigned bal = __ballot_sync(0xffffffffu, d);
+    __syncthreads();                       // wcnt of the previous iteration is consumed
+    if (lane == 0) wcnt[w] = __popc(bal);
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int q = 0; q < DP_THREADS / 32; ++q) {
+      const int c = wcnt[q];
+      before += (q < w) ? c : 0;
+      all += c;
+    }
+    if (d) {
+      const int dst = base + before + __popc(bal & ((1u << lane) - 1u));
+      ckey[(size_t)s * M + dst] = key;
+      cval[(size_t)s * M + dst] = (uint32_t)u;
+    }
+    base += all;
   }
 }
 
@@ -276,14 +384,15 @@ __device__ __forceinline__ void st_warp_hist(const uint32_t* __restrict__ k, int
 // ghist[(s*256 + digit)*P + p] = number of entries of tile p of step s with that digit
 __global__ void __launch_bounds__(ST_THREADS)
 hole_sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t* __restrict__ ghist, int M, int P,
-                      int shift) {
+                      int shift, const int* __restrict__ mdev) {
   __shared__ uint32_t wh[ST_WARPS][256];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int p = blockIdx.x, s = blockIdx.y;
   for (int i = tid; i < ST_WARPS * 256; i += ST_THREADS) (&wh[0][0])[i] = 0;
   __syncthreads();
-  const uint32_t* k = keys + (size_t)s * M;
-  const int lo = min(M, p * ST_TILE + w * ST_SLICE), hi = min(M, lo + ST_SLICE);
+  const uint32_t* k = keys + (size_t)s * M;               // arrays are M apart, Ms entries of a step are in use
+  const int Ms = mdev ? mdev[s] : M;
+  const int lo = min(Ms, p * ST_TILE + w * ST_SLICE), hi = min(Ms, lo + ST_SLICE);
   st_warp_hist(k, lo, hi, shift, wh[w], lane);
   __syncthreads();
   uint32_t tot = 0;
@@ -321,7 +430,8 @@ hole_sort_scan_kernel(uint32_t* __restrict__ ghist, int P) {
 __global__ void __launch_bounds__(ST_THREADS)
 hole_sort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                          uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                         const uint32_t* __restrict__ ghist, int M, int P, int shift) {
+                         const uint32_t* __restrict__ ghist, int M, int P, int shift,
+                         const int* __restrict__ mdev) {
   __shared__ uint32_t wh[ST_WARPS][256];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int p = blockIdx.x, s = blockIdx.y;
@@ -332,7 +442,9 @@ hole_sort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* _
   const uint32_t* v = vals_in ? vals_in + base : nullptr;
   uint32_t* ko = keys_out + base;
   uint32_t* vo = vals_out + base;
-  const int lo = min(M, p * ST_TILE + w * ST_SLICE), hi = min(M, lo + ST_SLICE);
+  const int Ms = mdev ? mdev[s] : M;
+  if (p * ST_TILE >= Ms) return;             // (block-uniform) nothing of this step in my tile
+  const int lo = min(Ms, p * ST_TILE + w * ST_SLICE), hi = min(Ms, lo + ST_SLICE);
   st_warp_hist(k, lo, hi, shift, wh[w], lane);
   __syncthreads();
   {   // per digit: exclusive scan over the warps of this tile, on top of the global offset
@@ -373,45 +485,55 @@ hole_sort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* _
   }
 }
 
-// Segments of the sorted keys.  gslot[original position] = HOLE_SLOT_UNIQUE if the row occurs
-// exactly once in the step (such rows are updated in place by K1; nobody else reads them
-// during the step), else the sorted index of that use = the row of G its gradient goes to
-// (so K3 reads the gradients of one table row from consecutive G rows).
+// Segments of the sorted duplicated uses.  gslot[original position] = the sorted index of that use = the
+// row of G its gradient goes to (so K3 reads the gradients of one table row from consecutive G rows);
+// uses of rows that occur exactly once were marked HOLE_SLOT_UNIQUE by hole_plan_dupflag_kernel (such
+// rows are updated in place by K1; nobody else reads them during the step).
 // For rows that occur n >= 2 times, every sorted entry that heads a chunk of C occurrences
 // is appended to the step's compact work list heads[] = {sorted index, segment start, n, row}
 // (list order is irrelevant: each entry is an independent leaf of the combine tree).
 __global__ void __launch_bounds__(256)
 hole_plan_segments_kernel(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ spos,
                           uint32_t* __restrict__ gslot, uint4* __restrict__ heads,
-                          int* __restrict__ nheads, int M, int heads_cap) {
+                          int* __restrict__ nheads, int Mcap, const int* __restrict__ mdev, int heads_cap) {
   constexpr int C = HOLE_TREE_C;
-  const size_t base = (size_t)blockIdx.y * M;
+  const size_t base = (size_t)blockIdx.y * Mcap;
   const uint32_t* k = skey + base;
+  const int M = mdev[blockIdx.y];              // the step's duplicated uses, sorted by (row, position)
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
     const uint32_t key = k[j];
-    if (key == HOLE_KEY_ABSENT) continue;      // relation use folded into its run's first triple
     const bool head = (j == 0) || (k[j - 1] != key);
     const bool last = (j == M - 1) || (k[j + 1] != key);
-    gslot[base + spos[base + j]] = (head && last) ? HOLE_SLOT_UNIQUE : (uint32_t)j;
-    if (head && last) continue;
+    gslot[base + spos[base + j]] = (uint32_t)j;
+    if (head && last) continue;                // (cannot happen: every listed row occurs at least twice)
+    // segment [s, e) of this row.  Most duplicated rows are used two or three times: look at the
+    // neighbours first, and only search (binary, over the whole step) when the run is longer than that.
     int s = j;
-    if (!head) {          // lower_bound(key) in [0, j)
-      int lo = 0, hi = j;
-      while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (k[mid] < key) lo = mid + 1; else hi = mid;
+    if (!head) {
+      if (j < 2 || k[j - 2] != key) s = j - 1;
+      else if (j < 3 || k[j - 3] != key) s = j - 2;
+      else {              // lower_bound(key) in [0, j - 3)
+        int lo = 0, hi = j - 3;
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (k[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        s = lo;
       }
-      s = lo;
     }
     if ((j - s) % C != 0) continue;
     int e = j + 1;
-    if (!last) {          // upper_bound(key) in (j, M)
-      int lo = j + 1, hi = M;
-      while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (k[mid] <= key) lo = mid + 1; else hi = mid;
+    if (!last) {
+      if (j + 2 >= M || k[j + 2] != key) e = j + 2;
+      else if (j + 3 >= M || k[j + 3] != key) e = j + 3;
+      else {              // upper_bound(key) in (j + 3, M)
+        int lo = j + 4, hi = M;
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (k[mid] <= key) lo = mid + 1; else hi = mid;
+        }
+        e = lo;
       }
-      e = lo;
     }
     const int slot = atomicAdd(&nheads[blockIdx.y], 1);
     heads[(size_t)blockIdx.y * heads_cap + slot] = make_uint4((uint32_t)j, (uint32_t)s, (uint32_t)(e - s), key);
@@ -1159,17 +1281,21 @@ hole_l2_finish_kernel(const float* __restrict__ partial, int n, float* __restric
   if (threadIdx.x == 0) *out = (float)(0.5 * sm[0]);
 }
 
-// E[row] += D[row]; D[row] = 0  for every distinct row of one pass (first entry of each run of
-// its sorted keys).  A row shared by several passes is applied by the first and adds zero after.
+// E[row] += D[row]; D[row] = 0  for every distinct row of one pass: every use of a row that occurs once,
+// and the first sorted entry of every duplicated row.  A row shared by several passes is applied by the
+// first and adds zero after.
 template <int GS, int V>
 __global__ void __launch_bounds__(256)
-hole_apply_delta_kernel(float* __restrict__ E, float* __restrict__ D, const uint32_t* __restrict__ skey, int M,
+hole_apply_delta_kernel(float* __restrict__ E, float* __restrict__ D, const uint32_t* __restrict__ keys,
+                        const uint32_t* __restrict__ gslot, const uint32_t* __restrict__ skey, int M,
                         int nvec, int stride) {
   const int lane = threadIdx.x % GS;
-  const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
-  if (j >= M) return;
-  const uint32_t key = skey[j];
-  if (key == HOLE_KEY_ABSENT || (j > 0 && skey[j - 1] == key)) return;
+  const int64_t u = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GS;
+  if (u >= M) return;
+  const uint32_t key = keys[u];
+  if (key == HOLE_KEY_ABSENT) return;
+  const uint32_t j = gslot[u];
+  if (j != HOLE_SLOT_UNIQUE && j > 0 && skey[j - 1] == key) return;
   Row<V> x, d, z;
   row_zero(z);
   row_load<GS, V, false>(x, E + (size_t)key * stride, lane, nvec);
@@ -1330,7 +1456,10 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
 }
 
 static void plan_free(hole_plan& p) {
-  cudaFree(p.keysA); cudaFree(p.keysB); cudaFree(p.valsA); cudaFree(p.valsB);
+  cudaFree(p.keysA); cudaFree(p.keysB); cudaFree(p.keysC); cudaFree(p.valsA); cudaFree(p.valsB);
+  cudaFree(p.seen); cudaFree(p.dup); cudaFree(p.blkcnt); cudaFree(p.mdup);
+  p.keysC = p.seen = p.dup = nullptr;
+  p.blkcnt = p.mdup = nullptr;
   cudaFree(p.gslot); cudaFree(p.heads); cudaFree(p.nheads); cudaFree(p.neg); cudaFree(p.ghist); cudaFree(p.perm);
   p.perm = nullptr;
   p.keysA = p.keysB = p.valsA = p.valsB = nullptr;
@@ -1409,8 +1538,15 @@ int hole_ws_reserve(hole_ctx* c, int64_t B, int64_t S) {
   WS_ALLOC(c->loss_sum, (size_t)S * 4);
   for (int k = 0; k < 2; ++k) {
     hole_plan& p = c->plan[k];
-    WS_ALLOC(p.keysA, S * M * 4); WS_ALLOC(p.keysB, S * M * 4);
+    WS_ALLOC(p.keysA, S * M * 4); WS_ALLOC(p.keysB, S * M * 4); WS_ALLOC(p.keysC, S * M * 4);
     WS_ALLOC(p.valsA, S * M * 4); WS_ALLOC(p.valsB, S * M * 4);
+    {
+      const size_t W = (size_t)(c->n_rows + 31) / 32;
+      WS_ALLOC(p.seen, (size_t)S * W * 4);
+      WS_ALLOC(p.dup, (size_t)S * W * 4);
+      WS_ALLOC(p.blkcnt, (size_t)S * ((M + DP_TILE - 1) / DP_TILE + 1) * 4);
+      WS_ALLOC(p.mdup, (size_t)S * 4);
+    }
     WS_ALLOC(p.gslot, S * M * 4);
     WS_ALLOC(p.heads, (size_t)S * (M / 2 + 1) * sizeof(uint4));
     WS_ALLOC(p.nheads, (size_t)S * 4);
@@ -1487,19 +1623,21 @@ extern "C" int hole_score(hole_ctx* c, const float* table, const int32_t* triple
 // Stable LSD radix sort of S independent arrays of M (key, value = original index) pairs.
 // Keys start in kA (destroyed); kB, vA, vB are scratch; the last pass writes the values to
 // v_final when given.  Returns where the sorted keys / values ended up.
+// v_init: the values travelling with the keys of kA live in vA (else value = index).  mdev: per-array
+// element counts on the device (else M); the arrays are M apart either way.
 static int radix_sort(uint32_t* ghist, uint32_t* kA, uint32_t* kB, uint32_t* vA, uint32_t* vB,
                       uint32_t* v_final, int64_t S, int M, int passes, cudaStream_t st,
-                      uint32_t** k_out, uint32_t** v_out) {
+                      uint32_t** k_out, uint32_t** v_out, bool v_init = false, const int* mdev = nullptr) {
   const int P = (M + ST_TILE - 1) / ST_TILE;
-  uint32_t *kin = kA, *vin = nullptr, *kout = kB, *vout = vB;
+  uint32_t *kin = kA, *vin = v_init ? vA : nullptr, *kout = kB, *vout = vB;
   dim3 grid((unsigned)P, (unsigned)S);
   for (int pass = 0; pass < passes; ++pass) {
     if (pass == passes - 1 && v_final != nullptr) vout = v_final;
-    hole_sort_hist_kernel<<<grid, ST_THREADS, 0, st>>>(kin, ghist, M, P, 8 * pass);
+    hole_sort_hist_kernel<<<grid, ST_THREADS, 0, st>>>(kin, ghist, M, P, 8 * pass, mdev);
     HOLE_LAUNCHED();
     hole_sort_scan_kernel<<<(unsigned)S, 256, 0, st>>>(ghist, P);
     HOLE_LAUNCHED();
-    hole_sort_scatter_kernel<<<grid, ST_THREADS, 0, st>>>(kin, vin, kout, vout, ghist, M, P, 8 * pass);
+    hole_sort_scatter_kernel<<<grid, ST_THREADS, 0, st>>>(kin, vin, kout, vout, ghist, M, P, 8 * pass, mdev);
     HOLE_LAUNCHED();
     uint32_t* nk = (kout == kB) ? kA : kB;
     uint32_t* nv = (vout == vB) ? vA : vB;
@@ -1602,19 +1740,31 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
   int rc = radix_sort(pl.ghist, pl.keysA, pl.keysB, pl.valsA, pl.valsB, reinterpret_cast<uint32_t*>(pl.perm),
                       S, (int)B, c->rel_passes, ps, &ko, &vo);
   if (rc) return rc;
-  // 2. corruption + the 4B row keys of every step
+  // 2. corruption + the 4B row keys of every step; rows used more than once are marked in the bitmaps
   pl.T = triples_per_group(c, B);
+  const int W = (int)((c->n_rows + 31) / 32);
+  HOLE_CUDA_TRY(cudaMemsetAsync(pl.seen, 0, (size_t)S * W * 4, ps));
+  HOLE_CUDA_TRY(cudaMemsetAsync(pl.dup, 0, (size_t)S * W * 4, ps));
   hole_plan_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, tstride, pl.T, pl.perm, type_of, csr_off, csr_ids,
-                                              seed, first_step, neg_in, pl.neg, pl.keysA);
+                                              seed, first_step, neg_in, pl.neg, pl.keysA, pl.seen, pl.dup, W);
   HOLE_LAUNCHED();
-  // 3. sort by row, 4. segments
-  rc = radix_sort(pl.ghist, pl.keysA, pl.keysB, pl.valsA, pl.valsB, nullptr, S, M, c->row_passes, ps,
-                  &pl.skey, &pl.spos);
+  // 3. the uses of duplicated rows, compacted in position order (the others are marked UNIQUE)
+  const int nblk = (M + DP_TILE - 1) / DP_TILE;
+  dim3 dgrid((unsigned)nblk, (unsigned)S);
+  hole_plan_dupflag_kernel<<<dgrid, DP_THREADS, 0, ps>>>(pl.keysA, pl.dup, M, W, pl.gslot, pl.blkcnt);
+  HOLE_LAUNCHED();
+  hole_plan_dupscan_kernel<<<(unsigned)S, 256, 0, ps>>>(pl.blkcnt, nblk, pl.mdup);
+  HOLE_LAUNCHED();
+  hole_plan_compact_kernel<<<dgrid, DP_THREADS, 0, ps>>>(pl.keysA, pl.dup, M, W, pl.blkcnt, pl.keysB, pl.valsA);
+  HOLE_LAUNCHED();
+  // 4. sort them by row (stable: equal rows stay in position order), 5. segments
+  rc = radix_sort(pl.ghist, pl.keysB, pl.keysC, pl.valsA, pl.valsB, nullptr, S, M, c->row_passes, ps,
+                  &pl.skey, &pl.spos, /*v_init=*/true, pl.mdup);
   if (rc) return rc;
   pl.heads_cap = M / 2 + 1;
   HOLE_CUDA_TRY(cudaMemsetAsync(pl.nheads, 0, (size_t)S * 4, ps));
   dim3 sgrid((unsigned)std::min<int64_t>((M + 255) / 256, 1024), (unsigned)S);
-  hole_plan_segments_kernel<<<sgrid, 256, 0, ps>>>(pl.skey, pl.spos, pl.gslot, pl.heads, pl.nheads, M,
+  hole_plan_segments_kernel<<<sgrid, 256, 0, ps>>>(pl.skey, pl.spos, pl.gslot, pl.heads, pl.nheads, M, pl.mdup,
                                                   pl.heads_cap);
   HOLE_LAUNCHED();
   HOLE_CUDA_TRY(cudaEventRecord(pl.ready, ps));
@@ -1821,7 +1971,8 @@ extern "C" int hole_train_step_logloss(hole_ctx* c, float* table, float* delta_w
   const int M = (int)(4 * B);
   for (int j = 0; j < k; ++j)
     HOLE_DISPATCH(c, hole_apply_delta_kernel, grid_for_groups(M, c->gs), 256, st, table, delta_ws,
-                  pl.skey + (size_t)j * M, M, c->nvec, c->row_stride);
+                  pl.keysA + (size_t)j * M, pl.gslot + (size_t)j * M, pl.skey + (size_t)j * M, M, c->nvec,
+                  c->row_stride);
   pl.used = true;
   HOLE_CUDA_TRY(cudaEventRecord(pl.released, st));
   return HOLE_OK;

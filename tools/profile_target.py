@@ -10,7 +10,7 @@ import torch
 from graphembeddings_b200 import data as D
 from graphembeddings_b200.engine import HoleEngine
 
-B, steps = 32768, 6
+B, steps = 32768, int(os.environ.get("PT_STEPS", 6))
 kg = D.make_config("diffbot_d256", n_triples=B * steps)
 off, ids = D.build_type_csr(kg.type_of)
 e = HoleEngine(kg.n_rows, kg.dim).set_embeddings(kg.E).set_types(kg.type_of, off, ids)
