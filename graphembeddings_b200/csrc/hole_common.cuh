@@ -48,7 +48,9 @@ struct hole_plan {
   uint32_t* keysB = nullptr;     // [S][4B] keys of the duplicated uses, compacted: sort ping
   uint32_t* keysC = nullptr;     // [S][4B] sort pong
   uint32_t* seen = nullptr;      // [S][n_rows/32] bitmap: row used by the step
-  uint32_t* dup = nullptr;       // [S][n_rows/32] bitmap: row used more than once
+  uint32_t* dup = nullptr;       // [S][n_rows/32] bitmap: row used more than once (second half of `seen`'s allocation)
+  size_t bitmap_words = 0;
+  unsigned* done = nullptr;      // [S] "last tile block of the step" tickets of the sort (zero between uses)
   int* blkcnt = nullptr;         // [S][tiles+1] duplicated uses per tile -> offsets; total last
   int* mdup = nullptr;           // [S] duplicated uses of the step
   uint32_t* valsA = nullptr;
@@ -115,6 +117,7 @@ struct hole_ctx {
   hole_shard_state* shard_state = nullptr;   // row-sharded step (hole_shard_init)
   // multi-GPU step routing (hole_shard_route): sort scratch for 3B entity keys
   uint32_t* route_buf = nullptr;
+  unsigned* route_done = nullptr;
   int64_t route_cap = 0;
 
   // ---- measurement hooks

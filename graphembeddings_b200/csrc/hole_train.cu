@@ -381,11 +381,17 @@ __device__ __forceinline__ void st_warp_hist(const uint32_t* __restrict__ k, int
   }
 }
 
-// ghist[(s*256 + digit)*P + p] = number of entries of tile p of step s with that digit
+// One radix pass = two launches.  This one: ghist[(s*256 + digit)*P + p] = number of entries of tile p of
+// step s with that digit; the LAST tile block of a step to finish (ticket counter, self-resetting) then
+// turns the step's counts into exclusive offsets in (digit-major, tile-minor) order -- the scan that used
+// to be a launch of its own.  Only the tiles the step really uses (Ms entries) are scanned: a warp takes
+// four digits at a time, its lanes the tiles (coalesced, four independent loads in flight).
 __global__ void __launch_bounds__(ST_THREADS)
 hole_sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t* __restrict__ ghist, int M, int P,
-                      int shift, const int* __restrict__ mdev) {
+                      int shift, const int* __restrict__ mdev, unsigned* __restrict__ done) {
   __shared__ uint32_t wh[ST_WARPS][256];
+  __shared__ uint32_t wsum[ST_WARPS];
+  __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int p = blockIdx.x, s = blockIdx.y;
   for (int i = tid; i < ST_WARPS * 256; i += ST_THREADS) (&wh[0][0])[i] = 0;
@@ -395,34 +401,76 @@ hole_sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t* __restrict__ 
   const int lo = min(Ms, p * ST_TILE + w * ST_SLICE), hi = min(Ms, lo + ST_SLICE);
   st_warp_hist(k, lo, hi, shift, wh[w], lane);
   __syncthreads();
-  uint32_t tot = 0;
+  uint32_t* gh = ghist + (size_t)s * 256 * P;
+  {
+    uint32_t tot = 0;
 #pragma unroll
-  for (int q = 0; q < ST_WARPS; ++q) tot += wh[q][tid];
-  ghist[((size_t)s * 256 + tid) * P + p] = tot;
-}
-
-// exclusive scan of one step's [256][P] tile histogram in (digit-major, tile-minor) order
-__global__ void __launch_bounds__(256)
-hole_sort_scan_kernel(uint32_t* __restrict__ ghist, int P) {
-  __shared__ uint32_t wsum[8];
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  uint32_t* h = ghist + ((size_t)blockIdx.x * 256 + tid) * P;
-  uint32_t tot = 0;
-  for (int p = 0; p < P; ++p) tot += h[p];
-  uint32_t inc = tot;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += y;
+    for (int q = 0; q < ST_WARPS; ++q) tot += wh[q][tid];
+    gh[(size_t)tid * P + p] = tot;
   }
-  if (lane == 31) wsum[w] = inc;
+  __threadfence();
   __syncthreads();
-  uint32_t base = inc - tot;
-  for (int q = 0; q < w; ++q) base += wsum[q];
-  for (int p = 0; p < P; ++p) {
-    uint32_t c = h[p];
-    h[p] = base;
-    base += c;
+  if (tid == 0) s_last = atomicAdd(done + s, 1u) == (unsigned)P - 1u;
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) done[s] = 0;                              // ready for the next pass
+  __threadfence();
+  const int Pe = max(1, (Ms + ST_TILE - 1) / ST_TILE);    // tiles that hold entries
+  uint32_t* s_tot = &wh[0][0];                            // 256 digit totals (the tile histograms are spent)
+  for (int d0 = w * 4; d0 < 256; d0 += ST_WARPS * 4) {
+    uint32_t t[4] = {0u, 0u, 0u, 0u};
+    for (int q0 = 0; q0 < Pe; q0 += 32) {
+      const int q = q0 + lane;
+      if (q < Pe) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t[u] += __ldcg(gh + (size_t)(d0 + u) * P + q);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t[u] += __shfl_xor_sync(0xffffffffu, t[u], o);
+    }
+    __syncwarp();
+    if (lane < 4) s_tot[d0 + lane] = (lane == 0) ? t[0] : (lane == 1) ? t[1] : (lane == 2) ? t[2] : t[3];
+  }
+  __syncthreads();
+  {
+    const uint32_t tot = s_tot[tid];
+    uint32_t inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    uint32_t base = inc - tot;
+    for (int q = 0; q < w; ++q) base += wsum[q];
+    s_tot[tid] = base;
+  }
+  __syncthreads();
+  for (int d0 = w * 4; d0 < 256; d0 += ST_WARPS * 4) {
+    uint32_t carry[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) carry[u] = s_tot[d0 + u];
+    for (int q0 = 0; q0 < Pe; q0 += 32) {
+      const int q = q0 + lane;
+      uint32_t c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) c[u] = (q < Pe) ? __ldcg(gh + (size_t)(d0 + u) * P + q) : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t inc = c[u];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += y;
+        }
+        if (q < Pe) gh[(size_t)(d0 + u) * P + q] = carry[u] + inc - c[u];
+        carry[u] += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
   }
 }
 
@@ -1457,8 +1505,9 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
 
 static void plan_free(hole_plan& p) {
   cudaFree(p.keysA); cudaFree(p.keysB); cudaFree(p.keysC); cudaFree(p.valsA); cudaFree(p.valsB);
-  cudaFree(p.seen); cudaFree(p.dup); cudaFree(p.blkcnt); cudaFree(p.mdup);
+  cudaFree(p.seen); cudaFree(p.blkcnt); cudaFree(p.mdup); cudaFree(p.done);
   p.keysC = p.seen = p.dup = nullptr;
+  p.done = nullptr;
   p.blkcnt = p.mdup = nullptr;
   cudaFree(p.gslot); cudaFree(p.heads); cudaFree(p.nheads); cudaFree(p.neg); cudaFree(p.ghist); cudaFree(p.perm);
   p.perm = nullptr;
@@ -1492,6 +1541,7 @@ extern "C" int hole_ctx_destroy(hole_ctx* c) {
   ws_free(c);
   hole_rank_ws_free(c);
   cudaFree(c->route_buf);
+  cudaFree(c->route_done);
   cudaFree(c->triples_stage[0]); cudaFree(c->triples_stage[1]);
   if (c->loss_sum_pinned) cudaFreeHost(c->loss_sum_pinned);
   for (int k = 0; k < 2; ++k) {
@@ -1542,8 +1592,11 @@ int hole_ws_reserve(hole_ctx* c, int64_t B, int64_t S) {
     WS_ALLOC(p.valsA, S * M * 4); WS_ALLOC(p.valsB, S * M * 4);
     {
       const size_t W = (size_t)(c->n_rows + 31) / 32;
-      WS_ALLOC(p.seen, (size_t)S * W * 4);
-      WS_ALLOC(p.dup, (size_t)S * W * 4);
+      p.bitmap_words = (size_t)S * W;
+      WS_ALLOC(p.seen, 2 * p.bitmap_words * 4);
+      p.dup = p.seen + p.bitmap_words;
+      WS_ALLOC(p.done, (size_t)S * sizeof(unsigned));
+      HOLE_CUDA_TRY(cudaMemset(p.done, 0, (size_t)S * sizeof(unsigned)));
       WS_ALLOC(p.blkcnt, (size_t)S * ((M + DP_TILE - 1) / DP_TILE + 1) * 4);
       WS_ALLOC(p.mdup, (size_t)S * 4);
     }
@@ -1624,18 +1677,18 @@ extern "C" int hole_score(hole_ctx* c, const float* table, const int32_t* triple
 // Keys start in kA (destroyed); kB, vA, vB are scratch; the last pass writes the values to
 // v_final when given.  Returns where the sorted keys / values ended up.
 // v_init: the values travelling with the keys of kA live in vA (else value = index).  mdev: per-array
-// element counts on the device (else M); the arrays are M apart either way.
+// element counts on the device (else M); the arrays are M apart either way.  done: S zero-initialised
+// ticket counters (left zero).
 static int radix_sort(uint32_t* ghist, uint32_t* kA, uint32_t* kB, uint32_t* vA, uint32_t* vB,
                       uint32_t* v_final, int64_t S, int M, int passes, cudaStream_t st,
-                      uint32_t** k_out, uint32_t** v_out, bool v_init = false, const int* mdev = nullptr) {
+                      uint32_t** k_out, uint32_t** v_out, unsigned* done, bool v_init = false,
+                      const int* mdev = nullptr) {
   const int P = (M + ST_TILE - 1) / ST_TILE;
   uint32_t *kin = kA, *vin = v_init ? vA : nullptr, *kout = kB, *vout = vB;
   dim3 grid((unsigned)P, (unsigned)S);
   for (int pass = 0; pass < passes; ++pass) {
     if (pass == passes - 1 && v_final != nullptr) vout = v_final;
-    hole_sort_hist_kernel<<<grid, ST_THREADS, 0, st>>>(kin, ghist, M, P, 8 * pass, mdev);
-    HOLE_LAUNCHED();
-    hole_sort_scan_kernel<<<(unsigned)S, 256, 0, st>>>(ghist, P);
+    hole_sort_hist_kernel<<<grid, ST_THREADS, 0, st>>>(kin, ghist, M, P, 8 * pass, mdev, done);
     HOLE_LAUNCHED();
     hole_sort_scatter_kernel<<<grid, ST_THREADS, 0, st>>>(kin, vin, kout, vout, ghist, M, P, 8 * pass, mdev);
     HOLE_LAUNCHED();
@@ -1738,13 +1791,12 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
   HOLE_LAUNCHED();
   uint32_t *ko, *vo;
   int rc = radix_sort(pl.ghist, pl.keysA, pl.keysB, pl.valsA, pl.valsB, reinterpret_cast<uint32_t*>(pl.perm),
-                      S, (int)B, c->rel_passes, ps, &ko, &vo);
+                      S, (int)B, c->rel_passes, ps, &ko, &vo, pl.done);
   if (rc) return rc;
   // 2. corruption + the 4B row keys of every step; rows used more than once are marked in the bitmaps
   pl.T = triples_per_group(c, B);
   const int W = (int)((c->n_rows + 31) / 32);
-  HOLE_CUDA_TRY(cudaMemsetAsync(pl.seen, 0, (size_t)S * W * 4, ps));
-  HOLE_CUDA_TRY(cudaMemsetAsync(pl.dup, 0, (size_t)S * W * 4, ps));
+  HOLE_CUDA_TRY(cudaMemsetAsync(pl.seen, 0, (size_t)2 * pl.bitmap_words * 4, ps));   // seen | dup (one allocation)
   hole_plan_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, tstride, pl.T, pl.perm, type_of, csr_off, csr_ids,
                                               seed, first_step, neg_in, pl.neg, pl.keysA, pl.seen, pl.dup, W);
   HOLE_LAUNCHED();
@@ -1759,7 +1811,7 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
   HOLE_LAUNCHED();
   // 4. sort them by row (stable: equal rows stay in position order), 5. segments
   rc = radix_sort(pl.ghist, pl.keysB, pl.keysC, pl.valsA, pl.valsB, nullptr, S, M, c->row_passes, ps,
-                  &pl.skey, &pl.spos, /*v_init=*/true, pl.mdup);
+                  &pl.skey, &pl.spos, pl.done, /*v_init=*/true, pl.mdup);
   if (rc) return rc;
   pl.heads_cap = M / 2 + 1;
   HOLE_CUDA_TRY(cudaMemsetAsync(pl.nheads, 0, (size_t)S * 4, ps));
@@ -2031,6 +2083,15 @@ static int route_reserve(hole_ctx* c, int64_t M, int64_t S = 1) {
     return hole_set_error(HOLE_ERR_ALLOC, "route workspace allocation failed");
   }
   c->route_cap = M * S;
+  // the sort's ticket counters (one per step of a chunk; zero between uses)
+  cudaFree(c->route_done);
+  c->route_done = nullptr;
+  const size_t nd = (size_t)std::max<int64_t>(S, 64);
+  if (cudaMalloc((void**)&c->route_done, nd * sizeof(unsigned)) != cudaSuccess) {
+    cudaGetLastError();
+    return hole_set_error(HOLE_ERR_ALLOC, "route workspace allocation failed");
+  }
+  HOLE_CUDA_TRY(cudaMemset(c->route_done, 0, nd * sizeof(unsigned)));
   return HOLE_OK;
 }
 
@@ -2058,7 +2119,7 @@ static int shard_route(hole_ctx* c, const int32_t* pos, const int32_t* neg_ent, 
   hole_shard_keys_kernel<<<kgrid, 256, 0, st>>>(pos, neg_ent, (int)B, kA);
   HOLE_LAUNCHED();
   uint32_t *sk, *sp;
-  rc = radix_sort(ghist, kA, kB, vA, vB, nullptr, S, M, passes, st, &sk, &sp);
+  rc = radix_sort(ghist, kA, kB, vA, vB, nullptr, S, M, passes, st, &sk, &sp, c->route_done);
   if (rc) return rc;
   // the sort's tile histogram is free again: per step, tile head counts + the total live there
   const int tiles = (M + RT_TILE - 1) / RT_TILE;
