@@ -146,6 +146,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
+def settle_clocks(seconds=0.25):
+    """Keep the GPU busy with device fills for a moment: after the clock sampler's start-up pause the SM
+    and memory clocks have dropped to idle, and W = 3-5 warm-up steps (0.3 ms) are too short to raise them
+    again.  Not a step; nothing of the workload runs here."""
+    import torch
+    buf = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(8):
+            buf.fill_(1.0)
+        torch.cuda.synchronize()
+    del buf
+
+
 def make_workload(n_triples, with_embeddings=True):
     from graphembeddings_b200 import data as D
     kg = D.make_config(WORKLOAD, n_triples=n_triples, with_embeddings=with_embeddings)
@@ -348,6 +362,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(1.0)
+    settle_clocks()
     eng.train_steps(dev_tri[: W * B], B, 1, 0, MARGIN, lr_schedule(W, 0, batch_count))
     barrier()
     eng.reset_launch_count()
@@ -394,6 +409,7 @@ def run_ours(args):
             "workload": workload_desc(B),
             "batch": B, "margin": MARGIN, "lr0": LR0, "triples_generated": int(kg.triples.shape[0]),
             "epoch_triples": 30_000_000, "l2": "table (1.2 GB) larger than L2; no flush",
+            "clock_settle": "0.25 s of device fills after the clock sampler's start-up pause, before the warm-up steps",
             "mean_loss_last_pass": mean_loss, "gen_seconds": round(t_gen, 1)},
         "e2e": {"value": e2e, "unit": "triples/s", "h2d_bytes_per_step": 12 * B,
                 "d2h_bytes_per_step": 4, "call": "hole_train_steps_host (pinned host triples in, loss sums out)"},

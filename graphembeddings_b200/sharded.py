@@ -667,6 +667,7 @@ def bench(args, dist, rank, world, local_rank):
     if rank == 0 and os.environ.get("HOLE_NO_SAMPLER") != "1":
         sampler.start()
         time.sleep(1.0)
+    B_.settle_clocks()
 
     def run_steps(k0, n, first_step):
         if p2p:
