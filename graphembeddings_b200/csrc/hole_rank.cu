@@ -36,8 +36,7 @@ constexpr int RANK_THREADS = 64 + 32 * EPI_WARPS;
 // that feed the tensor pipe must not be starved by the epilogue warps, so they come last.
 constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1, WARP_EPI0 = 0;
 constexpr int EPI_COLS = 256 / (EPI_WARPS / 4);    // columns of the 256-wide tile one warp owns
-constexpr int EPI_CHUNKS = EPI_COLS / 32;
-constexpr int MAX_STAGES = 8;     // barrier slots; the single-CTA kernel uses at most 4 (32 KB stages)
+constexpr int MAX_STAGES = 8;     // barrier slots
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 enum { MODE_COUNT = 0, MODE_DIAG = 1 };
@@ -147,6 +146,43 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// The same load without the wait: the registers are valid only after tmem_ld_wait(v).
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// Waits for every tcgen05.ld of this thread; the registers pass through the statement so that no
+// use of them can be scheduled ahead of the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+        "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),
+        "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]),
+        "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),
+        "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+      :
+      : "memory");
+}
+// c += (a < b): one FSETP and one predicated add
+__device__ __forceinline__ void count_lt(int& c, uint32_t a_bits, float b) {
+  asm("{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.lt.f32 p, %1, %2;\n\t"
+      "@p add.s32 %0, %0, 1;\n\t"
+      "}"
+      : "+r"(c)
+      : "f"(__uint_as_float(a_bits)), "f"(b));
+}
 
 
 // ---- CTA-pair (cta_group::2) variants
@@ -222,6 +258,50 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Rank-count epilogue of 32 accumulator columns held by one thread (one query row): how many of the
+// candidates j0 .. j0+31 rank before the true one.  thr_hi = nextafter(thr): s <= thr <=> s < thr_hi;
+// candidates with index < tie win ties (holE.py:427-469 walks the heap in index order).
+__device__ __forceinline__ void epi_count32(const uint32_t (&v)[32], int j0, float thr, float thr_hi, int tie,
+                                            int Nc, int& c0, int& c1, int& c2, int& c3) {
+  const bool slow = (j0 < tie && tie < j0 + 32) || (j0 + 32 > Nc);
+  if (!__any_sync(0xffffffffu, slow)) {
+    const float tt = (j0 + 32 <= tie) ? thr_hi : thr;
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) {      // four independent chains
+      count_lt(c0, v[k], tt);
+      count_lt(c1, v[k + 1], tt);
+      count_lt(c2, v[k + 2], tt);
+      count_lt(c3, v[k + 3], tt);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int j = j0 + k;
+      const float tt = (j < tie) ? thr_hi : thr;
+      c0 += (j < Nc && __uint_as_float(v[k]) < tt) ? 1 : 0;
+    }
+  }
+}
+// 128 columns (four chunks) of one accumulator row; the TMEM load of a chunk is in flight while
+// the previous one is counted.
+__device__ __forceinline__ int epi_count128(uint32_t taddr0, int j0, float thr, float thr_hi, int tie, int Nc) {
+  uint32_t va[32], vb[32];
+  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  tmem_ld32_async(taddr0, va);
+  tmem_ld_wait(va);
+  tmem_ld32_async(taddr0 + 32, vb);
+  epi_count32(va, j0, thr, thr_hi, tie, Nc, c0, c1, c2, c3);
+  tmem_ld_wait(vb);
+  tmem_ld32_async(taddr0 + 64, va);
+  epi_count32(vb, j0 + 32, thr, thr_hi, tie, Nc, c0, c1, c2, c3);
+  tmem_ld_wait(va);
+  tmem_ld32_async(taddr0 + 96, vb);
+  epi_count32(va, j0 + 64, thr, thr_hi, tie, Nc, c0, c1, c2, c3);
+  tmem_ld_wait(vb);
+  epi_count32(vb, j0 + 96, thr, thr_hi, tie, Nc, c0, c1, c2, c3);
+  return (c0 + c1) + (c2 + c3);
+}
+
 struct SmemLayout {
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
@@ -269,6 +349,8 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0, a_phase = 0;
+      // DIAG: only the tile's own 128 true rows are needed (the map's box is 128 rows there)
+      const uint32_t b_bytes = (p.mode == MODE_DIAG) ? B_KB_BYTES / 2 : B_KB_BYTES;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int m_tile = item / p.n_chunks, chunk = item % p.n_chunks;
         mbar_wait(&sl->a_empty, a_phase ^ 1);
@@ -282,7 +364,7 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int row0 = (p.mode == MODE_DIAG) ? m_tile * BM : t * BN;
           for (int kb = 0; kb < nkb_all; ++kb) {
             mbar_wait(&sl->empty[stage], phase ^ 1);
-            mbar_expect_tx(&sl->full[stage], B_KB_BYTES);
+            mbar_expect_tx(&sl->full[stage], b_bytes);
             tma_load_2d(sB + (size_t)stage * B_KB_BYTES, &tmB, &sl->full[stage], kb * BK, row0);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -292,7 +374,7 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = (p.mode == MODE_DIAG) ? umma_idesc_bf16(BM, BM) : umma_idesc_bf16(BM, BN);
       const int a_lo_off = p.num_kb * A_KB_BYTES;   // query lo part sits after the hi part
       int stage = 0; uint32_t phase = 0, a_phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -375,25 +457,8 @@ hole_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + cgrp * EPI_COLS);
         if (p.mode == MODE_COUNT) {
-#pragma unroll 1
-          for (int c = 0; c < EPI_CHUNKS; ++c) {
-            uint32_t v[32];
-            tmem_ld32(taddr0 + c * 32, v);
-            const int j0 = t * BN + cgrp * EPI_COLS + c * 32;  // shard-local index of v[0]
-            const bool slow = (j0 < tie && tie < j0 + 32) || (j0 + 32 > p.Nc);
-            if (!__any_sync(0xffffffffu, slow)) {
-              const float tt = (j0 + 32 <= tie) ? thr_hi : thr;
-#pragma unroll
-              for (int k = 0; k < 32; ++k) cnt += (__uint_as_float(v[k]) < tt) ? 1 : 0;
-            } else {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) {
-                const int j = j0 + k;
-                const float tt = (j < tie) ? thr_hi : thr;
-                cnt += (j < p.Nc && __uint_as_float(v[k]) < tt) ? 1 : 0;
-              }
-            }
-          }
+          static_assert(EPI_COLS == 128, "epi_count128 covers 128 columns per warp");
+          cnt += epi_count128(taddr0, t * BN + cgrp * EPI_COLS, thr, thr_hi, tie, p.Nc);
         } else if (cgrp == (quarter * 32) / EPI_COLS) {
           // DIAG: row i of the tile wants column i, which lives in chunk `quarter`, register `lane`
           uint32_t v[32];
@@ -555,25 +620,7 @@ hole_rank_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
         if (p.mode == MODE_COUNT) {
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(taddr0 + c * 32, v);
-            const int j0 = t * BN + half * 128 + c * 32;
-            const bool slow = (j0 < tie && tie < j0 + 32) || (j0 + 32 > p.Nc);
-            if (!__any_sync(0xffffffffu, slow)) {
-              const float tt = (j0 + 32 <= tie) ? thr_hi : thr;
-#pragma unroll
-              for (int k = 0; k < 32; ++k) cnt += (__uint_as_float(v[k]) < tt) ? 1 : 0;
-            } else {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) {
-                const int j = j0 + k;
-                const float tt = (j < tie) ? thr_hi : thr;
-                cnt += (j < p.Nc && __uint_as_float(v[k]) < tt) ? 1 : 0;
-              }
-            }
-          }
+          cnt += epi_count128(taddr0, t * BN + half * 128, thr, thr_hi, tie, p.Nc);
         } else if (half == (int)cta) {
           // DIAG: the tile's columns [cta*128, +128) are the true rows of this CTA's queries
           uint32_t v[32];
@@ -635,20 +682,30 @@ hole_rank_pack_cand_kernel(const float* __restrict__ table, int stride, int H, i
 
 // Query operand (App. A.4): tail side q = h * r; head side q = r * conj(t) with the imaginary
 // half negated.  Also records the shard-local index of the true candidate.
+// One warp per query; a lane holds groups of four complex components of both factor rows
+// (float4 loads of the [Re | pad | Im | pad] row layout) in registers between the norm pass and
+// the product pass.  PQ_ITERS = ceil(Hp / 128), at most 3 for the dimensions the ranking kernel's smem admits.
+template <int PQ_ITERS>
 __global__ void __launch_bounds__(256)
 hole_rank_pack_query_kernel(const float* __restrict__ table, int stride, int H,
                             const int32_t* __restrict__ queries, int Q, int Qpad, int side,
                             int64_t ent_begin, int K, int parts, __nv_bfloat16* __restrict__ out,
                             int32_t* __restrict__ true_idx) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ uint4 pq_smem[];                    // one operand row per warp, written out as 16-byte vectors
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t qi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (qi >= Qpad) return;
-  __nv_bfloat16* o = out + (size_t)qi * K * parts;      // row = [hi part (K) | lo part (K)]
+  const int row_vecs = K * parts / 8;                   // K is a multiple of 64
+  uint4* o4 = reinterpret_cast<uint4*>(out + (size_t)qi * K * parts);      // row = [hi part (K) | lo part (K)]
   if (qi >= Q) {
-    for (int k = lane; k < K * parts; k += 32) o[k] = __float2bfloat16(0.f);
+    for (int k = lane; k < row_vecs; k += 32) o4[k] = make_uint4(0, 0, 0, 0);
     if (lane == 0) true_idx[qi] = -1;
     return;
   }
+  uint4* row4 = pq_smem + (size_t)wib * row_vecs;
+  __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(row4);
+#pragma unroll 1
+  for (int k = lane; k < row_vecs; k += 32) row4[k] = make_uint4(0, 0, 0, 0);      // the padding stays zero
   // HOLE_SIDE_BOTH: Q = 2 * Qsrc rows, the first half ranks tails, the second half heads
   int64_t src = qi;
   if (side == HOLE_SIDE_BOTH) {
@@ -657,14 +714,22 @@ hole_rank_pack_query_kernel(const float* __restrict__ table, int stride, int H,
     src = (qi < half) ? qi : qi - half;
   }
   const int h = queries[3 * src], t = queries[3 * src + 1], r = queries[3 * src + 2];
-  const int Hp = stride / 2;
-  const float* x1 = table + (size_t)(side == HOLE_SIDE_TAIL ? h : r) * stride;   // first factor
-  const float* x2 = table + (size_t)(side == HOLE_SIDE_TAIL ? r : t) * stride;   // second factor
+  const int Hp = stride / 2, G4 = Hp / 4;
+  const float4* x1 = reinterpret_cast<const float4*>(table + (size_t)(side == HOLE_SIDE_TAIL ? h : r) * stride);
+  const float4* x2 = reinterpret_cast<const float4*>(table + (size_t)(side == HOLE_SIDE_TAIL ? r : t) * stride);
+  float4 A[PQ_ITERS], Bv[PQ_ITERS], C[PQ_ITERS], Dv[PQ_ITERS];   // (A,Bv) = first factor re/im, (C,Dv) = second
   float s1 = 0.f, s2 = 0.f;
-  for (int k = lane; k < H; k += 32) {
-    float a = x1[k], b = x1[Hp + k], c = x2[k], d = x2[Hp + k];
-    s1 = fmaf(a, a, fmaf(b, b, s1));
-    s2 = fmaf(c, c, fmaf(d, d, s2));
+#pragma unroll
+  for (int it = 0; it < PQ_ITERS; ++it) {
+    const int g = lane + 32 * it;
+    A[it] = Bv[it] = C[it] = Dv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < G4) {          // components H..Hp-1 of a half row are zero padding
+      A[it] = x1[g]; Bv[it] = x1[G4 + g]; C[it] = x2[g]; Dv[it] = x2[G4 + g];
+      s1 += A[it].x * A[it].x + A[it].y * A[it].y + A[it].z * A[it].z + A[it].w * A[it].w +
+            Bv[it].x * Bv[it].x + Bv[it].y * Bv[it].y + Bv[it].z * Bv[it].z + Bv[it].w * Bv[it].w;
+      s2 += C[it].x * C[it].x + C[it].y * C[it].y + C[it].z * C[it].z + C[it].w * C[it].w +
+            Dv[it].x * Dv[it].x + Dv[it].y * Dv[it].y + Dv[it].z * Dv[it].z + Dv[it].w * Dv[it].w;
+    }
   }
 #pragma unroll
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
@@ -672,36 +737,69 @@ hole_rank_pack_query_kernel(const float* __restrict__ table, int stride, int H,
     s2 += __shfl_xor_sync(0xffffffffu, s2, o2);
   }
   const float c1 = fminf(__frsqrt_rn(s1), 1.0f), c2 = fminf(__frsqrt_rn(s2), 1.0f);
-  for (int k = lane; k < K * parts; k += 32) o[k] = __float2bfloat16(0.f);
+  const float c1s = (side == HOLE_SIDE_TAIL) ? c1 : -c1;
   __syncwarp();
-  for (int k = lane; k < H; k += 32) {
-    const float a = x1[k] * c1, b = x1[Hp + k] * c1, c = x2[k] * c2, d = x2[Hp + k] * c2;
-    float re, im;
-    if (side == HOLE_SIDE_TAIL) { re = a * c - b * d; im = a * d + b * c; }   // (a,b)=h (c,d)=r
-    else                        { re = a * c + b * d; im = a * d - b * c; }   // (a,b)=r (c,d)=t
-    const __nv_bfloat16 rh = __float2bfloat16(re), ih = __float2bfloat16(im);
-    o[k] = rh;
-    o[H + k] = ih;
-    if (parts == 2) {
-      o[K + k] = __float2bfloat16(re - __bfloat162float(rh));
-      o[K + H + k] = __float2bfloat16(im - __bfloat162float(ih));
+#pragma unroll
+  for (int it = 0; it < PQ_ITERS; ++it) {
+    const int g = lane + 32 * it;
+    if (g < G4) {
+      const float a[4] = {A[it].x * c1, A[it].y * c1, A[it].z * c1, A[it].w * c1};        // clipped factors
+      const float b[4] = {Bv[it].x * c1s, Bv[it].y * c1s, Bv[it].z * c1s, Bv[it].w * c1s};   // head side: -Im
+      const float c[4] = {C[it].x * c2, C[it].y * c2, C[it].z * c2, C[it].w * c2};
+      const float d[4] = {Dv[it].x * c2, Dv[it].y * c2, Dv[it].z * c2, Dv[it].w * c2};
+      float re[4], im[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // tail: (a,b)=h (c,d)=r, q = h*r;  head: (a,b)=r (c,d)=t with b negated: q = (ac+bd, ad-bc)
+        re[i] = a[i] * c[i] - b[i] * d[i];
+        im[i] = a[i] * d[i] + b[i] * c[i];
+      }
+      const int k0 = 4 * g;
+      if (k0 + 4 <= H) {       // whole group: the real part is 8-byte aligned in the row
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(re[0], re[1]), p1 = __floats2bfloat162_rn(re[2], re[3]);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&p0);
+        u.y = *reinterpret_cast<uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(row + k0) = u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) row[H + k0 + i] = __float2bfloat16(im[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (k0 + i < H) { row[k0 + i] = __float2bfloat16(re[i]); row[H + k0 + i] = __float2bfloat16(im[i]); }
+      }
+      if (parts == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (k0 + i < H) {
+            row[K + k0 + i] = __float2bfloat16(re[i] - __bfloat162float(__float2bfloat16(re[i])));
+            row[K + H + k0 + i] = __float2bfloat16(im[i] - __bfloat162float(__float2bfloat16(im[i])));
+          }
+      }
     }
   }
+  __syncwarp();
+#pragma unroll 1
+  for (int k = lane; k < row_vecs; k += 32) o4[k] = row4[k];
   if (lane == 0) true_idx[qi] = (int32_t)((int64_t)(side == HOLE_SIDE_TAIL ? t : h) - ent_begin);
 }
 
-// T[q] = packed candidate row of q's true candidate (zeros when it is not in this shard)
+// T[q] = packed candidate row of q's true candidate (zeros when it is not in this shard).
+// Eight lanes per row, four rows per warp: the kernel is two dependent loads deep, so rows in
+// flight per SM are what sets its speed.
 __global__ void __launch_bounds__(256)
 hole_rank_gather_true_kernel(const __nv_bfloat16* __restrict__ cand, const int32_t* __restrict__ true_idx,
                              int Nc, int rows, int K, __nv_bfloat16* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t qi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int sub = threadIdx.x & 7;
+  const int64_t qi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
   if (qi >= rows) return;
   const int ti = true_idx[qi];
   const bool ok = ti >= 0 && ti < Nc;
   const uint4* src = reinterpret_cast<const uint4*>(cand + (size_t)(ok ? ti : 0) * K);
   uint4* dst = reinterpret_cast<uint4*>(out + (size_t)qi * K);
-  for (int k = lane; k < K / 8; k += 32) dst[k] = ok ? src[k] : make_uint4(0, 0, 0, 0);
+  const int nv = K / 8;                                  // a multiple of 8 (K is a multiple of 64)
+#pragma unroll 4
+  for (int k = sub; k < nv; k += 8) dst[k] = ok ? src[k] : make_uint4(0, 0, 0, 0);
 }
 
 // Filtered counts: one warp per query walks its filter list (known-true candidates,
@@ -824,10 +922,8 @@ static int rank_impl(hole_ctx* c, const float* table, int64_t ent_begin, int64_t
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
 
-  static const bool use_pair = []() {
-    const char* e = getenv("HOLE_RANK_PAIR");      // experimental cta_group::2 kernel
-    return e != nullptr && e[0] == '1';
-  }();
+  const char* pe_ = getenv("HOLE_RANK_PAIR");      // experimental cta_group::2 kernel
+  const bool use_pair = pe_ != nullptr && pe_[0] == '1';
   const int Nc = (int)(ent_end - ent_begin);
   const int K = (c->dim + BK - 1) / BK * BK;
   const int num_kb = K / BK;
@@ -838,7 +934,8 @@ static int rank_impl(hole_ctx* c, const float* table, int64_t ent_begin, int64_t
   const int a_bytes = num_kb * parts * A_KB_BYTES;
   const int b_stage_bytes = use_pair ? B_HALF_BYTES : B_KB_BYTES;
   int stages = (SMEM_LIMIT - a_bytes - 2048) / b_stage_bytes;
-  stages = std::min(stages, use_pair ? MAX_STAGES : 4);
+  stages = std::min(stages, use_pair ? MAX_STAGES : 4);   // a fifth 32 KB stage measured no gain
+  if (const char* se_ = getenv("HOLE_RANK_STAGES")) stages = std::min(stages, std::max(2, atoi(se_)));   // tuning knob
   if (stages < 2)
     return hole_set_error(HOLE_ERR_UNSUPPORTED, "embedding_dim %d too large for the ranking kernel's smem budget at precision %d",
                           c->dim, precision);
@@ -892,8 +989,20 @@ static int rank_impl(hole_ctx* c, const float* table, int64_t ent_begin, int64_t
     return HOLE_OK;
   }
   w->last_qpad = Qpad;
-  hole_rank_pack_query_kernel<<<(unsigned)((Qpad + 7) / 8), 256, 0, st>>>(query_table, c->row_stride, c->H, queries, (int)Q, Qpad, side, ent_begin, K, parts, w->qp, w->true_idx);
-  HOLE_LAUNCHED();
+  {
+    const unsigned pq_grid = (unsigned)((Qpad + 7) / 8);
+    const size_t pq_smem = (size_t)8 * Kall * 2;
+    const int pq_iters = (c->row_stride / 2 + 127) / 128;
+#define HOLE_PQ_LAUNCH(N)                                                                                          \
+    hole_rank_pack_query_kernel<N><<<pq_grid, 256, pq_smem, st>>>(query_table, c->row_stride, c->H, queries, (int)Q, \
+                                                                  Qpad, side, ent_begin, K, parts, w->qp, w->true_idx)
+    if (pq_iters == 1) HOLE_PQ_LAUNCH(1);
+    else if (pq_iters == 2) HOLE_PQ_LAUNCH(2);
+    else if (pq_iters == 3) HOLE_PQ_LAUNCH(3);
+    else return hole_set_error(HOLE_ERR_UNSUPPORTED, "embedding_dim %d too large for the ranking query packer", c->dim);
+#undef HOLE_PQ_LAUNCH
+    HOLE_LAUNCHED();
+  }
 
   CUtensorMap mapA, mapB;
   int rc = make_map(&mapA, w->qp, Qpad, Kall, BM);
@@ -911,10 +1020,10 @@ static int rank_impl(hole_ctx* c, const float* table, int64_t ent_begin, int64_t
 
   if (compute_true) {
     const int rows = Qpad + BN;
-    hole_rank_gather_true_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w->cand, w->true_idx, Nc, Qpad, Kall, w->tq);
+    hole_rank_gather_true_kernel<<<(unsigned)((Qpad + 31) / 32), 256, 0, st>>>(w->cand, w->true_idx, Nc, Qpad, Kall, w->tq);
     HOLE_LAUNCHED();
     HOLE_CUDA_TRY(cudaMemsetAsync(w->tq + (size_t)Qpad * Kall, 0, (size_t)BN * Kall * 2, st));
-    rc = make_map(&mapB, w->tq, rows, Kall, use_pair ? BN / 2 : BN);
+    rc = make_map(&mapB, w->tq, rows, Kall, BN / 2);      // DIAG tiles: 128 true rows per CTA in both kernels
     if (rc) return rc;
     p.mode = MODE_DIAG;
     p.n_tiles = 1; p.chunk_tiles = 1; p.n_chunks = 1;
