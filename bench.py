@@ -274,6 +274,19 @@ def coverage_records(args, eng1, kg1, dev_tri1, peak):
         eng.set_relation_count(kg.n_relations)
         record("diffbot_d256_" + tag, eng, kg, torch.from_numpy(kg.triples).cuda(), args.batch,
                f"configs[1] shape, B={args.batch}, {note}")
+        if tag == "trained_scale":
+            # the archived FFT / tanh score variant (direct O(H^2) correlations on CUDA
+            # cores: compute-bound, ~4 * 4 * H^2 FMAs per triple, not an HBM-roofline kernel)
+            eng.set_score_mode("ccorr_tanh")
+            v, ms = timed_train(eng, torch.from_numpy(kg.triples).cuda(), args.batch, min(K, 10), min(W, 3),
+                                max(16, kg.triples.shape[0] // args.batch), first_step=2000)
+            H = kg.dim // 2
+            out["diffbot_d256_ccorr_tanh"] = {
+                "workload": f"configs[1] shape, B={args.batch}, archived score variant tanh(sum r*ccorr(h,t)) "
+                            "(holE-20170724/graph.pbtxt:6221-6521), margin as the headline",
+                "batch": args.batch, "value": v, "unit": "triples/s", "ms_per_step": ms, "steps": min(K, 10),
+                "fp32_tflops": v * (4 * 8 * H * H) / 1e12, "bound": "fp32 FMA (CUDA cores)"}
+            eng.set_score_mode("complex")
         eng.close()
         del eng, kg
     for tag, kw in (("uniform", {}), ("zipf", dict(zipf_entities=True))):

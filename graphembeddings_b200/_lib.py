@@ -27,6 +27,7 @@ SIGNATURES = {
     "hole_ctx_create": (_int, [C.POINTER(_p), _int, _i64, _int]),
     "hole_ctx_destroy": (_int, [_p]),
     "hole_ctx_set_relations": (_int, [_p, _i64]),
+    "hole_ctx_set_score_mode": (_int, [_p, _int]),
     "hole_pack_rows": (_int, [_p, _p, _p, _i64, _p]),
     "hole_unpack_rows": (_int, [_p, _p, _p, _i64, _p]),
     "hole_corrupt": (_int, [_p, _p, _i64, _p, _p, _p, _u64, _u64, _p, _p, C.POINTER(_int), _p]),

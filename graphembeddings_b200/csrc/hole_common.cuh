@@ -93,6 +93,8 @@ struct hole_ctx {
   int host_first = 0;  // hole_train_steps_host: steps in a short first chunk; 0 = off (measured slower: r02_e2e_ab.jsonl)
   int ramp_factor = 4; //   (HOLE_PLAN_RAMP=first,factor; measured slower than no ramp, profiles/r02_train_ab.txt:
                        //   a plan's latency is ~120 us of dependent launches whatever its size)
+  int score_mode = 0;  // HOLE_SCORE_COMPLEX (live holE.py) or HOLE_SCORE_CCORR_TANH (archived variant, hole_ccorr.cuh)
+  bool cc_ready = false;   // shared-memory attributes of the ccorr kernels set
   int row_passes = 1;  // 8-bit radix passes for row keys
   int rel_passes = 1;  // ... for relation ids (hole_ctx_set_relations)
 

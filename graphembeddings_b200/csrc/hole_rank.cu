@@ -892,6 +892,8 @@ static int rank_impl(hole_ctx* c, const float* table, int64_t ent_begin, int64_t
                      int compute_true, int32_t* raw_before, int32_t* filt_before, void* stream,
                      bool prepare_only) {
   HOLE_CHECK_ARG(c && Q >= 0 && ent_begin >= 0 && ent_end >= ent_begin && ent_end <= c->n_rows);
+  if (c->score_mode != HOLE_SCORE_COMPLEX)
+    return hole_set_error(HOLE_ERR_UNSUPPORTED, "the archived ccorr/tanh score mode has no ranking kernel");
   HOLE_CHECK_ARG(side == HOLE_SIDE_TAIL || side == HOLE_SIDE_HEAD || side == HOLE_SIDE_BOTH);
   if ((Q == 0 && !prepare_only) || ent_end == ent_begin) return HOLE_OK;
   if (side == HOLE_SIDE_BOTH) Q *= 2;    // output rows: [tail ranks of all queries | head ranks]

@@ -230,6 +230,8 @@ extern "C" int hole_shard_init(hole_ctx* c, int world, int me, int64_t n_relatio
                                const int64_t* csr_off, const int32_t* csr_ids) {
   HOLE_CHECK_ARG(c && shard && peer_shard && peer_stage && peer_relstage && peer_inbox && peer_meta && peer_flags);
   HOLE_CHECK_ARG(err_flag && type_of && csr_off && csr_ids);
+  if (c->score_mode != HOLE_SCORE_COMPLEX)
+    return hole_set_error(HOLE_ERR_UNSUPPORTED, "the archived ccorr/tanh score mode has no row-sharded step");
   HOLE_CHECK_ARG(world >= 1 && world <= HOLE_MAX_RANKS && me >= 0 && me < world);
   HOLE_CHECK_ARG(n_relations >= 0 && n_entities > 0 && rows_per_rank > 0 && rows_per_rank * world >= n_entities);
   HOLE_CHECK_ARG(n_relations + rows_per_rank * world < (int64_t(1) << 31));

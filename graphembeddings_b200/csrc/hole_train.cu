@@ -1107,6 +1107,7 @@ hole_apply_kernel(float* __restrict__ E, float* __restrict__ G, const uint4* __r
 
 // ---------------------------------------------------------------------------------------
 #include "hole_k1.cuh"
+#include "hole_ccorr.cuh"
 
 // table[ids[k]] += rows[k] for UNIQUE ids (multi-GPU: the owner applies one source rank's
 // row deltas; ranks are applied one after the other, so the sum order is fixed)
@@ -1426,6 +1427,48 @@ extern "C" int hole_row_stride(int dim) {
   return 2 * (((dim / 2) + 3) / 4 * 4);
 }
 
+// ---- the archived FFT / tanh score variant (hole_ccorr.cuh)
+#define HOLE_CC_DISPATCH(NVNEED, STMT)                                                       \
+  do {                                                                                       \
+    const int nv_ = (NVNEED);                                                                \
+    if (nv_ <= 1) { constexpr int NV = 1; STMT; }                                            \
+    else if (nv_ <= 2) { constexpr int NV = 2; STMT; }                                       \
+    else if (nv_ <= 3) { constexpr int NV = 3; STMT; }                                       \
+    else if (nv_ <= 4) { constexpr int NV = 4; STMT; }                                       \
+    else if (nv_ <= 6) { constexpr int NV = 6; STMT; }                                       \
+    else if (nv_ <= 8) { constexpr int NV = 8; STMT; }                                       \
+    else { constexpr int NV = 12; STMT; }                                                    \
+  } while (0)
+
+static int cc_nv(const hole_ctx* c) { return (c->row_stride / 2 + 31) / 32; }
+
+// warps per block such that the block's rows fit the opt-in shared memory
+static int cc_warps(int floats_per_warp) {
+  return std::max(1, std::min(8, (220 * 1024) / (floats_per_warp * (int)sizeof(float))));
+}
+
+static int cc_prepare(hole_ctx* c) {
+  if (c->cc_ready) return HOLE_OK;
+  const int lim = 227 * 1024;
+  cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+  HOLE_CC_DISPATCH(cc_nv(c),
+                   e1 = cudaFuncSetAttribute(hole_ccorr_fwd_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+                   e2 = cudaFuncSetAttribute(hole_ccorr_score_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  HOLE_CUDA_TRY(e1);
+  HOLE_CUDA_TRY(e2);
+  c->cc_ready = true;
+  return HOLE_OK;
+}
+
+extern "C" int hole_ctx_set_score_mode(hole_ctx* c, int mode) {
+  HOLE_CHECK_ARG(c != nullptr);
+  HOLE_CHECK_ARG(mode == HOLE_SCORE_COMPLEX || mode == HOLE_SCORE_CCORR_TANH);
+  if (mode == HOLE_SCORE_CCORR_TANH && c->shard_state != nullptr)
+    return hole_set_error(HOLE_ERR_UNSUPPORTED, "the archived ccorr/tanh score mode has no row-sharded step");
+  c->score_mode = mode;
+  return HOLE_OK;
+}
+
 static int ctx_create_streams(hole_ctx* c) {
   HOLE_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   {   // the plan is small integer work that the next step waits for: highest priority
@@ -1668,6 +1711,18 @@ extern "C" int hole_score(hole_ctx* c, const float* table, const int32_t* triple
   if (B == 0) return HOLE_OK;
   HOLE_CHECK_ARG(table && triples && out_sigma);
   HOLE_CUDA_TRY(cudaSetDevice(c->device));
+  if (c->score_mode == HOLE_SCORE_CCORR_TANH) {       // archived variant: tanh(s) instead of sigma(s)
+    int rc = cc_prepare(c);
+    if (rc) return rc;
+    const int fw = cc_score_warp_floats(c->H), warps = cc_warps(fw);
+    const unsigned grid = (unsigned)((B + warps - 1) / warps);
+    HOLE_CC_DISPATCH(cc_nv(c), (hole_ccorr_score_kernel<NV><<<grid, 32 * warps, (size_t)warps * fw * sizeof(float),
+                                                            (cudaStream_t)stream>>>(table, triples, B, c->H, c->row_stride,
+                                                                                    out_sigma)));
+    HOLE_CUDA_TRY(cudaGetLastError());
+    HOLE_LAUNCHED();
+    return HOLE_OK;
+  }
   HOLE_DISPATCH(c, hole_score_kernel, grid_for_groups(B, c->gs), 256, (cudaStream_t)stream, table,
                 triples, B, c->nvec, c->row_stride, out_sigma);
   return HOLE_OK;
@@ -1853,7 +1908,20 @@ static int run_step(hole_ctx* c, hole_plan& pl, float* table, const int32_t* pos
     k3s.cuts = shard->cuts; k3s.R = shard->R; k3s.me = shard->me; k3s.world = shard->world;
     k3s.cap = shard->cap; k3s.stage = shard->stage;
   }
-  if ((flags & 3) == 0) {
+  if (c->score_mode == HOLE_SCORE_CCORR_TANH) {
+    if (shard != nullptr || delta_out != nullptr || (flags & 3) != 0)
+      return hole_set_error(HOLE_ERR_UNSUPPORTED, "the archived ccorr/tanh score mode supports the hinge step on one table only");
+    int rc = cc_prepare(c);
+    if (rc) return rc;
+    const int fw = cc_warp_floats(c->H), warps = cc_warps(fw);
+    const int64_t groups = (B + pl.T - 1) / pl.T;
+    const unsigned grid = (unsigned)((groups + warps - 1) / warps);
+    HOLE_CC_DISPATCH(cc_nv(c), (hole_ccorr_fwd_bwd_kernel<NV><<<grid, 32 * warps, (size_t)warps * fw * sizeof(float), st>>>(
+                                   table, pos, neg, pl.perm + (size_t)slot * B, pl.gslot + off, side, (int)B, pl.T, c->H,
+                                   c->row_stride, margin, lr, c->G, loss_out, sigma_out)));
+    HOLE_CUDA_TRY(cudaGetLastError());
+    HOLE_LAUNCHED();
+  } else if ((flags & 3) == 0) {
     hole_k1_args ka = {};
     ka.E = table; ka.tri = shard ? shard_tri : pos; ka.neg = shard ? shard_neg : neg;
     ka.perm = pl.perm + (size_t)slot * B; ka.gslot = pl.gslot + off;
@@ -1985,6 +2053,8 @@ extern "C" int hole_train_step_logloss(hole_ctx* c, float* table, float* delta_w
                                        float* l2_loss_out, int32_t* neg_out, int32_t* sides_out,
                                        void* stream) {
   HOLE_CHECK_ARG(c && B >= 0 && negative_ratio >= 1 && negative_ratio <= 64);
+  if (c->score_mode != HOLE_SCORE_COMPLEX)
+    return hole_set_error(HOLE_ERR_UNSUPPORTED, "the archived ccorr/tanh score mode has no log-loss branch");
   if (B == 0) return HOLE_OK;
   HOLE_CHECK_ARG(table && delta_ws && triples && type_of && csr_off && csr_ids && loss_out);
   HOLE_CHECK_ARG(4 * B < (int64_t(1) << 31));

@@ -58,6 +58,13 @@ class HoleEngine:
         check(self.lib.hole_ctx_set_relations(self._ctx, int(n_relations)))
         return self
 
+    def set_score_mode(self, mode):
+        """"complex" (live holE.py:191-198, sigma of the Hermitian product) or "ccorr_tanh" (the archived
+        variant of holE-20170724/graph.pbtxt:6221-6521: tanh of r-weighted circular correlation)."""
+        code = {"complex": 0, "ccorr_tanh": 1}.get(mode, mode)      # HOLE_SCORE_COMPLEX / HOLE_SCORE_CCORR_TANH
+        check(self.lib.hole_ctx_set_score_mode(self._ctx, int(code)))
+        return self
+
     def close(self):
         if getattr(self, "_ctx", None):
             self.lib.hole_ctx_destroy(self._ctx)

@@ -227,6 +227,10 @@ def run_training(data, flags=None, seed=0, max_steps=None, log=print):
     else:
         E = D.init_embeddings(data.entity_count, flags.embedding_dim, np.random.default_rng(seed))
     eng = make_engine(data.entity_count, data.relation_count, flags.embedding_dim, E, data.id_to_type)
+    if getattr(flags, 'score_variant', 'complex') != 'complex':
+        if flags.log_loss:
+            raise SystemExit("--score_variant ccorr_tanh has no --log_loss branch")
+        eng.set_score_mode(flags.score_variant)      # archived FFT / tanh score (holE-20170724/graph.pbtxt:6221-6521)
     B = flags.batch_size
     triples_dev = torch.from_numpy(data.triples).to(eng.device)
     valid = data.validation_triples
@@ -505,6 +509,10 @@ def build_parser():
                         help='Tensor-core operand precision of --infer (bf16x3 = split-bf16, ~fp32 ranks).')
     parser.add_argument('--valid_sample', action='store_true',
                         help='Validate on one sampled batch as holE.py does (default: the whole triples-valid.txt).')
+    parser.add_argument('--score_variant', choices=['complex', 'ccorr_tanh'], default='complex',
+                        help="Score function: 'complex' = holE.py:191-198 (default); 'ccorr_tanh' = the archived "
+                             "variant of the holE-20170724 run (tanh of the r-weighted circular correlation, "
+                             "trained there with --margin 1.0); training and validation only.")
     parser.add_argument('--seed', type=int, default=0)
     parser.add_argument('--max_steps', type=int, default=None, help='Stop after this many steps (testing).')
     return parser
@@ -516,6 +524,8 @@ def main(argv=None):
     if FLAGS.save_embeddings:
         raise SystemExit("--save_embeddings (holE.py:501-527, a py2-only debug dump) is out of scope")
     if FLAGS.infer:
+        if FLAGS.score_variant != 'complex':
+            raise SystemExit("--infer ranks with the live score function only (--score_variant complex)")
         infer_triples(FLAGS)
     else:
         training_data = init_data(FLAGS)

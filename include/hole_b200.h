@@ -75,6 +75,17 @@ HOLE_API int hole_ctx_destroy(hole_ctx* ctx);
  * shortens the per-step "group triples by relation" sort.  Default: n_rows. */
 HOLE_API int hole_ctx_set_relations(hole_ctx* ctx, int64_t n_relations);
 
+/* Score variant.  HOLE_SCORE_COMPLEX (default) is the live holE.py:191-198:
+ * sigma(sum_k Re(h_k r_k conj(t_k))).  HOLE_SCORE_CCORR_TANH is the ARCHIVED variant of the run
+ * directory holE-20170724 (graph.pbtxt:6221-6521): tanh(sum_k Re(m_k) + Im(m_k)),
+ * m = r * ifft(conj(fft(h)) * fft(t)), with the loss max(tanh(s+) - tanh(s-) + margin, 0)
+ * (graph.pbtxt:15874-15988; margin 1.0 in that run).  In that mode hole_score returns tanh(s) and
+ * hole_train_step / hole_train_steps[_host] run the direct-correlation kernel; the log-loss
+ * branch, the delta-table step, the row-sharded step and hole_rank* return HOLE_ERR_UNSUPPORTED. */
+#define HOLE_SCORE_COMPLEX 0
+#define HOLE_SCORE_CCORR_TANH 1
+HOLE_API int hole_ctx_set_score_mode(hole_ctx* ctx, int mode);
+
 /* Checkpoint layout [n, dim] <-> device layout [n, row_stride]. */
 HOLE_API int hole_pack_rows(hole_ctx* ctx, const float* src_nd, float* dst_padded, int64_t n, void* stream);
 HOLE_API int hole_unpack_rows(hole_ctx* ctx, const float* src_padded, float* dst_nd, int64_t n, void* stream);

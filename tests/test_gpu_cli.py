@@ -199,3 +199,26 @@ def test_typed_candidate_protocol_matches_heap_restatement():
     m = hole.score_mrr(raw, filt, log=lambda *a: None)
     mw = O.score_mrr(want_r, want_f)
     assert abs(m["filtered_mrr"] - mw["filtered_mrr"]) < 5e-3
+
+
+def test_archived_ccorr_tanh_variant_trains_through_the_driver(tmp_path):
+    """--score_variant ccorr_tanh --margin 1.0 (the archived holE-20170724 run's score and margin) through the
+    training loop: the validation loss of the hinge on tanh scores falls, the checkpoint is written."""
+    from graphembeddings_b200 import build, hole, tf_bundle
+    build.build()
+    kg = D.synthetic_kg(8, 1500, 9000, 4, 64, seed=5)
+    d = tmp_path / "data"; d.mkdir()
+    _write_data_dir(str(d), kg, 600, 400)
+    out = str(tmp_path / "run")
+    args = ["--data_dir", str(d), "--output_dir", out, "--batch_size", "256", "--embedding_dim", "64",
+            "--num_epochs", "12", "--score_variant", "ccorr_tanh", "--margin", "1.0", "--learning_rate", "0.5"]
+    hole.main(args)
+    rows = [dict(kv.split("=") for kv in line.split("\t")) for line in open(os.path.join(out, "summaries.tsv"))]
+    v = [float(r["valid_loss_mean"]) for r in rows]
+    assert all(np.isfinite(v)) and abs(v[0] - 1.0) < 0.05          # near-zero scores at the Xavier start: loss = margin
+    assert min(v) < v[0] - 0.02                                      # the pocket checkpoint keeps the best one
+    E1 = tf_bundle.load_bundle(os.path.join(out, "model.ckpt"))["embeddings"]
+    assert np.isfinite(E1).all()
+    with pytest.raises(SystemExit):
+        hole.main(["--data_dir", str(d), "--output_dir", out, "--embedding_dim", "64", "--infer",
+                   "--score_variant", "ccorr_tanh"])
