@@ -25,6 +25,16 @@ def _tensor_peak():
     return 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def _tensor_peak_sustained():
+    """The pool's back-to-back bf16 GEMM figure (power-capped clocks): what a 50 ms tensor kernel can reach."""
+    path = os.path.join(_ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            v = json.load(f).get("bf16_tflops_sustained")
+            return float(v) if v else None
+    return None
+
+
 def time_rank(eng, queries, ent_begin, ent_end, sides=(HOLE_SIDE_TAIL, HOLE_SIDE_HEAD), reps=3,
               filters=None):
     """Best-of-reps milliseconds for ranking `queries` on every side in `sides`."""
@@ -57,6 +67,7 @@ def _report(name, Q, n_sides, N, dim, ms, extra=None):
            "ms": ms, "scores_per_s": scores / (ms * 1e-3),
            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s",
                         "frac": tflops / peak, "peak_source": src,
+                        "frac_of_sustained_peak": (tflops / _tensor_peak_sustained()) if _tensor_peak_sustained() else None,
                         "kernel": "hole_rank_kernel (tcgen05 bf16, rank-count epilogue)"},
            "dtype": "bf16 operands, f32 accumulate"}
     if extra:
