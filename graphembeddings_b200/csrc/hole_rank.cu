@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include "hole_common.cuh"
+#include "hole_ccorr_core.cuh"
 
 namespace {
 
@@ -991,6 +992,76 @@ hole_rank_pack_query_kernel(const float* __restrict__ table, int stride, int H,
   if (lane == 0) true_idx[qi] = (int32_t)((int64_t)(side == HOLE_SIDE_TAIL ? t : h) - ent_begin);
 }
 
+// Query operand of the ARCHIVED score variant (hole_ccorr.cuh): s = Re sum_k rho_k c_k with rho = (1 - i) r is
+// linear in the candidate entity, so the all-candidate form is the same dense contraction with another
+// query vector:   tail side  s(h, r, .) = [Re t ; Im t] . [Re w ; -Im w],  w_m = sum_k rho_k conj(h_{m-k})
+//                 head side  s(., r, t) = [Re h ; Im h] . [Re u ;  Im u],  u_j = sum_k rho_k t_{j+k}
+// One warp per query, one direct O(H^2) correlation out of shared memory.  tanh is monotone: ranking on s.
+template <int NV>
+__global__ void __launch_bounds__(256)
+hole_rank_pack_query_ccorr_kernel(const float* __restrict__ table, int stride, int H,
+                                  const int32_t* __restrict__ queries, int Q, int Qpad, int side,
+                                  int64_t ent_begin, int K, int parts, __nv_bfloat16* __restrict__ out,
+                                  int32_t* __restrict__ true_idx) {
+  extern __shared__ float pqc_smem[];                   // per warp: entity row doubled (4H), rho (2H)
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t qi = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (qi >= Qpad) return;
+  __nv_bfloat16* o = out + (size_t)qi * K * parts;
+  if (qi >= Q) {
+    for (int k = lane * 8; k < K * parts; k += 256) *reinterpret_cast<uint4*>(o + k) = make_uint4(0, 0, 0, 0);
+    if (lane == 0) true_idx[qi] = -1;
+    return;
+  }
+  int64_t src = qi;
+  if (side == HOLE_SIDE_BOTH) {
+    const int64_t half = Q / 2;
+    side = (qi < half) ? HOLE_SIDE_TAIL : HOLE_SIDE_HEAD;
+    src = (qi < half) ? qi : qi - half;
+  }
+  const int h = queries[3 * src], t = queries[3 * src + 1], r = queries[3 * src + 2];
+  const int Hp = stride / 2;
+  float* sm = pqc_smem + (size_t)wib * (6 * H);
+  float *e_re = sm, *e_im = sm + 2 * H, *rho_re = sm + 4 * H, *rho_im = sm + 5 * H;
+  CVec<NV> yr;
+  // the relation row lands in the entity buffers first (overwritten below); rho = (1 - i) r
+  cc_load_row<NV>(table + (size_t)r * stride, H, Hp, lane, e_re, e_im, &yr);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int k = lane + 32 * v;
+    if (k < H) { rho_re[k] = yr.re[v] + yr.im[v]; rho_im[k] = yr.im[v] - yr.re[v]; }
+  }
+  __syncwarp();
+  cc_load_row<NV>(table + (size_t)(side == HOLE_SIDE_TAIL ? h : t) * stride, H, Hp, lane, e_re, e_im, nullptr);
+  __syncwarp();
+  CVec<NV> qv;
+  if (side == HOLE_SIDE_TAIL) {
+    cc_corr<NV, false, true, false>(qv, rho_re, rho_im, e_re, e_im, H, lane);       // w; q = [Re w ; -Im w]
+#pragma unroll
+    for (int v = 0; v < NV; ++v) qv.im[v] = -qv.im[v];
+  } else {
+    cc_corr<NV, false, false, true>(qv, rho_re, rho_im, e_re, e_im, H, lane);       // u; q = [Re u ; Im u]
+  }
+  for (int k = 2 * H + lane; k < K; k += 32) {
+    o[k] = __float2bfloat16(0.f);
+    if (parts == 2) o[K + k] = __float2bfloat16(0.f);
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int k = lane + 32 * v;
+    if (k < H) {
+      const __nv_bfloat16 rh = __float2bfloat16(qv.re[v]), ih = __float2bfloat16(qv.im[v]);
+      o[k] = rh;
+      o[H + k] = ih;
+      if (parts == 2) {
+        o[K + k] = __float2bfloat16(qv.re[v] - __bfloat162float(rh));
+        o[K + H + k] = __float2bfloat16(qv.im[v] - __bfloat162float(ih));
+      }
+    }
+  }
+  if (lane == 0) true_idx[qi] = (int32_t)((int64_t)(side == HOLE_SIDE_TAIL ? t : h) - ent_begin);
+}
+
 // T[q] = packed candidate row of q's true candidate (zeros when it is not in this shard).
 // Eight lanes per row, four rows per warp: the kernel is two dependent loads deep, so rows in
 // flight per SM are what sets its speed.
@@ -1114,8 +1185,6 @@ static int rank_impl(hole_ctx* c, const float* table, int64_t ent_begin, int64_t
                      int compute_true, int32_t* raw_before, int32_t* filt_before, void* stream,
                      bool prepare_only) {
   HOLE_CHECK_ARG(c && Q >= 0 && ent_begin >= 0 && ent_end >= ent_begin && ent_end <= c->n_rows);
-  if (c->score_mode != HOLE_SCORE_COMPLEX)
-    return hole_set_error(HOLE_ERR_UNSUPPORTED, "the archived ccorr/tanh score mode has no ranking kernel");
   HOLE_CHECK_ARG(side == HOLE_SIDE_TAIL || side == HOLE_SIDE_HEAD || side == HOLE_SIDE_BOTH);
   if ((Q == 0 && !prepare_only) || ent_end == ent_begin) return HOLE_OK;
   if (side == HOLE_SIDE_BOTH) Q *= 2;    // output rows: [tail ranks of all queries | head ranks]
@@ -1203,7 +1272,30 @@ static int rank_impl(hole_ctx* c, const float* table, int64_t ent_begin, int64_t
     return HOLE_OK;
   }
   w->last_qpad = Qpad;
-  {
+  if (c->score_mode == HOLE_SCORE_CCORR_TANH) {
+    // archived score variant: another query vector, the same contraction (see the kernel's comment)
+    const int nv = (c->row_stride / 2 + 31) / 32;
+    const int warps = std::max(1, std::min(8, (200 * 1024) / (6 * c->H * (int)sizeof(float))));
+    const unsigned grid = (unsigned)((Qpad + warps - 1) / warps);
+    const size_t smem = (size_t)warps * 6 * c->H * sizeof(float);
+#define HOLE_PQC_LAUNCH(N)                                                                                           \
+    do {                                                                                                             \
+      HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_rank_pack_query_ccorr_kernel<N>,                                       \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));                 \
+      hole_rank_pack_query_ccorr_kernel<N><<<grid, 32 * warps, smem, st>>>(query_table, c->row_stride, c->H, queries, \
+                                                                           (int)Q, Qpad, side, ent_begin, K, parts,  \
+                                                                           w->qp, w->true_idx);                      \
+    } while (0)
+    if (nv <= 1) HOLE_PQC_LAUNCH(1);
+    else if (nv <= 2) HOLE_PQC_LAUNCH(2);
+    else if (nv <= 3) HOLE_PQC_LAUNCH(3);
+    else if (nv <= 4) HOLE_PQC_LAUNCH(4);
+    else if (nv <= 6) HOLE_PQC_LAUNCH(6);
+    else if (nv <= 8) HOLE_PQC_LAUNCH(8);
+    else HOLE_PQC_LAUNCH(12);
+#undef HOLE_PQC_LAUNCH
+    HOLE_LAUNCHED();
+  } else {
     const unsigned pq_grid = (unsigned)((Qpad + 7) / 8);
     const size_t pq_smem = (size_t)8 * Kall * 2;
     const int pq_iters = (c->row_stride / 2 + 127) / 128;

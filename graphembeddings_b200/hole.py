@@ -467,6 +467,10 @@ def infer_triples(flags=None, log=print):
         raise ValueError(f"checkpoint has embeddings {E.shape}, expected "
                          f"{(data.entity_count, flags.embedding_dim)}")
     eng = HoleEngine(data.entity_count, flags.embedding_dim).set_embeddings(E)
+    if getattr(flags, 'score_variant', 'complex') != 'complex':
+        if getattr(flags, "infer_gate", False):
+            raise SystemExit("--infer_gate is defined on sigma(score): not available with --score_variant ccorr_tanh")
+        eng.set_score_mode(flags.score_variant)      # ranks on the raw score s (tanh is monotone)
     threshold = flags.infer_threshold if getattr(flags, "infer_gate", False) else None
     precision = HOLE_RANK_BF16 if getattr(flags, "rank_precision", "bf16x3") == "bf16" else HOLE_RANK_BF16X3
     raw, filt = eval_link_prediction(eng, data.test, data.known, data.relation_count, data.entity_count,
@@ -512,7 +516,7 @@ def build_parser():
     parser.add_argument('--score_variant', choices=['complex', 'ccorr_tanh'], default='complex',
                         help="Score function: 'complex' = holE.py:191-198 (default); 'ccorr_tanh' = the archived "
                              "variant of the holE-20170724 run (tanh of the r-weighted circular correlation, "
-                             "trained there with --margin 1.0); training and validation only.")
+                             "trained there with --margin 1.0); no --log_loss branch.")
     parser.add_argument('--seed', type=int, default=0)
     parser.add_argument('--max_steps', type=int, default=None, help='Stop after this many steps (testing).')
     return parser
@@ -524,8 +528,6 @@ def main(argv=None):
     if FLAGS.save_embeddings:
         raise SystemExit("--save_embeddings (holE.py:501-527, a py2-only debug dump) is out of scope")
     if FLAGS.infer:
-        if FLAGS.score_variant != 'complex':
-            raise SystemExit("--infer ranks with the live score function only (--score_variant complex)")
         infer_triples(FLAGS)
     else:
         training_data = init_data(FLAGS)

@@ -80,8 +80,10 @@ HOLE_API int hole_ctx_set_relations(hole_ctx* ctx, int64_t n_relations);
  * directory holE-20170724 (graph.pbtxt:6221-6521): tanh(sum_k Re(m_k) + Im(m_k)),
  * m = r * ifft(conj(fft(h)) * fft(t)), with the loss max(tanh(s+) - tanh(s-) + margin, 0)
  * (graph.pbtxt:15874-15988; margin 1.0 in that run).  In that mode hole_score returns tanh(s) and
- * hole_train_step / hole_train_steps[_host] run the direct-correlation kernel; the log-loss
- * branch, the delta-table step, the row-sharded step and hole_rank* return HOLE_ERR_UNSUPPORTED. */
+ * hole_train_step / hole_train_steps[_host] run the direct-correlation kernel; hole_rank* rank on the
+ * raw score s (tanh is monotone; s is linear in the candidate entity, so the same tensor-core
+ * contraction runs on another query vector); the log-loss branch, the delta-table step and the
+ * row-sharded step return HOLE_ERR_UNSUPPORTED. */
 #define HOLE_SCORE_COMPLEX 0
 #define HOLE_SCORE_CCORR_TANH 1
 HOLE_API int hole_ctx_set_score_mode(hole_ctx* ctx, int mode);

@@ -130,3 +130,19 @@ def sgd_step(E, pos, neg_ent, side, margin, lr, dtype=np.float32):
     if Ew is not E:
         E[...] = Ew
     return loss, vp, vn
+
+
+def all_scores(E, queries, side, cand_ids, dtype=np.float64):
+    """Raw scores s of every candidate for every query, [Q, C]: side "tail" scores (h, c, r), "head" (c, t, r).
+    Straight from the definition (raw_score on the expanded triples), not through the query-vector form the
+    device kernel uses."""
+    queries = np.asarray(queries)
+    cand_ids = np.asarray(cand_ids)
+    out = np.empty((len(queries), len(cand_ids)), dtype=dtype)
+    for i, (h, t, r) in enumerate(queries.tolist()):
+        tri = np.empty((len(cand_ids), 3), dtype=np.int64)
+        tri[:, 0] = cand_ids if side == "head" else h
+        tri[:, 1] = cand_ids if side == "tail" else t
+        tri[:, 2] = r
+        out[i] = raw_score(E, tri, dtype)
+    return out

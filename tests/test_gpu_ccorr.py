@@ -91,12 +91,45 @@ def test_ccorr_train_steps_device_loop_matches_single_steps(eng_mod):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("dim", [64, 150, 256])
+@pytest.mark.parametrize("side", [0, 1])
+def test_ccorr_ranking_matches_fp64_oracle(eng_mod, dim, side):
+    """All-candidate ranking in the archived mode (the score is linear in the candidate entity, so the same
+    tensor-core contraction runs on another query vector): split-bf16 ranks agree with the fp64 oracle's
+    scores, computed from the definition, except for candidates within 3e-5 of the threshold."""
+    from oracle import hole_ccorr as oc
+    n_rel, n, Q = 6, 1500, 160
+    E = _table(n, dim, 300 + dim + side)
+    rng = np.random.default_rng(dim + side)
+    q = _triples(rng, n_rel, n, Q)
+    e = eng_mod.HoleEngine(n, dim).set_embeddings(E).set_score_mode("ccorr_tanh")
+    name, col = ("tail", 1) if side == 0 else ("head", 0)
+    S = oc.all_scores(E.astype(np.float64), q, name, np.arange(n_rel, n), np.float64)
+    tj = q[:, col].astype(np.int64) - n_rel
+    thr = S[np.arange(Q), tj]
+    raw, filt, ts = e.rank(q, side, n_rel, n, precision=eng_mod.HOLE_RANK_BF16X3)
+    raw, ts = raw.cpu().numpy(), ts.cpu().numpy()
+    eps = 3e-5
+    assert np.abs(ts - thr).max() < eps
+    lo = (S < thr[:, None] - eps).sum(1)
+    hi = (S <= thr[:, None] + eps).sum(1) - 1
+    assert np.all(raw >= lo) and np.all(raw <= hi)
+    exact = (S < thr[:, None]).sum(1)
+    assert np.all((raw == exact) | (hi > lo))
+    assert np.mean(raw == exact) > 0.9
+    # plain bf16 operands: scores within the bf16 bound
+    raw_bf, _, ts_bf = e.rank(q, side, n_rel, n)
+    assert np.abs(ts_bf.cpu().numpy() - thr).max() < 4e-3
+    e.close()
+
+
 def test_ccorr_mode_refuses_what_it_does_not_build(eng_mod):
-    n, dim = 64, 16
-    e = eng_mod.HoleEngine(n, dim).set_embeddings(_table(n, dim, 1)).set_score_mode("ccorr_tanh")
-    q = np.array([[5, 6, 1]], dtype=np.int32)
+    from graphembeddings_b200 import data as D
+    kg = D.synthetic_kg(4, 60, 64, 3, 16, seed=1)
+    off, ids = D.build_type_csr(kg.type_of)
+    e = eng_mod.HoleEngine(kg.n_rows, kg.dim).set_embeddings(kg.E).set_types(kg.type_of, off, ids).set_score_mode("ccorr_tanh")
     with pytest.raises(eng_mod.HoleError):
-        e.rank(q, 0, 4, n)
+        e.train_step_logloss(kg.triples, 1, 0, 0.1)
     e.set_score_mode("complex")
-    e.rank(q, 0, 4, n)
+    e.train_step_logloss(kg.triples, 1, 0, 0.1)
     e.close()

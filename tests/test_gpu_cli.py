@@ -219,6 +219,12 @@ def test_archived_ccorr_tanh_variant_trains_through_the_driver(tmp_path):
     assert min(v) < v[0] - 0.02                                      # the pocket checkpoint keeps the best one
     E1 = tf_bundle.load_bundle(os.path.join(out, "model.ckpt"))["embeddings"]
     assert np.isfinite(E1).all()
-    with pytest.raises(SystemExit):
-        hole.main(["--data_dir", str(d), "--output_dir", out, "--embedding_dim", "64", "--infer",
-                   "--score_variant", "ccorr_tanh"])
+    # --infer in the archived mode: the same all-entity filtered ranking on the raw score
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        flags = hole.build_parser().parse_args(args + ["--infer"])
+        m = hole.infer_triples(flags, log=lambda *a: None)
+    finally:
+        os.chdir(cwd)
+    assert 0 < m["filtered_mrr"] <= 1 and m["raw_mean_pos"] >= m["filtered_mean_pos"]
