@@ -16,13 +16,10 @@ PKG = os.path.join(ROOT, "graphembeddings_b200")
 PREV = os.path.join(PKG, "libhole_b200_prev.so")   # the previous commit's sources built beside the current library
 VARIANTS = [  # (name, env); earlier rounds of variants: profiles/r02_train_ab_README.md
     ("default", {}),
-    ("prev", {"HOLE_B200_LIB": PREV}),
-    ("default (again)", {}),
-    ("prev (again)", {"HOLE_B200_LIB": PREV}),
-    ("prev B=512", {"HOLE_B200_LIB": PREV, "AB_BATCH": "512"}),
     ("trained-scale table (clips fire)", {"AB_TRAINED": "1"}),
     ("B=512", {"AB_BATCH": "512"}),
     ("B=8192", {"AB_BATCH": "8192"}),
+    ("prev", {"HOLE_B200_LIB": PREV}),
 ]
 
 
