@@ -589,6 +589,162 @@ hole_plan_segments_kernel(const uint32_t* __restrict__ skey, const uint32_t* __r
 }
 
 // ---------------------------------------------------------------------------------------
+// The row sort + segments of a step in ONE launch, one block per step: the same stable LSD passes as
+// hole_sort_{hist,scatter}_kernel and the same segment rules as hole_plan_segments_kernel (identical
+// output), with the (key, position) pairs in shared memory when the step has at most SS_CAP duplicated
+// uses (a typical step of a large table: ~7 % of the 4B uses) and in the global ping-pong buffers
+// otherwise (correct but slow: the host only takes this path while the steps it has seen were small).
+// Replaces 2 * passes + 1 dependent launches of the plan chain, whose length -- not its work -- is what
+// a training call waits for before its first step.
+// ---------------------------------------------------------------------------------------
+// max over the plan's steps of their duplicated-use count -> mapped host memory (atomicMax: plans only raise it)
+__global__ void hole_plan_dupmax_kernel(const int* __restrict__ mdup, int S, int* __restrict__ out_host) {
+  int m = 0;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) m = max(m, mdup[s]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ int sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < (int)(blockDim.x >> 5); ++q) m = max(m, sm[q]);
+    if (m > *reinterpret_cast<volatile int*>(out_host)) *reinterpret_cast<volatile int*>(out_host) = m;
+    __threadfence_system();
+  }
+}
+
+constexpr int SS_THREADS = 1024;
+constexpr int SS_WARPS = SS_THREADS / 32;
+constexpr int SS_CAP = 11264;                      // 4 arrays x 4 B x SS_CAP + 32 KB of histograms < 227 KB
+constexpr int SS_SMEM = (SS_WARPS * 256 + 4 * SS_CAP) * 4;
+
+__global__ void __launch_bounds__(SS_THREADS)
+hole_plan_sortseg_small_kernel(uint32_t* ck, uint32_t* cv, uint32_t* ak, uint32_t* av, uint32_t* skey_out,
+                               uint32_t* spos_out, uint32_t* __restrict__ gslot,
+                               uint4* __restrict__ heads, int* __restrict__ nheads, int Mcap,
+                               const int* __restrict__ mdev, int heads_cap, int passes) {
+  extern __shared__ uint32_t ss_smem[];
+  __shared__ uint32_t s_wsum[SS_WARPS];
+  __shared__ int s_nh;
+  constexpr int C = HOLE_TREE_C;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int step = blockIdx.x;
+  const int n = mdev[step];
+  const size_t base = (size_t)step * Mcap;
+  if (tid == 0) s_nh = 0;
+  if (n == 0) { if (tid == 0) nheads[step] = 0; return; }
+  uint32_t (*wh)[256] = reinterpret_cast<uint32_t (*)[256]>(ss_smem);
+  const bool small = n <= SS_CAP;
+  uint32_t *kin, *vin, *kout, *vout;
+  if (small) {
+    kin = ss_smem + SS_WARPS * 256; vin = kin + SS_CAP; kout = vin + SS_CAP; vout = kout + SS_CAP;
+    for (int j = tid; j < n; j += SS_THREADS) { kin[j] = ck[base + j]; vin[j] = cv[base + j]; }
+  } else {
+    kin = ck + base; vin = cv + base; kout = ak + base; vout = av + base;
+  }
+  const int L = ((n + SS_WARPS - 1) / SS_WARPS + 31) & ~31;      // entries per warp
+  const int lo = min(n, w * L), hi = min(n, lo + L);
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = 8 * pass;
+    for (int i = tid; i < SS_WARPS * 256; i += SS_THREADS) (&wh[0][0])[i] = 0;
+    __syncthreads();                                             // (also: the previous pass's scatter is complete)
+    for (int j0 = lo; j0 < hi; j0 += 32) {                       // (plain loads: this kernel wrote kin itself)
+      const int j = j0 + lane;
+      const bool ok = j < hi;
+      const uint32_t d = ok ? ((kin[j] >> shift) & 255u) : 256u + lane;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      if (ok && lane == __ffs(peers) - 1) wh[w][d] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    {   // exclusive scan in (digit-major, warp-minor) order: thread t takes digit t/4, warps 8*(t%4) .. +8
+      const int d = tid >> 2, w0 = (tid & 3) * 8;
+      uint32_t cnt[8], tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { cnt[q] = wh[w0 + q][d]; tot += cnt[q]; }
+      uint32_t inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+      }
+      if (lane == 31) s_wsum[w] = inc;
+      __syncthreads();
+      uint32_t run = inc - tot;
+      for (int q = 0; q < w; ++q) run += s_wsum[q];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { wh[w0 + q][d] = run; run += cnt[q]; }
+    }
+    __syncthreads();
+    uint32_t* myh = wh[w];
+    for (int j0 = lo; j0 < hi; j0 += 32) {                       // stable scatter of the warp's slice
+      const int j = j0 + lane;
+      const bool ok = j < hi;
+      const uint32_t key = ok ? kin[j] : 0u, val = ok ? vin[j] : 0u;
+      const uint32_t d = ok ? ((key >> shift) & 255u) : 256u + lane;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      if (ok) {
+        const uint32_t dst = myh[d] + rank;
+        kout[dst] = key;
+        vout[dst] = val;
+      }
+      __syncwarp();
+      if (ok && lane == __ffs(peers) - 1) myh[d] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    uint32_t* t = kin; kin = kout; kout = t;
+    t = vin; vin = vout; vout = t;
+  }
+  // kin / vin: the step's duplicated uses sorted by (row, position).  Consumers read them from skey_out / spos_out.
+  uint32_t* so = skey_out + base;
+  uint32_t* po = spos_out + base;
+  if (kin != so)
+    for (int j = tid; j < n; j += SS_THREADS) { so[j] = kin[j]; po[j] = vin[j]; }
+  // segments (hole_plan_segments_kernel's rules)
+  const uint32_t* k = kin;
+  for (int j = tid; j < n; j += SS_THREADS) {
+    const uint32_t key = k[j];
+    const bool head = (j == 0) || (k[j - 1] != key);
+    const bool last = (j == n - 1) || (k[j + 1] != key);
+    gslot[base + vin[j]] = (uint32_t)j;
+    if (head && last) continue;
+    int sg = j;
+    if (!head) {
+      if (j < 2 || k[j - 2] != key) sg = j - 1;
+      else if (j < 3 || k[j - 3] != key) sg = j - 2;
+      else {
+        int a = 0, b = j - 3;
+        while (a < b) {
+          const int mid = (a + b) >> 1;
+          if (k[mid] < key) a = mid + 1; else b = mid;
+        }
+        sg = a;
+      }
+    }
+    if ((j - sg) % C != 0) continue;
+    int e = j + 1;
+    if (!last) {
+      if (j + 2 >= n || k[j + 2] != key) e = j + 2;
+      else if (j + 3 >= n || k[j + 3] != key) e = j + 3;
+      else {
+        int a = j + 4, b = n;
+        while (a < b) {
+          const int mid = (a + b) >> 1;
+          if (k[mid] <= key) a = mid + 1; else b = mid;
+        }
+        e = a;
+      }
+    }
+    const int slot = atomicAdd(&s_nh, 1);
+    heads[(size_t)step * heads_cap + slot] = make_uint4((uint32_t)j, (uint32_t)sg, (uint32_t)(e - sg), key);
+  }
+  __syncthreads();
+  if (tid == 0) nheads[step] = s_nh;
+}
+
+// ---------------------------------------------------------------------------------------
 // forward only: sigma(score)  (evaluate_triples, holE.py:179-202)
 // ---------------------------------------------------------------------------------------
 template <int GS, int V>
@@ -1478,6 +1634,10 @@ static int ctx_create_streams(hole_ctx* c) {
     HOLE_CUDA_TRY(cudaStreamCreateWithPriority(&c->plan_stream, cudaStreamNonBlocking, hi));
   }
   HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
+  HOLE_CUDA_TRY(cudaHostAlloc((void**)&c->dup_max_host, sizeof(int), cudaHostAllocMapped));
+  *c->dup_max_host = -1;
+  HOLE_CUDA_TRY(cudaHostGetDevicePointer((void**)&c->dup_max_host_dev, c->dup_max_host, 0));
+  HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_plan_sortseg_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM));
   for (int k = 0; k < 2; ++k) {
     HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming));
     HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->plan[k].ready, cudaEventDisableTiming));
@@ -1533,6 +1693,7 @@ extern "C" int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int d
   if (const char* e = getenv("HOLE_K1_BLOCK")) c->k1_block = atoi(e);
   if (c->k1_block != 128 && c->k1_block != 192 && c->k1_block != 256) c->k1_block = 256;
   if (const char* e = getenv("HOLE_HOST_FIRST")) c->host_first = atoi(e);
+  if (const char* e = getenv("HOLE_SORT_SMALL")) c->sort_small = atoi(e);   // 0 = always the radix chain, 2 = always one launch
   if (const char* e = getenv("HOLE_PLAN_RAMP")) {     // "first,factor"; "0" disables the ramp
     int a = 0, b = 4;
     if (sscanf(e, "%d,%d", &a, &b) >= 1) { c->ramp_first = a; c->ramp_factor = b < 2 ? 2 : b; }
@@ -1595,6 +1756,7 @@ extern "C" int hole_ctx_destroy(hole_ctx* c) {
   if (c->ev_entry) cudaEventDestroy(c->ev_entry);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->plan_stream) cudaStreamDestroy(c->plan_stream);
+  if (c->dup_max_host) cudaFreeHost(c->dup_max_host);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   delete c;
   return HOLE_OK;
@@ -1865,16 +2027,38 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
   hole_plan_compact_kernel<<<dgrid, DP_THREADS, 0, ps>>>(pl.keysA, pl.dup, M, W, pl.blkcnt, pl.keysB, pl.valsA);
   HOLE_LAUNCHED();
   // 4. sort them by row (stable: equal rows stay in position order), 5. segments
-  rc = radix_sort(pl.ghist, pl.keysB, pl.keysC, pl.valsA, pl.valsB, nullptr, S, M, c->row_passes, ps,
-                  &pl.skey, &pl.spos, pl.done, /*v_init=*/true, pl.mdup);
-  if (rc) return rc;
   pl.heads_cap = M / 2 + 1;
-  HOLE_CUDA_TRY(cudaMemsetAsync(pl.nheads, 0, (size_t)S * 4, ps));
-  dim3 sgrid((unsigned)std::min<int64_t>((M + 255) / 256, 1024), (unsigned)S);
-  hole_plan_segments_kernel<<<sgrid, 256, 0, ps>>>(pl.skey, pl.spos, pl.gslot, pl.heads, pl.nheads, M, pl.mdup,
-                                                  pl.heads_cap);
-  HOLE_LAUNCHED();
+  // How many duplicated uses the steps of the previous plans of this batch size had (read back without
+  // waiting: a plan that has not reported yet counts as "unknown").  While they fit the one-launch kernel's
+  // shared memory, it replaces the 2 * passes + 1 launches below; it stays correct for a larger step.
+  if (c->dup_seen_B != B) { c->dup_seen_B = B; c->dup_seen_max = -1; *c->dup_max_host = -1; }
+  {
+    const int reported = *reinterpret_cast<volatile int*>(c->dup_max_host);
+    c->dup_seen_max = std::max(c->dup_seen_max, reported);
+  }
+  const bool one_launch = c->sort_small == 2 || (c->sort_small == 1 && c->dup_seen_max >= 0 && c->dup_seen_max <= SS_CAP);
+  if (one_launch) {
+    const bool odd = (c->row_passes & 1) != 0;
+    pl.skey = odd ? pl.keysC : pl.keysB;
+    pl.spos = odd ? pl.valsB : pl.valsA;
+    hole_plan_sortseg_small_kernel<<<(unsigned)S, SS_THREADS, SS_SMEM, ps>>>(
+        pl.keysB, pl.valsA, pl.keysC, pl.valsB, pl.skey, pl.spos, pl.gslot, pl.heads, pl.nheads, M, pl.mdup,
+        pl.heads_cap, c->row_passes);
+    HOLE_LAUNCHED();
+  } else {
+    rc = radix_sort(pl.ghist, pl.keysB, pl.keysC, pl.valsA, pl.valsB, nullptr, S, M, c->row_passes, ps,
+                    &pl.skey, &pl.spos, pl.done, /*v_init=*/true, pl.mdup);
+    if (rc) return rc;
+    HOLE_CUDA_TRY(cudaMemsetAsync(pl.nheads, 0, (size_t)S * 4, ps));
+    dim3 sgrid((unsigned)std::min<int64_t>((M + 255) / 256, 1024), (unsigned)S);
+    hole_plan_segments_kernel<<<sgrid, 256, 0, ps>>>(pl.skey, pl.spos, pl.gslot, pl.heads, pl.nheads, M, pl.mdup,
+                                                    pl.heads_cap);
+    HOLE_LAUNCHED();
+  }
   HOLE_CUDA_TRY(cudaEventRecord(pl.ready, ps));
+  // (off the consumer's path) report the largest step of this plan to the host
+  hole_plan_dupmax_kernel<<<1, 256, 0, ps>>>(pl.mdup, (int)S, c->dup_max_host_dev);
+  HOLE_LAUNCHED();
   return HOLE_OK;
 }
 

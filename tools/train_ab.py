@@ -19,7 +19,9 @@ VARIANTS = [  # (name, env); earlier rounds of variants: profiles/r02_train_ab_R
     ("trained-scale table (clips fire)", {"AB_TRAINED": "1"}),
     ("B=512", {"AB_BATCH": "512"}),
     ("B=8192", {"AB_BATCH": "8192"}),
-    ("prev", {"HOLE_B200_LIB": PREV}),
+    ("radix chain (HOLE_SORT_SMALL=0)", {"HOLE_SORT_SMALL": "0"}),
+    ("B=512 radix chain", {"HOLE_SORT_SMALL": "0", "AB_BATCH": "512"}),
+    ("default (again)", {}),
 ]
 
 
