@@ -264,9 +264,13 @@ __device__ __forceinline__ bool plan_is_dup(const uint32_t* __restrict__ dp, uin
 }
 
 // gslot[u] = UNIQUE for uses of rows that occur once; blkcnt[s][blk] = duplicated uses in the block's tile
+__device__ __forceinline__ void plan_dupscan(int* __restrict__ c, int nblk, int* __restrict__ mdup_s);
+
 __global__ void __launch_bounds__(DP_THREADS)
 hole_plan_dupflag_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ dup, int M, int W,
-                         uint32_t* __restrict__ gslot, int* __restrict__ blkcnt) {
+                         uint32_t* __restrict__ gslot, int* __restrict__ blkcnt, int* __restrict__ mdup,
+                         unsigned* __restrict__ done) {
+  __shared__ bool s_last;
   const int s = blockIdx.y, nblk = gridDim.x;
   const uint32_t* k = keys + (size_t)s * M;
   const uint32_t* dp = dup + (size_t)s * W;
@@ -282,18 +286,27 @@ hole_plan_dupflag_kernel(const uint32_t* __restrict__ keys, const uint32_t* __re
     }
     cnt += __syncthreads_count(d);
   }
-  if (threadIdx.x == 0) blkcnt[(size_t)s * (nblk + 1) + blockIdx.x] = cnt;
+  if (threadIdx.x == 0) {
+    __stcg(&blkcnt[(size_t)s * (nblk + 1) + blockIdx.x], cnt);
+    __threadfence();
+    s_last = atomicAdd(done + s, 1u) == (unsigned)nblk - 1u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // the last block of the step to finish turns the step's block counts into offsets (it used to be a launch
+  // of its own: the plan chain is paid per launch)
+  if (threadIdx.x == 0) done[s] = 0;
+  __threadfence();
+  plan_dupscan(blkcnt + (size_t)s * (nblk + 1), nblk, mdup + s);
 }
 
 // per step: block counts -> exclusive offsets; the total goes to blkcnt[s][nblk] and mdup[s]
-__global__ void __launch_bounds__(256)
-hole_plan_dupscan_kernel(int* __restrict__ blkcnt, int nblk, int* __restrict__ mdup) {
+__device__ __forceinline__ void plan_dupscan(int* __restrict__ c, int nblk, int* __restrict__ mdup_s) {
   __shared__ int wsum[8];
-  int* c = blkcnt + (size_t)blockIdx.x * (nblk + 1);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int per = (nblk + 255) / 256;
   int tot = 0;
-  for (int q = tid * per; q < min(nblk, (tid + 1) * per); ++q) tot += c[q];
+  for (int q = tid * per; q < min(nblk, (tid + 1) * per); ++q) tot += __ldcg(c + q);
   int inc = tot;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -305,11 +318,11 @@ hole_plan_dupscan_kernel(int* __restrict__ blkcnt, int nblk, int* __restrict__ m
   int base = inc - tot;
   for (int q = 0; q < w; ++q) base += wsum[q];
   for (int q = tid * per; q < min(nblk, (tid + 1) * per); ++q) {
-    const int v = c[q];
+    const int v = __ldcg(c + q);
     c[q] = base;
     base += v;
   }
-  if (tid == 255) { c[nblk] = base; mdup[blockIdx.x] = base; }
+  if (tid == 255) { c[nblk] = base; *mdup_s = base; }
 }
 
 // (key, position) of every duplicated use, in position order
@@ -597,6 +610,89 @@ hole_plan_segments_kernel(const uint32_t* __restrict__ skey, const uint32_t* __r
 // Replaces 2 * passes + 1 dependent launches of the plan chain, whose length -- not its work -- is what
 // a training call waits for before its first step.
 // ---------------------------------------------------------------------------------------
+// The per-step "group the triples by relation" sort in ONE launch (it used to be hole_rel_keys_kernel + one
+// histogram / scatter pair per pass): one block per step, the B relation ids in shared memory, stable LSD
+// passes as in hole_plan_sortseg_small_kernel.  One pass (relation ids < 256) scatters the triple indices
+// straight into perm; a second pass goes through a 16-bit index array.  The host takes this kernel when the
+// step fits (plan_relsort_smem), else the radix chain.
+constexpr int RS_THREADS = 1024;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_SMEM_MAX = 227 * 1024 - 1024;   // dynamic + the kernel's static shared memory <= 227 KB
+
+static size_t plan_relsort_smem(int64_t B, int passes) {      // 0: does not fit
+  if (passes < 1 || passes > 2 || B > 65536) return 0;
+  const size_t need = (size_t)RS_WARPS * 256 * 4 + (size_t)B * 4 + (passes == 2 ? (size_t)B * 2 : 0);
+  return need <= (size_t)RS_SMEM_MAX ? need : 0;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+hole_plan_relsort_kernel(const int32_t* __restrict__ triples, int B, int64_t tstride, int passes,
+                         int32_t* __restrict__ perm) {
+  extern __shared__ uint32_t rs_smem[];
+  __shared__ uint32_t s_wsum[RS_WARPS];
+  uint32_t (*wh)[256] = reinterpret_cast<uint32_t (*)[256]>(rs_smem);
+  uint32_t* keys = rs_smem + RS_WARPS * 256;
+  uint16_t* p0 = reinterpret_cast<uint16_t*>(keys + B);           // order after the first of two passes
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int32_t* tr = triples + (size_t)blockIdx.x * tstride;
+  int32_t* pm = perm + (size_t)blockIdx.x * B;
+  for (int j = tid; j < B; j += RS_THREADS) keys[j] = (uint32_t)tr[3 * (size_t)j + 2];
+  const int L = ((B + RS_WARPS - 1) / RS_WARPS + 31) & ~31;       // entries per warp
+  const int lo = min(B, w * L), hi = min(B, lo + L);
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = 8 * pass;
+    const bool first = pass == 0, last = pass == passes - 1;
+    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    for (int j0 = lo; j0 < hi; j0 += 32) {
+      const int j = j0 + lane;
+      const bool ok = j < hi;
+      const uint32_t d = ok ? ((keys[first ? j : (int)p0[j]] >> shift) & 255u) : 256u + lane;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      if (ok && lane == __ffs(peers) - 1) wh[w][d] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    {   // exclusive scan in (digit-major, warp-minor) order: thread t takes digit t/4, warps 8*(t%4) .. +8
+      const int d = tid >> 2, w0 = (tid & 3) * 8;
+      uint32_t cnt[8], tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { cnt[q] = wh[w0 + q][d]; tot += cnt[q]; }
+      uint32_t inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+      }
+      if (lane == 31) s_wsum[w] = inc;
+      __syncthreads();
+      uint32_t run = inc - tot;
+      for (int q = 0; q < w; ++q) run += s_wsum[q];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { wh[w0 + q][d] = run; run += cnt[q]; }
+    }
+    __syncthreads();
+    uint32_t* myh = wh[w];
+    // two passes: the second reads p0 in order while it ... writes perm (global), so p0 is not overwritten
+    for (int j0 = lo; j0 < hi; j0 += 32) {
+      const int j = j0 + lane;
+      const bool ok = j < hi;
+      const int idx = ok ? (first ? j : (int)p0[j]) : 0;
+      const uint32_t d = ok ? ((keys[idx] >> shift) & 255u) : 256u + lane;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      if (ok) {
+        const uint32_t dst = myh[d] + rank;
+        if (last) pm[dst] = idx; else p0[dst] = (uint16_t)idx;
+      }
+      __syncwarp();
+      if (ok && lane == __ffs(peers) - 1) myh[d] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+}
+
 // max over the plan's steps of their duplicated-use count -> mapped host memory (atomicMax: plans only raise it)
 __global__ void hole_plan_dupmax_kernel(const int* __restrict__ mdup, int S, int* __restrict__ out_host) {
   int m = 0;
@@ -1638,6 +1734,7 @@ static int ctx_create_streams(hole_ctx* c) {
   *c->dup_max_host = -1;
   HOLE_CUDA_TRY(cudaHostGetDevicePointer((void**)&c->dup_max_host_dev, c->dup_max_host, 0));
   HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_plan_sortseg_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM));
+  HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_plan_relsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_MAX));
   for (int k = 0; k < 2; ++k) {
     HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming));
     HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->plan[k].ready, cudaEventDisableTiming));
@@ -1799,6 +1896,7 @@ int hole_ws_reserve(hole_ctx* c, int64_t B, int64_t S) {
       const size_t W = (size_t)(c->n_rows + 31) / 32;
       p.bitmap_words = (size_t)S * W;
       WS_ALLOC(p.seen, 2 * p.bitmap_words * 4);
+      HOLE_CUDA_TRY(cudaMemset(p.seen, 0, 2 * p.bitmap_words * 4));
       p.dup = p.seen + p.bitmap_words;
       WS_ALLOC(p.done, (size_t)S * sizeof(unsigned));
       HOLE_CUDA_TRY(cudaMemset(p.done, 0, (size_t)S * sizeof(unsigned)));
@@ -2004,25 +2102,29 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
   const int M = (int)(4 * B);
   dim3 grid((unsigned)std::min<int64_t>((B + 255) / 256, 4096), (unsigned)S);
   // 1. perm: triples grouped by relation (stable)
-  hole_rel_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, tstride, pl.keysA);
-  HOLE_LAUNCHED();
-  uint32_t *ko, *vo;
-  int rc = radix_sort(pl.ghist, pl.keysA, pl.keysB, pl.valsA, pl.valsB, reinterpret_cast<uint32_t*>(pl.perm),
-                      S, (int)B, c->rel_passes, ps, &ko, &vo, pl.done);
-  if (rc) return rc;
+  int rc = HOLE_OK;
+  if (const size_t rs_smem = c->sort_small ? plan_relsort_smem(B, c->rel_passes) : 0) {
+    hole_plan_relsort_kernel<<<(unsigned)S, RS_THREADS, rs_smem, ps>>>(triples_dev, (int)B, tstride, c->rel_passes, pl.perm);
+    HOLE_LAUNCHED();
+  } else {
+    hole_rel_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, tstride, pl.keysA);
+    HOLE_LAUNCHED();
+    uint32_t *ko, *vo;
+    rc = radix_sort(pl.ghist, pl.keysA, pl.keysB, pl.valsA, pl.valsB, reinterpret_cast<uint32_t*>(pl.perm),
+                    S, (int)B, c->rel_passes, ps, &ko, &vo, pl.done);
+    if (rc) return rc;
+  }
   // 2. corruption + the 4B row keys of every step; rows used more than once are marked in the bitmaps
   pl.T = triples_per_group(c, B);
   const int W = (int)((c->n_rows + 31) / 32);
-  HOLE_CUDA_TRY(cudaMemsetAsync(pl.seen, 0, (size_t)2 * pl.bitmap_words * 4, ps));   // seen | dup (one allocation)
+  // (the bitmaps seen | dup are clean here: cleared at allocation and after every plan, off the chain)
   hole_plan_keys_kernel<<<grid, 256, 0, ps>>>(triples_dev, B, tstride, pl.T, pl.perm, type_of, csr_off, csr_ids,
                                               seed, first_step, neg_in, pl.neg, pl.keysA, pl.seen, pl.dup, W);
   HOLE_LAUNCHED();
   // 3. the uses of duplicated rows, compacted in position order (the others are marked UNIQUE)
   const int nblk = (M + DP_TILE - 1) / DP_TILE;
   dim3 dgrid((unsigned)nblk, (unsigned)S);
-  hole_plan_dupflag_kernel<<<dgrid, DP_THREADS, 0, ps>>>(pl.keysA, pl.dup, M, W, pl.gslot, pl.blkcnt);
-  HOLE_LAUNCHED();
-  hole_plan_dupscan_kernel<<<(unsigned)S, 256, 0, ps>>>(pl.blkcnt, nblk, pl.mdup);
+  hole_plan_dupflag_kernel<<<dgrid, DP_THREADS, 0, ps>>>(pl.keysA, pl.dup, M, W, pl.gslot, pl.blkcnt, pl.mdup, pl.done);
   HOLE_LAUNCHED();
   hole_plan_compact_kernel<<<dgrid, DP_THREADS, 0, ps>>>(pl.keysA, pl.dup, M, W, pl.blkcnt, pl.keysB, pl.valsA);
   HOLE_LAUNCHED();
@@ -2056,7 +2158,8 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
     HOLE_LAUNCHED();
   }
   HOLE_CUDA_TRY(cudaEventRecord(pl.ready, ps));
-  // (off the consumer's path) report the largest step of this plan to the host
+  // (off the consumer's path) clean bitmaps for the next plan in this slot; report the largest step to the host
+  HOLE_CUDA_TRY(cudaMemsetAsync(pl.seen, 0, (size_t)2 * pl.bitmap_words * 4, ps));   // seen | dup (one allocation)
   hole_plan_dupmax_kernel<<<1, 256, 0, ps>>>(pl.mdup, (int)S, c->dup_max_host_dev);
   HOLE_LAUNCHED();
   return HOLE_OK;
