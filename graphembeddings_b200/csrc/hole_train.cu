@@ -372,6 +372,20 @@ constexpr int ST_WARPS = ST_THREADS / 32;
 constexpr int ST_SLICE = 512;                    // entries per warp
 constexpr int ST_TILE = ST_SLICE * ST_WARPS;     // entries per block
 
+// lanes of the warp whose 8-bit digit equals mine (`ok` lanes only): eight ballots.  (match.any is an order of
+// magnitude slower when the 32 digits are all different, and it serialises the warps of an SM: the one-block
+// sort kernels spent ~90 % of their time in it -- profiles/r02b_train_full_summary.csv.)
+__device__ __forceinline__ uint32_t warp_match_digit(uint32_t d, bool ok) {
+  uint32_t peers = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool bit = (d >> k) & 1u;
+    const uint32_t b = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? b : ~b;
+  }
+  return peers;
+}
+
 // per-warp digit histogram of the warp's slice of the tile (wh = this warp's 256 counters)
 __device__ __forceinline__ void st_warp_hist(const uint32_t* __restrict__ k, int lo, int hi,
                                              int shift, uint32_t* wh, int lane) {
@@ -387,7 +401,7 @@ __device__ __forceinline__ void st_warp_hist(const uint32_t* __restrict__ k, int
       int j = j0 + 32 * u + lane;
       bool ok = j < hi;
       uint32_t d = ok ? ((key[u] >> shift) & 255u) : 256u + lane;   // inactive lanes: unique
-      uint32_t peers = __match_any_sync(0xffffffffu, d);
+      uint32_t peers = warp_match_digit(d, ok);
       if (ok && lane == __ffs(peers) - 1) wh[d] += __popc(peers);
       __syncwarp();
     }
@@ -532,7 +546,7 @@ hole_sort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* _
       int j = j0 + 32 * u + lane;
       bool ok = j < hi;
       uint32_t d = ok ? ((key[u] >> shift) & 255u) : 256u + lane;
-      uint32_t peers = __match_any_sync(0xffffffffu, d);
+      uint32_t peers = warp_match_digit(d, ok);
       uint32_t rank = __popc(peers & ((1u << lane) - 1u));
       if (ok) {
         uint32_t dst = myh[d] + rank;
@@ -648,7 +662,7 @@ hole_plan_relsort_kernel(const int32_t* __restrict__ triples, int B, int64_t tst
       const int j = j0 + lane;
       const bool ok = j < hi;
       const uint32_t d = ok ? ((keys[first ? j : (int)p0[j]] >> shift) & 255u) : 256u + lane;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t peers = warp_match_digit(d, ok);
       if (ok && lane == __ffs(peers) - 1) wh[w][d] += __popc(peers);
       __syncwarp();
     }
@@ -679,7 +693,7 @@ hole_plan_relsort_kernel(const int32_t* __restrict__ triples, int B, int64_t tst
       const bool ok = j < hi;
       const int idx = ok ? (first ? j : (int)p0[j]) : 0;
       const uint32_t d = ok ? ((keys[idx] >> shift) & 255u) : 256u + lane;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t peers = warp_match_digit(d, ok);
       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
       if (ok) {
         const uint32_t dst = myh[d] + rank;
@@ -734,7 +748,20 @@ hole_plan_sortseg_small_kernel(uint32_t* ck, uint32_t* cv, uint32_t* ak, uint32_
   uint32_t *kin, *vin, *kout, *vout;
   if (small) {
     kin = ss_smem + SS_WARPS * 256; vin = kin + SS_CAP; kout = vin + SS_CAP; vout = kout + SS_CAP;
-    for (int j = tid; j < n; j += SS_THREADS) { kin[j] = ck[base + j]; vin[j] = cv[base + j]; }
+    for (int j0 = tid; j0 < n; j0 += 4 * SS_THREADS) {          // (loads first: the pointers may alias)
+      uint32_t a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * SS_THREADS;
+        a[u] = j < n ? __ldcg(ck + base + j) : 0u;
+        b[u] = j < n ? __ldcg(cv + base + j) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * SS_THREADS;
+        if (j < n) { kin[j] = a[u]; vin[j] = b[u]; }
+      }
+    }
   } else {
     kin = ck + base; vin = cv + base; kout = ak + base; vout = av + base;
   }
@@ -748,7 +775,7 @@ hole_plan_sortseg_small_kernel(uint32_t* ck, uint32_t* cv, uint32_t* ak, uint32_
       const int j = j0 + lane;
       const bool ok = j < hi;
       const uint32_t d = ok ? ((kin[j] >> shift) & 255u) : 256u + lane;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t peers = warp_match_digit(d, ok);
       if (ok && lane == __ffs(peers) - 1) wh[w][d] += __popc(peers);
       __syncwarp();
     }
@@ -778,7 +805,7 @@ hole_plan_sortseg_small_kernel(uint32_t* ck, uint32_t* cv, uint32_t* ak, uint32_
       const bool ok = j < hi;
       const uint32_t key = ok ? kin[j] : 0u, val = ok ? vin[j] : 0u;
       const uint32_t d = ok ? ((key >> shift) & 255u) : 256u + lane;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t peers = warp_match_digit(d, ok);
       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
       if (ok) {
         const uint32_t dst = myh[d] + rank;

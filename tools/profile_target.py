@@ -16,7 +16,11 @@ off, ids = D.build_type_csr(kg.type_of)
 e = HoleEngine(kg.n_rows, kg.dim).set_embeddings(kg.E).set_types(kg.type_of, off, ids)
 e.set_relation_count(kg.n_relations)
 tri = torch.from_numpy(kg.triples).cuda()
-sums = e.train_steps(tri, B, 1, 0, 0.2, [0.1] * steps)
+# two calls: the plan of the first one reports how many duplicated uses a step has, the second one then
+# takes the one-launch sort (as every call after the first does in a training run)
+e.train_steps(tri[:2 * B], B, 1, 0, 0.2, [0.1] * 2)
+torch.cuda.synchronize()
+sums = e.train_steps(tri[2 * B:], B, 1, 2, 0.2, [0.1] * (steps - 2))
 torch.cuda.synchronize()
 q = kg.triples[:20000]
 raw, filt, ts = e.rank(q, 0, kg.n_relations, kg.n_rows)

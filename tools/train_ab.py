@@ -16,12 +16,10 @@ PKG = os.path.join(ROOT, "graphembeddings_b200")
 PREV = os.path.join(PKG, "libhole_b200_prev.so")   # the previous commit's sources built beside the current library
 VARIANTS = [  # (name, env); earlier rounds of variants: profiles/r02_train_ab_README.md
     ("default", {}),
-    ("ramp 2,32", {"HOLE_PLAN_RAMP": "2,32"}),
-    ("ramp 3,32", {"HOLE_PLAN_RAMP": "3,32"}),
-    ("ramp 4,16", {"HOLE_PLAN_RAMP": "4,16"}),
-    ("ramp 6,16", {"HOLE_PLAN_RAMP": "6,16"}),
-    ("B=512 ramp 4,16", {"AB_BATCH": "512", "HOLE_PLAN_RAMP": "4,16"}),
-    ("B=512 ramp 8,16", {"AB_BATCH": "512", "HOLE_PLAN_RAMP": "8,16"}),
+    ("trained-scale table (clips fire)", {"AB_TRAINED": "1"}),
+    ("B=512", {"AB_BATCH": "512"}),
+    ("B=8192", {"AB_BATCH": "8192"}),
+    ("radix chain (HOLE_SORT_SMALL=0)", {"HOLE_SORT_SMALL": "0"}),
     ("default (again)", {}),
 ]
 
