@@ -742,7 +742,7 @@ hole_plan_sortseg_small_kernel(uint32_t* ck, uint32_t* cv, uint32_t* ak, uint32_
   const int n = mdev[step];
   const size_t base = (size_t)step * Mcap;
   if (tid == 0) s_nh = 0;
-  if (n == 0) { if (tid == 0) nheads[step] = 0; return; }
+  if (n <= 0) { if (tid == 0 && nheads != nullptr) nheads[step] = 0; return; }   // (n < 0: the load-the-module launch)
   uint32_t (*wh)[256] = reinterpret_cast<uint32_t (*)[256]>(ss_smem);
   const bool small = n <= SS_CAP;
   uint32_t *kin, *vin, *kout, *vout;
@@ -1762,6 +1762,13 @@ static int ctx_create_streams(hole_ctx* c) {
   HOLE_CUDA_TRY(cudaHostGetDevicePointer((void**)&c->dup_max_host_dev, c->dup_max_host, 0));
   HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_plan_sortseg_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM));
   HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_plan_relsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_MAX));
+  // The first launch of a kernel loads its module (tens of microseconds with lazy loading).  The one-launch
+  // sort is first used by a context's SECOND training call (the first one reports the step sizes), so it
+  // is launched once here on nothing: mdev = the mapped word, still -1 -> every thread returns.
+  hole_plan_sortseg_small_kernel<<<1, SS_THREADS, SS_SMEM, c->plan_stream>>>(
+      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, c->dup_max_host_dev, 0, 0);
+  HOLE_LAUNCHED();
+  --g_hole_launches;      // (not a step's launch)
   for (int k = 0; k < 2; ++k) {
     HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming));
     HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->plan[k].ready, cudaEventDisableTiming));
