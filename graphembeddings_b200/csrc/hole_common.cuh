@@ -98,8 +98,8 @@ struct hole_ctx {
   int sort_small = 1;          // plan: one-launch sort + segments while the steps seen so far were small enough
                                //   (HOLE_SORT_SMALL: 0 never, 1 adaptive, 2 always -- tests of its large-step path)
   int64_t dup_seen_B = -1;     //   batch size the observation below belongs to
-  int dup_seen_max = -1;       //   largest duplicated-use count of a step seen so far (-1: none reported yet)
-  int* dup_max_host = nullptr;     //   mapped pinned int the plans report into (host view)
+  int dup_seen_max = -1;       //   largest duplicated-use count of a step in the last plan of either slot (-1: none yet)
+  int* dup_max_host = nullptr;     //   mapped pinned int[2] the plans report into, one word per plan slot (host view)
   int* dup_max_host_dev = nullptr; //   ... its device address
   int row_passes = 1;  // 8-bit radix passes for row keys
   int rel_passes = 1;  // ... for relation ids (hole_ctx_set_relations)

@@ -707,7 +707,7 @@ hole_plan_relsort_kernel(const int32_t* __restrict__ triples, int B, int64_t tst
   }
 }
 
-// max over the plan's steps of their duplicated-use count -> mapped host memory (atomicMax: plans only raise it)
+// max over the plan's steps of their duplicated-use count -> the plan slot's word in mapped host memory
 __global__ void hole_plan_dupmax_kernel(const int* __restrict__ mdup, int S, int* __restrict__ out_host) {
   int m = 0;
   for (int s = threadIdx.x; s < S; s += blockDim.x) m = max(m, mdup[s]);
@@ -718,7 +718,7 @@ __global__ void hole_plan_dupmax_kernel(const int* __restrict__ mdup, int S, int
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int q = 1; q < (int)(blockDim.x >> 5); ++q) m = max(m, sm[q]);
-    if (m > *reinterpret_cast<volatile int*>(out_host)) *reinterpret_cast<volatile int*>(out_host) = m;
+    *reinterpret_cast<volatile int*>(out_host) = m;
     __threadfence_system();
   }
 }
@@ -1757,8 +1757,8 @@ static int ctx_create_streams(hole_ctx* c) {
     HOLE_CUDA_TRY(cudaStreamCreateWithPriority(&c->plan_stream, cudaStreamNonBlocking, hi));
   }
   HOLE_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
-  HOLE_CUDA_TRY(cudaHostAlloc((void**)&c->dup_max_host, sizeof(int), cudaHostAllocMapped));
-  *c->dup_max_host = -1;
+  HOLE_CUDA_TRY(cudaHostAlloc((void**)&c->dup_max_host, 2 * sizeof(int), cudaHostAllocMapped));   // one word per plan slot
+  c->dup_max_host[0] = c->dup_max_host[1] = -1;
   HOLE_CUDA_TRY(cudaHostGetDevicePointer((void**)&c->dup_max_host_dev, c->dup_max_host, 0));
   HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_plan_sortseg_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM));
   HOLE_CUDA_TRY(cudaFuncSetAttribute(hole_plan_relsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_MAX));
@@ -2167,11 +2167,12 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
   // How many duplicated uses the steps of the previous plans of this batch size had (read back without
   // waiting: a plan that has not reported yet counts as "unknown").  While they fit the one-launch kernel's
   // shared memory, it replaces the 2 * passes + 1 launches below; it stays correct for a larger step.
-  if (c->dup_seen_B != B) { c->dup_seen_B = B; c->dup_seen_max = -1; *c->dup_max_host = -1; }
-  {
-    const int reported = *reinterpret_cast<volatile int*>(c->dup_max_host);
-    c->dup_seen_max = std::max(c->dup_seen_max, reported);
-  }
+  // Every plan overwrites the word of its slot, so the decision follows the last plan of each slot (a window of
+  // two chunks), not an all-time maximum: one unusually large step does not switch the context to the chain
+  // for good.
+  volatile int* rep = c->dup_max_host;
+  if (c->dup_seen_B != B) { c->dup_seen_B = B; rep[0] = rep[1] = -1; }
+  c->dup_seen_max = std::max(rep[0], rep[1]);
   const bool one_launch = c->sort_small == 2 || (c->sort_small == 1 && c->dup_seen_max >= 0 && c->dup_seen_max <= SS_CAP);
   if (one_launch) {
     const bool odd = (c->row_passes & 1) != 0;
@@ -2194,7 +2195,7 @@ static int plan_steps(hole_ctx* c, hole_plan& pl, const int32_t* triples_dev, in
   HOLE_CUDA_TRY(cudaEventRecord(pl.ready, ps));
   // (off the consumer's path) clean bitmaps for the next plan in this slot; report the largest step to the host
   HOLE_CUDA_TRY(cudaMemsetAsync(pl.seen, 0, (size_t)2 * pl.bitmap_words * 4, ps));   // seen | dup (one allocation)
-  hole_plan_dupmax_kernel<<<1, 256, 0, ps>>>(pl.mdup, (int)S, c->dup_max_host_dev);
+  hole_plan_dupmax_kernel<<<1, 256, 0, ps>>>(pl.mdup, (int)S, c->dup_max_host_dev + (&pl - c->plan));
   HOLE_LAUNCHED();
   return HOLE_OK;
 }
