@@ -570,3 +570,35 @@ def test_full_size_properties_config1(eng_mod):
     # every changed row was used by a triple or drawn as a corrupt entity (same type => entity row)
     assert not bool(changed[: kg.n_relations][~used[: kg.n_relations]].any())
     assert int(changed.sum()) > 3 * B          # most touched rows really moved
+
+
+@pytest.mark.parametrize("case", ["few_duplicates", "relation_hint", "all_duplicates"])
+def test_update_plan_paths_give_identical_tables(eng_mod, monkeypatch, case):
+    """The one-launch plan kernels (relation sort, row sort + segments: one block per step, shared memory) produce
+    the plan of the multi-launch radix chain: training through either gives the same table bit for bit.
+    HOLE_SORT_SMALL is read when a context is created: 0 = radix chain only, 1 = adaptive (radix chain in the
+    first call, one-launch kernels from the second call on while the steps fit), 2 = one-launch row sort always
+    (all_duplicates: 16,000 duplicated uses per step do not fit its shared memory -- its global-memory path)."""
+    if case == "all_duplicates":
+        kg = D.synthetic_kg(3, 60, 4000 * 4, 2, 64, seed=5, trained_scale=True, zipf_entities=True)
+        B, calls, per_call = 4000, 2, 2
+    else:
+        kg = D.synthetic_kg(9, 50000, 3000 * 6, 4, 150, seed=6, trained_scale=True)
+        B, calls, per_call = 3000, 3, 2
+    outs = []
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("HOLE_SORT_SMALL", mode)
+        e, _, _ = _engine(eng_mod, kg)
+        if case == "relation_hint":
+            e.set_relation_count(kg.n_relations)          # one 8-bit pass in the relation sort
+        sums = []
+        for c in range(calls):
+            k0 = c * per_call
+            tri = kg.triples[k0 * B:(k0 + per_call) * B]
+            sums.append(e.train_steps(tri, B, 3, k0, 0.2, [0.1] * per_call).cpu().numpy())
+        outs.append((np.concatenate(sums), e.embeddings().cpu()))
+        e.close()
+    monkeypatch.delenv("HOLE_SORT_SMALL")
+    for sums, table in outs[1:]:
+        assert np.array_equal(sums, outs[0][0]) and torch.equal(table, outs[0][1])
+    assert not torch.equal(outs[0][1], torch.from_numpy(kg.E))
