@@ -234,7 +234,7 @@ def run_reference(args):
 def timed_train(eng, dev_tri, B, K, W, batch_count, first_step=0):
     """(triples/s, ms per step) of one hole_train_steps call of K steps after W warm-up steps."""
     import torch
-    eng.train_steps(dev_tri[: W * B], B, 1, first_step, MARGIN, lr_schedule(W, first_step, batch_count))
+    warm_up(eng, dev_tri, B, W, first_step, batch_count)
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tri, lrs = dev_tri[W * B:(W + K) * B], lr_schedule(K, first_step + W, batch_count)
@@ -244,6 +244,18 @@ def timed_train(eng, dev_tri, B, K, W, batch_count, first_step=0):
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     return K * B / (ms * 1e-3), ms / K
+
+
+def warm_up(eng, dev_tri, B, W, first_step, batch_count):
+    """The W untimed warm-up steps, issued as TWO calls (W - 2 and 2 steps).  One-time costs of a context do
+    not all fall into its first call: the first call's update plan reports how many duplicated uses a step
+    has, and the second call is the first to run the one-launch sort (tools/first_call_probe.py: ~140 us, once
+    per context; every later call is at the steady state the timed call is meant to measure)."""
+    a = W - 2 if W >= 3 else max(W - 1, 1)
+    for k0, n in ((0, a), (a, W - a)):
+        if n > 0:
+            eng.train_steps(dev_tri[k0 * B:(k0 + n) * B], B, 1, first_step + k0, MARGIN,
+                            lr_schedule(n, first_step + k0, batch_count))
 
 
 def coverage_records(args, eng1, kg1, dev_tri1, peak):
@@ -383,7 +395,7 @@ def run_ours(args):
     sampler.start()
     time.sleep(1.0)
     settle_clocks()
-    eng.train_steps(dev_tri[: W * B], B, 1, 0, MARGIN, lr_schedule(W, 0, batch_count))
+    warm_up(eng, dev_tri, B, W, 0, batch_count)
     barrier()
     eng.reset_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -431,6 +443,8 @@ def run_ours(args):
             "batch": B, "margin": MARGIN, "lr0": LR0, "triples_generated": int(kg.triples.shape[0]),
             "epoch_triples": 30_000_000, "l2": "table (1.2 GB) larger than L2; no flush",
             "clock_settle": "0.25 s of device fills after the clock sampler's start-up pause, before the warm-up steps",
+            "warmup_calls": "the W warm-up steps are two calls (W-2 and 2 steps): the second training call of a context "
+                            "still carries one-time costs (tools/first_call_probe.py)",
             "mean_loss_last_pass": mean_loss, "gen_seconds": round(t_gen, 1)},
         "e2e": {"value": e2e, "unit": "triples/s", "h2d_bytes_per_step": 12 * B,
                 "d2h_bytes_per_step": 4, "call": "hole_train_steps_host (pinned host triples in, loss sums out)"},
