@@ -103,6 +103,7 @@ struct hole_ctx {
   int* dup_max_host_dev = nullptr; //   ... its device address
   int row_passes = 1;  // 8-bit radix passes for row keys
   int rel_passes = 1;  // ... for relation ids (hole_ctx_set_relations)
+  int64_t n_rel_hint = int64_t(1) << 40;   // relation ids are < this (hole_ctx_set_relations); default: no promise
 
   // ---- training workspace (grown on demand; owned by the context)
   int64_t cap_B = 0, cap_S = 0;
