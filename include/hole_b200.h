@@ -72,7 +72,9 @@ HOLE_API int hole_ctx_create(hole_ctx** out, int device, int64_t n_rows, int dim
 HOLE_API int hole_ctx_destroy(hole_ctx* ctx);
 
 /* Optional hint: relation ids are < n_relations (holE.py:52 counts relation_ids.txt), which
- * shortens the per-step "group triples by relation" sort.  Default: n_rows. */
+ * shortens the per-step "group triples by relation" sort (one 8-bit pass below 256 relations, a
+ * per-thread counting sort up to 64).  Default: n_rows.  The grouping is a processing order only:
+ * an id >= n_relations is grouped with other relations (slower), never mis-trained. */
 HOLE_API int hole_ctx_set_relations(hole_ctx* ctx, int64_t n_relations);
 
 /* Score variant.  HOLE_SCORE_COMPLEX (default) is the live holE.py:191-198:
