@@ -176,3 +176,31 @@ def test_rows_in_and_id_checks():
         with pytest.raises(ValueError):
             D.check_triple_ids(np.array(bad), 7, 2)
     D.check_triple_ids(np.zeros((0, 3), np.int32), 7, 2)               # an empty file is fine
+
+
+@pytest.mark.parametrize("W", [1, 2, 3, 5, 8])
+def test_bench_warm_up_issues_exactly_w_steps_in_order(W):
+    """bench.py's warm-up is W steps, issued as two calls (the second training call of a context still carries
+    one-time costs): consecutive triples, consecutive step numbers, nothing skipped or repeated."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    class Rows:                      # stands in for the device triple tensor: records the slices taken
+        def __getitem__(self, sl):
+            return (sl.start, sl.stop)
+
+    class Eng:
+        calls = []
+
+        def train_steps(self, tri, B, seed, first_step, margin, lrs):
+            self.calls.append((tri, first_step, len(lrs)))
+
+    B, e = 64, Eng()
+    bench.warm_up(e, Rows(), B, W, 7, 1000)
+    assert 1 <= len(e.calls) <= 2
+    nxt = 0
+    for (lo, hi), first_step, n in e.calls:
+        assert lo == nxt * B and hi == (nxt + n) * B and first_step == 7 + nxt and n >= 1
+        nxt += n
+    assert nxt == W
