@@ -251,6 +251,8 @@ def warm_up(eng, dev_tri, B, W, first_step, batch_count):
     not all fall into its first call: the first call's update plan reports how many duplicated uses a step
     has, and the second call is the first to run the one-launch sort (tools/first_call_probe.py: ~140 us, once
     per context; every later call is at the steady state the timed call is meant to measure)."""
+    if W <= 0:
+        return
     a = W - 2 if W >= 3 else max(W - 1, 1)
     for k0, n in ((0, a), (a, W - a)):
         if n > 0:
